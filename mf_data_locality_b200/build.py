@@ -1,0 +1,72 @@
+"""In-tree build of the CUDA C-ABI library (libbp4.so) for sm_100a and of the C++ host
+library mirroring the reference's operator/solver surface (libbp4_host.so)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+LIB = os.path.join(HERE, "libbp4.so")
+HOSTLIB = os.path.join(HERE, "libbp4_host.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--threads", "0"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _sources(d, exts):
+    return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(exts)]
+
+
+def build_cuda(force=False, verbose=False):
+    srcs = _sources(CSRC, (".cu",))
+    deps = _sources(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "bp4.h")]
+    if not force and not _newer(LIB, deps):
+        return LIB
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(CSRC, os.path.basename(s) + ".o")
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd)))
+        objs.append(o)
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lnccl", "-lcudart"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+def build_host(force=False):
+    if not os.path.isdir(HOST):
+        return None
+    srcs = _sources(HOST, (".cc",))
+    if not srcs:
+        return None
+    deps = _sources(HOST, (".cc", ".h")) + [os.path.join(ROOT, "include", "bp4.h")]
+    if not force and not _newer(HOSTLIB, deps):
+        return HOSTLIB
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-Wall", "-o", HOSTLIB] + srcs + \
+          ["-I", os.path.join(ROOT, "include"), "-L", HERE, "-lbp4", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return HOSTLIB
+
+
+def build_all(force=False, verbose=False):
+    build_cuda(force, verbose)
+    build_host(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)

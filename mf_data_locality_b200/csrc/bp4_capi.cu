@@ -1,0 +1,692 @@
+// bp4_capi.cu -- implementation of the C ABI declared in include/bp4.h.
+// Owns the device copies of the mesh data LaplaceOperator::initialize builds
+// (poisson_operator.h:101-293), the vectors, the stream and the reduction scratch.
+// There is no CPU fallback: every entry point needs a CUDA device.
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bp4.h"
+#include "bp4_launch.h"
+
+namespace
+{
+  thread_local std::string g_err;
+
+  int fail(int code, const char *fmt, ...)
+  {
+    char    buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+  }
+} // namespace
+
+#define CU(call)                                                                              \
+  do                                                                                          \
+    {                                                                                         \
+      cudaError_t e_ = (call);                                                                \
+      if (e_ != cudaSuccess)                                                                  \
+        return fail(BP4_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,                  \
+                    cudaGetErrorString(e_));                                                  \
+    }                                                                                         \
+  while (0)
+
+#define NC(call)                                                                              \
+  do                                                                                          \
+    {                                                                                         \
+      ncclResult_t r_ = (call);                                                               \
+      if (r_ != ncclSuccess)                                                                  \
+        return fail(BP4_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call,                  \
+                    ncclGetErrorString(r_));                                                  \
+    }                                                                                         \
+  while (0)
+
+struct bp4_vec
+{
+  double  *buf[2] = {nullptr, nullptr}; // ping-pong pair (second one allocated on demand)
+  int      cur    = 0;
+  uint64_t n      = 0;
+  double  *p() const { return buf[cur]; }
+};
+
+struct ProfEvent
+{
+  cudaEvent_t a, b;
+  int         id;
+};
+
+struct bp4_ctx
+{
+  int          degree = 0, device = 0, sms = 0;
+  uint64_t     n_cells = 0, n_owned = 0, n_ghost = 0, n_constrained = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t    *d_entity = nullptr, *d_constrained = nullptr, *d_walk = nullptr;
+  double      *d_coef = nullptr, *d_gll = nullptr;
+  double      *d_acc  = nullptr; // [8] reduction scratch
+  int         *d_flag = nullptr;
+  double      *h_acc  = nullptr; // pinned [8]
+  int         *h_flag = nullptr; // pinned
+  int          merged_variant = 0;
+  // multi-GPU
+  ncclComm_t            comm = nullptr;
+  int                   rank = 0, n_ranks = 1;
+  std::vector<int>      peer;
+  std::vector<uint64_t> import_off, export_off;
+  uint32_t             *d_export = nullptr;
+  double               *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+  // measurement
+  bool                   profile = false;
+  std::vector<ProfEvent> events;
+  double                 prof_ms[BP4_K_COUNT]  = {0};
+  uint64_t               prof_cnt[BP4_K_COUNT] = {0};
+  uint64_t               launches               = 0;
+};
+
+namespace
+{
+  struct Timed // RAII: count a launch, and time it with events when profiling is on
+  {
+    bp4_ctx *c;
+    int      id;
+    ProfEvent ev{};
+    bool      on;
+    Timed(bp4_ctx *c_, int id_, int n_launches = 1) : c(c_), id(id_), on(c_->profile)
+    {
+      c->launches += n_launches;
+      c->prof_cnt[id] += 1;
+      if (on)
+        {
+          cudaEventCreate(&ev.a);
+          cudaEventCreate(&ev.b);
+          ev.id = id;
+          cudaEventRecord(ev.a, c->stream);
+        }
+    }
+    ~Timed()
+    {
+      if (on)
+        {
+          cudaEventRecord(ev.b, c->stream);
+          c->events.push_back(ev);
+        }
+    }
+  };
+
+  int drain_events(bp4_ctx *c)
+  {
+    for (auto &ev : c->events)
+      {
+        CU(cudaEventSynchronize(ev.b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        c->prof_ms[ev.id] += ms;
+        cudaEventDestroy(ev.a);
+        cudaEventDestroy(ev.b);
+      }
+    c->events.clear();
+    return 0;
+  }
+
+  int ensure_second(bp4_ctx *c, bp4_vec *v)
+  {
+    if (!v->buf[1])
+      {
+        CU(cudaMalloc(&v->buf[1], sizeof(double) * (v->n ? v->n : 1)));
+        CU(cudaMemsetAsync(v->buf[1], 0, sizeof(double) * v->n, c->stream));
+      }
+    return 0;
+  }
+
+  // sum of acc[0..k) over ranks, returned on the host
+  int reduce_to_host(bp4_ctx *c, int k, double *out)
+  {
+    if (c->comm)
+      NC(ncclAllReduce(c->d_acc, c->d_acc, k, ncclDouble, ncclSum, c->comm, c->stream));
+    CU(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < k; ++i)
+      out[i] = c->h_acc[i];
+    return 0;
+  }
+} // namespace
+
+extern "C" {
+
+const char *bp4_last_error(void) { return g_err.c_str(); }
+
+int bp4_device_count(int *count)
+{
+  if (!count)
+    return fail(BP4_ERR_ARG, "count is null");
+  CU(cudaGetDeviceCount(count));
+  return 0;
+}
+
+int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
+{
+  if (!d || !out)
+    return fail(BP4_ERR_ARG, "null argument");
+  if (d->degree < 2 || d->degree > 8)
+    return fail(BP4_ERR_ARG, "degree %d not supported (2..8)", d->degree);
+  if (d->n_owned % 3 || d->n_ghost % 3)
+    return fail(BP4_ERR_ARG, "n_owned/n_ghost must be multiples of 3");
+  if (d->n_owned + d->n_ghost >= 0xFFFFFFFFull)
+    return fail(BP4_ERR_ARG, "local vector exceeds 32-bit local indices (poisson_operator.h:693)");
+  if (d->n_cells && (!d->entity_index || !d->vertices))
+    return fail(BP4_ERR_ARG, "entity_index/vertices missing");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev == 0)
+    return fail(BP4_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  CU(cudaSetDevice(d->device));
+  bp4_ctx *c = new bp4_ctx;
+  c->degree  = d->degree;
+  c->device  = d->device;
+  c->n_cells = d->n_cells;
+  c->n_owned = d->n_owned;
+  c->n_ghost = d->n_ghost;
+  c->n_constrained = d->n_constrained;
+  CU(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, d->device));
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+  std::vector<uint32_t> walk;
+  CU(bp4::launch_init_degree(d->degree, walk));
+  CU(cudaMalloc(&c->d_walk, sizeof(uint32_t) * walk.size()));
+  CU(cudaMemcpy(c->d_walk, walk.data(), sizeof(uint32_t) * walk.size(), cudaMemcpyHostToDevice));
+
+  const size_t nc = d->n_cells ? d->n_cells : 1;
+  CU(cudaMalloc(&c->d_entity, sizeof(uint32_t) * 27 * nc));
+  CU(cudaMalloc(&c->d_coef, sizeof(double) * 24 * nc));
+  if (d->n_cells)
+    {
+      CU(cudaMemcpy(c->d_entity, d->entity_index, sizeof(uint32_t) * 27 * d->n_cells,
+                    cudaMemcpyHostToDevice));
+      // tri-linear coefficients from the 8 vertices, poisson_operator.h:161-178
+      std::vector<double> cf(24 * d->n_cells);
+      for (uint64_t i = 0; i < d->n_cells; ++i)
+        for (int k = 0; k < 3; ++k)
+          {
+            const double *v = d->vertices + 24 * i;
+            double       *o = cf.data() + 24 * i;
+            const double  v0 = v[0 + k], v1 = v[3 + k], v2 = v[6 + k], v3 = v[9 + k], v4 = v[12 + k],
+                         v5 = v[15 + k], v6 = v[18 + k], v7 = v[21 + k];
+            o[0 + k]  = v0;
+            o[3 + k]  = v1 - v0;
+            o[6 + k]  = v2 - v0;
+            o[9 + k]  = v3 - v2 - (v1 - v0);
+            o[12 + k] = v4 - v0;
+            o[15 + k] = v5 - v4 - (v1 - v0);
+            o[18 + k] = v6 - v4 - (v2 - v0);
+            o[21 + k] = (v7 - v6 - (v5 - v4) - (v3 - v2 - (v1 - v0)));
+          }
+      CU(cudaMemcpy(c->d_coef, cf.data(), sizeof(double) * cf.size(), cudaMemcpyHostToDevice));
+    }
+  CU(cudaMalloc(&c->d_constrained, sizeof(uint32_t) * (d->n_constrained ? d->n_constrained : 1)));
+  if (d->n_constrained)
+    CU(cudaMemcpy(c->d_constrained, d->constrained, sizeof(uint32_t) * d->n_constrained,
+                  cudaMemcpyHostToDevice));
+  std::vector<double> gll;
+  bp4::gll_table(d->degree, gll);
+  CU(cudaMalloc(&c->d_gll, sizeof(double) * gll.size()));
+  CU(cudaMemcpy(c->d_gll, gll.data(), sizeof(double) * gll.size(), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&c->d_acc, sizeof(double) * 8));
+  CU(cudaMemset(c->d_acc, 0, sizeof(double) * 8));
+  CU(cudaMalloc(&c->d_flag, sizeof(int)));
+  CU(cudaMallocHost(&c->h_acc, sizeof(double) * 8));
+  CU(cudaMallocHost(&c->h_flag, sizeof(int)));
+
+  // ghost exchange plan
+  if (d->n_peers > 0)
+    {
+      c->peer.assign(d->peer_rank, d->peer_rank + d->n_peers);
+      c->import_off.assign(d->import_offset, d->import_offset + d->n_peers + 1);
+      c->export_off.assign(d->export_offset, d->export_offset + d->n_peers + 1);
+      const uint64_t ne = c->export_off.back();
+      CU(cudaMalloc(&c->d_export, sizeof(uint32_t) * (ne ? ne : 1)));
+      if (ne)
+        CU(cudaMemcpy(c->d_export, d->export_index, sizeof(uint32_t) * ne, cudaMemcpyHostToDevice));
+      CU(cudaMalloc(&c->d_sendbuf, sizeof(double) * (ne ? ne : 1)));
+      CU(cudaMalloc(&c->d_recvbuf, sizeof(double) * (ne ? ne : 1)));
+    }
+  *out = c;
+  return 0;
+}
+
+int bp4_ctx_destroy(bp4_ctx *c)
+{
+  if (!c)
+    return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  drain_events(c);
+  if (c->comm)
+    ncclCommDestroy(c->comm);
+  cudaFree(c->d_entity);
+  cudaFree(c->d_constrained);
+  cudaFree(c->d_walk);
+  cudaFree(c->d_coef);
+  cudaFree(c->d_gll);
+  cudaFree(c->d_acc);
+  cudaFree(c->d_flag);
+  cudaFree(c->d_export);
+  cudaFree(c->d_sendbuf);
+  cudaFree(c->d_recvbuf);
+  cudaFreeHost(c->h_acc);
+  cudaFreeHost(c->h_flag);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int bp4_ctx_synchronize(bp4_ctx *c)
+{
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int bp4_ctx_stream(bp4_ctx *c, void **stream)
+{
+  if (!c || !stream)
+    return fail(BP4_ERR_ARG, "null argument");
+  *stream = (void *)c->stream;
+  return 0;
+}
+
+int bp4_vec_alloc(bp4_ctx *c, uint64_t n, bp4_vec **out)
+{
+  if (!c || !out)
+    return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  bp4_vec *v = new bp4_vec;
+  v->n       = n;
+  CU(cudaMalloc(&v->buf[0], sizeof(double) * (n ? n : 1)));
+  CU(cudaMemsetAsync(v->buf[0], 0, sizeof(double) * n, c->stream));
+  *out = v;
+  return 0;
+}
+
+int bp4_vec_free(bp4_ctx *c, bp4_vec *v)
+{
+  if (!v)
+    return 0;
+  if (c)
+    cudaStreamSynchronize(c->stream);
+  cudaFree(v->buf[0]);
+  cudaFree(v->buf[1]);
+  delete v;
+  return 0;
+}
+
+int bp4_vec_size(const bp4_vec *v, uint64_t *n)
+{
+  if (!v || !n)
+    return fail(BP4_ERR_ARG, "null argument");
+  *n = v->n;
+  return 0;
+}
+
+int bp4_vec_set_zero(bp4_ctx *c, bp4_vec *v)
+{
+  if (!c || !v)
+    return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaMemsetAsync(v->p(), 0, sizeof(double) * v->n, c->stream));
+  return 0;
+}
+
+int bp4_vec_upload(bp4_ctx *c, bp4_vec *v, const double *host, uint64_t n)
+{
+  if (!c || !v || (!host && n))
+    return fail(BP4_ERR_ARG, "null argument");
+  if (n > v->n)
+    return fail(BP4_ERR_ARG, "upload of %llu > vector size %llu", (unsigned long long)n,
+                (unsigned long long)v->n);
+  CU(cudaMemcpyAsync(v->p(), host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+int bp4_vec_download(bp4_ctx *c, const bp4_vec *v, double *host, uint64_t n)
+{
+  if (!c || !v || (!host && n))
+    return fail(BP4_ERR_ARG, "null argument");
+  if (n > v->n)
+    return fail(BP4_ERR_ARG, "download of %llu > vector size %llu", (unsigned long long)n,
+                (unsigned long long)v->n);
+  CU(cudaMemcpyAsync(host, v->p(), sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int bp4_vec_device_ptr(bp4_ctx *c, bp4_vec *v, double **dev)
+{
+  if (!c || !v || !dev)
+    return fail(BP4_ERR_ARG, "null argument");
+  *dev = v->p();
+  return 0;
+}
+
+static int check_len(const bp4_ctx *c, const bp4_vec *v, const char *name)
+{
+  if (!v)
+    return fail(BP4_ERR_ARG, "%s is null", name);
+  if (v->n < c->n_owned + c->n_ghost)
+    return fail(BP4_ERR_ARG, "%s has %llu entries, need n_owned+n_ghost = %llu", name,
+                (unsigned long long)v->n, (unsigned long long)(c->n_owned + c->n_ghost));
+  return 0;
+}
+
+// cell loop: dst = sum_cells A_cell src on the local vector (owned + ghost slots)
+static int cell_loop(bp4_ctx *c, double *dst, const double *src, bool zero_dst)
+{
+  const uint64_t n = c->n_owned + c->n_ghost;
+  if (zero_dst)
+    CU(cudaMemsetAsync(dst, 0, sizeof(double) * n, c->stream));
+  bp4::CellArgs a;
+  a.entity_index = c->d_entity;
+  a.coef         = c->d_coef;
+  a.walk         = c->d_walk;
+  a.n_cells      = c->n_cells;
+  a.src          = src;
+  a.dst          = dst;
+  Timed t(c, BP4_K_VMULT);
+  CU(bp4::launch_cell_plain(c->degree, a, c->sms, c->stream));
+  return 0;
+}
+
+int bp4_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src)
+{
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  if (int e = check_len(c, dst, "dst"))
+    return e;
+  if (int e = check_len(c, src, "src"))
+    return e;
+  if (dst == src)
+    return fail(BP4_ERR_ARG, "vmult: dst aliases src");
+  // update_ghost_values / compress(add) around the cell loop (MatrixFree::cell_loop,
+  // poisson_operator.h:310); no-ops on a single rank
+  if (c->n_ghost)
+    if (int e = bp4_update_ghost_values(c, const_cast<bp4_vec *>(src)))
+      return e;
+  if (int e = cell_loop(c, dst->p(), src->p(), true))
+    return e;
+  if (c->n_ghost)
+    if (int e = bp4_compress_add(c, dst))
+      return e;
+  {
+    Timed t(c, BP4_K_BLAS1);
+    CU(bp4::launch_fixup(c->n_constrained, c->d_constrained, dst->p(), src->p(), c->stream));
+  }
+  return 0;
+}
+
+int bp4_set_merged_variant(bp4_ctx *c, int variant)
+{
+  if (!c || variant < 0 || variant > 1)
+    return fail(BP4_ERR_ARG, "bad variant");
+  c->merged_variant = variant;
+  return 0;
+}
+
+int bp4_vmult_merged(bp4_ctx *c, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h, const bp4_vec *prec,
+                     double alpha, double beta, double alpha_old, double beta_old, double out[7])
+{
+  if (!c || !out)
+    return fail(BP4_ERR_ARG, "null argument");
+  for (auto pr : {std::make_pair((const bp4_vec *)x, "x"), std::make_pair((const bp4_vec *)g, "g"),
+                  std::make_pair((const bp4_vec *)d, "d"), std::make_pair((const bp4_vec *)h, "h")})
+    if (int e = check_len(c, pr.first, pr.second))
+      return e;
+  if (!prec || prec->n < c->n_owned / 3)
+    return fail(BP4_ERR_ARG, "prec needs n_owned/3 entries");
+  const uint64_t n = c->n_owned;
+  // three-kernel variant: pre sweep, cell loop, post sweep
+  {
+    Timed t(c, BP4_K_PRE);
+    CU(bp4::launch_pre(n, h->p(), x->p(), g->p(), d->p(), prec->p(), alpha, beta, alpha_old, beta_old,
+                       c->sms, c->stream));
+  }
+  if (c->n_ghost)
+    {
+      if (int e = bp4_update_ghost_values(c, d))
+        return e;
+      CU(cudaMemsetAsync(h->p() + n, 0, sizeof(double) * c->n_ghost, c->stream));
+    }
+  if (int e = cell_loop(c, h->p(), d->p(), false))
+    return e;
+  if (c->n_ghost)
+    if (int e = bp4_compress_add(c, h))
+      return e;
+  CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 7, c->stream));
+  {
+    Timed t(c, BP4_K_POST);
+    CU(bp4::launch_post(n, g->p(), d->p(), h->p(), prec->p(), c->d_acc, c->sms, c->stream));
+  }
+  return reduce_to_host(c, 7, out);
+}
+
+int bp4_inverse_diagonal(bp4_ctx *c, bp4_vec *out)
+{
+  if (!c || !out)
+    return fail(BP4_ERR_ARG, "null argument");
+  const uint64_t n_nodes = (c->n_owned + c->n_ghost) / 3;
+  if (out->n < c->n_owned / 3)
+    return fail(BP4_ERR_ARG, "diagonal vector needs n_owned/3 entries");
+  // assemble over owned+ghost nodes, invert, keep the owned part
+  if (c->n_ghost)
+    return fail(BP4_ERR_STATE, "bp4_inverse_diagonal: partitioned meshes need compress(add) of the "
+                               "node-wise diagonal, not implemented yet");
+  bp4_vec *tmp = nullptr;
+  if (int e = bp4_vec_alloc(c, n_nodes, &tmp))
+    return e;
+  {
+    Timed t(c, BP4_K_BLAS1, 2);
+    CU(bp4::launch_diag(c->degree, c->n_cells, c->d_entity, c->d_coef, c->d_gll, tmp->p(), n_nodes,
+                        c->stream));
+  }
+  CU(cudaMemcpyAsync(out->p(), tmp->p(), sizeof(double) * (c->n_owned / 3), cudaMemcpyDeviceToDevice,
+                     c->stream));
+  return bp4_vec_free(c, tmp);
+}
+
+int bp4_jacobi_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src, const bp4_vec *diag)
+{
+  if (!c || !dst || !src || !diag)
+    return fail(BP4_ERR_ARG, "null argument");
+  if (dst->n < c->n_owned || src->n < c->n_owned || 3 * diag->n < c->n_owned)
+    return fail(BP4_ERR_ARG, "Dimension mismatch %llu vs 3 x %llu", (unsigned long long)dst->n,
+                (unsigned long long)diag->n);
+  Timed t(c, BP4_K_BLAS1);
+  CU(bp4::launch_jacobi(c->n_owned, dst->p(), src->p(), diag->p(), c->sms, c->stream));
+  return 0;
+}
+
+int bp4_x_finalize_even(bp4_ctx *c, bp4_vec *x, const bp4_vec *d, const bp4_vec *g, const bp4_vec *prec,
+                        double c1, double c2)
+{
+  if (!c || !x || !d || !g || !prec)
+    return fail(BP4_ERR_ARG, "null argument");
+  Timed t(c, BP4_K_BLAS1);
+  CU(bp4::launch_xfinal(c->n_owned, x->p(), d->p(), g->p(), prec->p(), c1, c2, c->sms, c->stream));
+  return 0;
+}
+
+int bp4_equ(bp4_ctx *c, bp4_vec *dst, double a, const bp4_vec *src)
+{
+  if (!c || !dst || !src)
+    return fail(BP4_ERR_ARG, "null argument");
+  Timed t(c, BP4_K_BLAS1);
+  CU(bp4::launch_sadd(c->n_owned, dst->p(), 0., a, src->p(), c->sms, c->stream));
+  return 0;
+}
+
+int bp4_add(bp4_ctx *c, bp4_vec *dst, double a, const bp4_vec *src)
+{
+  if (!c || !dst || !src)
+    return fail(BP4_ERR_ARG, "null argument");
+  Timed t(c, BP4_K_BLAS1);
+  CU(bp4::launch_sadd(c->n_owned, dst->p(), 1., a, src->p(), c->sms, c->stream));
+  return 0;
+}
+
+int bp4_sadd(bp4_ctx *c, bp4_vec *dst, double s, double a, const bp4_vec *src)
+{
+  if (!c || !dst || !src)
+    return fail(BP4_ERR_ARG, "null argument");
+  Timed t(c, BP4_K_BLAS1);
+  CU(bp4::launch_sadd(c->n_owned, dst->p(), s, a, src->p(), c->sms, c->stream));
+  return 0;
+}
+
+int bp4_dot(bp4_ctx *c, const bp4_vec *a, const bp4_vec *b, double *result)
+{
+  if (!c || !a || !b || !result)
+    return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
+  {
+    Timed t(c, BP4_K_BLAS1);
+    CU(bp4::launch_dot(c->n_owned, a->p(), b->p(), c->d_acc, c->sms, c->stream));
+  }
+  return reduce_to_host(c, 1, result);
+}
+
+int bp4_add_and_dot(bp4_ctx *c, bp4_vec *g, double a, const bp4_vec *h, const bp4_vec *w, double *result)
+{
+  if (!c || !g || !h || !w || !result)
+    return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
+  {
+    Timed t(c, BP4_K_BLAS1);
+    CU(bp4::launch_add_and_dot(c->n_owned, g->p(), a, h->p(), w->p(), c->d_acc, c->sms, c->stream));
+  }
+  return reduce_to_host(c, 1, result);
+}
+
+int bp4_l2_norm(bp4_ctx *c, const bp4_vec *v, double *result)
+{
+  double s = 0;
+  if (int e = bp4_dot(c, v, v, &s))
+    return e;
+  *result = std::sqrt(s);
+  return 0;
+}
+
+int bp4_all_zero(bp4_ctx *c, const bp4_vec *v, int *result)
+{
+  if (!c || !v || !result)
+    return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+  {
+    Timed t(c, BP4_K_BLAS1);
+    CU(bp4::launch_nonzero(c->n_owned, v->p(), c->d_flag, c->sms, c->stream));
+  }
+  if (c->comm)
+    NC(ncclAllReduce(c->d_flag, c->d_flag, 1, ncclInt, ncclMax, c->comm, c->stream));
+  CU(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *result = *c->h_flag ? 0 : 1;
+  return 0;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------
+int bp4_comm_unique_id(unsigned char id[BP4_NCCL_ID_BYTES])
+{
+  static_assert(sizeof(ncclUniqueId) == BP4_NCCL_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId u;
+  NC(ncclGetUniqueId(&u));
+  memcpy(id, &u, sizeof(u));
+  return 0;
+}
+
+int bp4_comm_init(bp4_ctx *c, int rank, int n_ranks, const unsigned char id[BP4_NCCL_ID_BYTES])
+{
+  if (!c || !id)
+    return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  NC(ncclCommInitRank(&c->comm, n_ranks, u, rank));
+  c->rank    = rank;
+  c->n_ranks = n_ranks;
+  return 0;
+}
+
+int bp4_update_ghost_values(bp4_ctx *c, bp4_vec *v)
+{
+  (void)v;
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  if (c->peer.empty())
+    return 0;
+  return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
+}
+
+int bp4_compress_add(bp4_ctx *c, bp4_vec *v)
+{
+  (void)v;
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  if (c->peer.empty())
+    return 0;
+  return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
+}
+
+// ---- measurement -------------------------------------------------------------------------
+int bp4_profile_enable(bp4_ctx *c, int on)
+{
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  if (!on)
+    if (int e = drain_events(c))
+      return e;
+  c->profile = on != 0;
+  return 0;
+}
+
+int bp4_profile_reset(bp4_ctx *c)
+{
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  if (int e = drain_events(c))
+    return e;
+  for (int i = 0; i < BP4_K_COUNT; ++i)
+    {
+      c->prof_ms[i]  = 0;
+      c->prof_cnt[i] = 0;
+    }
+  c->launches = 0;
+  return 0;
+}
+
+int bp4_profile_get(bp4_ctx *c, int id, double *total_ms, uint64_t *launches)
+{
+  if (!c || id < 0 || id >= BP4_K_COUNT)
+    return fail(BP4_ERR_ARG, "bad kernel id");
+  if (int e = drain_events(c))
+    return e;
+  if (total_ms)
+    *total_ms = c->prof_ms[id];
+  if (launches)
+    *launches = c->prof_cnt[id];
+  return 0;
+}
+
+int bp4_launch_count(bp4_ctx *c, uint64_t *launches)
+{
+  if (!c || !launches)
+    return fail(BP4_ERR_ARG, "null argument");
+  *launches = c->launches;
+  return 0;
+}
+
+} // extern "C"

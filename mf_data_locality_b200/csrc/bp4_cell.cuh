@@ -1,0 +1,349 @@
+// bp4_cell.cuh -- per-cell sum-factorisation phases of the BP4 vector-Laplace operator
+// for one Q_p hexahedron with tri-linear geometry evaluated on the fly.
+//
+// Replaces the CPU SIMD kernels K1-K5 of the reference:
+//   read_dof_values_compressed        vector_access_reduced.h:51-283
+//   LaplaceOperator::local_apply      poisson_operator.h:429-685 (3-D branch :534-666)
+//   distribute_local_to_global_compr. vector_access_reduced.h:287-531
+// It is NOT a translation of that code: the reference keeps one cell per SIMD lane and
+// sweeps z-layers; here a thread block owns CPB cells and the work is cut into three
+// register-blocked phases that each do two or three 1-D contractions per shared-memory
+// round trip (B200 has 64 FP64 FMA/clk/SM but only 128 B/clk/SM of shared-memory
+// bandwidth, so a line-per-thread scheme with one contraction per round trip would be
+// shared-memory bound):
+//
+//   phase 1  item (comp c, node-row j)   : x-interp, z-interp, d/dzeta, d/dxi   -> smem
+//   phase 2  item (qx, qz), all 3 comps  : y-interp, d/deta, Jacobian, G = w/det K^T K,
+//                                          flux, d/deta^T, y-back-interp       -> smem
+//   phase 3  item (comp c, node-row j)   : d/dxi^T, d/dzeta^T, z- and x-back-interp
+//
+// d/dxi and d/dzeta are taken *before* the y-interpolation (they commute with it), so
+// phase 2 only ever needs y-lines and the three components of one quadrature point
+// meet in one thread for the geometry.
+//
+// The same source is compiled by g++ for tests/emu (a CPU emulation of the thread loops
+// used to check indexing without a GPU); the product never runs it on the CPU.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#  define BP4_HD __host__ __device__ __forceinline__
+#  define BP4_UNROLL _Pragma("unroll")
+#else
+#  define BP4_HD inline
+#  define BP4_UNROLL
+#endif
+
+namespace bp4
+{
+  template <int P>
+  struct Tab
+  {
+    static constexpr int N = P + 1; // nodes per direction (GLL)
+    static constexpr int Q = P + 2; // Gauss points per direction
+    double S[N][Q];                 // S[i][q]  = l_i^GLL(x_q)            (shape_values)
+    double Dn[N][Q];                // Dn[i][q] = d/dx l_i^GLL(x_q)       (= S * D)
+    double D[Q][Q];                 // D[i][q]  = d/dx l_i^Gauss(x_q)     (collocation gradient)
+    double xq[Q];                   // Gauss points on [0,1]
+    double wq[Q];                   // Gauss weights
+  };
+
+  template <int P>
+  struct Geom // sizes and shared-memory strides of one cell slot
+  {
+    static constexpr int N   = P + 1;
+    static constexpr int Q   = P + 2;
+    static constexpr int N3  = N * N * N;
+    static constexpr int DOF = 3 * N3;             // staged cell DoFs   [c][k][j][i]
+    // work[c][a][qz][j][qx], a = 0 value, 1 xi-derivative/flux, 2 zeta-derivative/flux
+    static constexpr int WJ  = Q;                  // stride of j
+    static constexpr int WZ  = N * Q;              // stride of qz
+    static constexpr int WA  = Q * N * Q;          // stride of a
+    static constexpr int WC  = 3 * WA;             // stride of c
+    static constexpr int WORK = 3 * WC;
+    static constexpr int ITEMS13 = 3 * N;          // phase 1/3 items per cell
+    static constexpr int ITEMS2  = Q * Q;          // phase 2 items per cell
+  };
+
+  // entity code of a node coordinate: 0 left vertex, 1 interior, 2 right vertex
+  template <int P>
+  BP4_HD int ecode(int i)
+  {
+    return i == 0 ? 0 : (i == P ? 2 : 1);
+  }
+
+  // packed (lexicographic node | entity << 10 | position-in-entity << 15) of the w-th node
+  // in entity-major order; entity a = ex + 3 ey + 9 ez, nodes lexicographic inside the
+  // entity (vector_access_reduced.h:176-258: idx[a] + 3 * position + component)
+  template <int P>
+  inline void build_walk(uint32_t *walk)
+  {
+    constexpr int N = P + 1;
+    int w = 0;
+    for (int a = 0; a < 27; ++a)
+      {
+        const int e[3] = {a % 3, (a / 3) % 3, a / 9};
+        int lo[3], hi[3];
+        for (int d = 0; d < 3; ++d)
+          {
+            lo[d] = e[d] == 0 ? 0 : (e[d] == 1 ? 1 : P);
+            hi[d] = e[d] == 0 ? 1 : (e[d] == 1 ? P : P + 1);
+          }
+        int pos = 0;
+        for (int k = lo[2]; k < hi[2]; ++k)
+          for (int j = lo[1]; j < hi[1]; ++j)
+            for (int i = lo[0]; i < hi[0]; ++i, ++pos, ++w)
+              walk[w] = uint32_t((k * N + j) * N + i) | (uint32_t(a) << 10) | (uint32_t(pos) << 15);
+      }
+  }
+
+  // ---------------------------------------------------------------------------------------
+  // phase 1: item = (c, j).  dofs[c][k][j][i] -> work[c][{0,1,2}][qz][j][qx]
+  // ---------------------------------------------------------------------------------------
+  template <int P>
+  BP4_HD void phase1(const Tab<P> &tb, const double *dofs, double *work, const int c, const int j)
+  {
+    using G         = Geom<P>;
+    constexpr int N = G::N, Q = G::Q;
+    const double *in = dofs + c * G::N3 + j * N;
+    double        t[N][Q];
+    BP4_UNROLL
+    for (int k = 0; k < N; ++k)
+      {
+        double r[N];
+        BP4_UNROLL
+        for (int i = 0; i < N; ++i)
+          r[i] = in[k * N * N + i];
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            double s = tb.S[0][q] * r[0];
+            BP4_UNROLL
+            for (int i = 1; i < N; ++i)
+              s += tb.S[i][q] * r[i];
+            t[k][q] = s;
+          }
+      }
+    double *out = work + c * G::WC + j * G::WJ;
+    BP4_UNROLL
+    for (int qz = 0; qz < Q; ++qz)
+      {
+        double u[Q], wz[Q];
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            double su = tb.S[0][qz] * t[0][q];
+            double sz = tb.Dn[0][qz] * t[0][q];
+            BP4_UNROLL
+            for (int k = 1; k < N; ++k)
+              {
+                su += tb.S[k][qz] * t[k][q];
+                sz += tb.Dn[k][qz] * t[k][q];
+              }
+            u[q]  = su;
+            wz[q] = sz;
+          }
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            double sx = tb.D[0][q] * u[0];
+            BP4_UNROLL
+            for (int i = 1; i < Q; ++i)
+              sx += tb.D[i][q] * u[i];
+            out[0 * G::WA + qz * G::WZ + q] = u[q];
+            out[1 * G::WA + qz * G::WZ + q] = sx;
+            out[2 * G::WA + qz * G::WZ + q] = wz[q];
+          }
+      }
+  }
+
+  // ---------------------------------------------------------------------------------------
+  // phase 2: item = (qx, qz), all three components, one y-line of quadrature points.
+  // cf = tri-linear coefficients [8][3] in the order v0,v1,v3,v4,v9,v10,v12,v13
+  // (poisson_operator.h:165-177); x = xq[qx], z = xq[qz], wxz = wq[qx]*wq[qz].
+  // ---------------------------------------------------------------------------------------
+  template <int P>
+  BP4_HD void phase2(const Tab<P> &tb, const double *cf, double *work, const int qx, const int qz,
+                     const double x, const double z, const double wxz)
+  {
+    using G         = Geom<P>;
+    constexpr int N = G::N, Q = G::Q;
+    double        gr[3][3][Q]; // [c][direction][qy]
+    double       *base = work + qz * G::WZ + qx;
+    BP4_UNROLL
+    for (int c = 0; c < 3; ++c)
+      {
+        BP4_UNROLL
+        for (int a = 0; a < 3; ++a)
+          {
+            double r[N];
+            BP4_UNROLL
+            for (int j = 0; j < N; ++j)
+              r[j] = base[c * G::WC + a * G::WA + j * G::WJ];
+            BP4_UNROLL
+            for (int q = 0; q < Q; ++q)
+              {
+                double s = tb.S[0][q] * r[0];
+                BP4_UNROLL
+                for (int j = 1; j < N; ++j)
+                  s += tb.S[j][q] * r[j];
+                gr[c][a == 0 ? 1 : (a == 1 ? 0 : 2)][q] = s; // a=0: value, parked in slot 1
+              }
+          }
+        // d/deta from the values parked in slot 1
+        double v[Q];
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          v[q] = gr[c][1][q];
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            double s = tb.D[0][q] * v[0];
+            BP4_UNROLL
+            for (int i = 1; i < Q; ++i)
+              s += tb.D[i][q] * v[i];
+            gr[c][1][q] = s;
+          }
+      }
+    // geometry along the line: rows of dX/dxi_e (poisson_operator.h:577-602)
+    //   r0 = dX/dxi   = (v1 + z v10) + y (v4 + z v13)
+    //   r1 = dX/deta  = (v3 + z v12) + x (v4 + z v13)      (constant along the line)
+    //   r2 = dX/dzeta = (v9 + x v10) + y (v12 + x v13)
+    double A[3], B[3], R1[3], Cc[3], Dd[3];
+    BP4_UNROLL
+    for (int d = 0; d < 3; ++d)
+      {
+        const double v1 = cf[3 + d], v3 = cf[6 + d], v4 = cf[9 + d], v9 = cf[12 + d],
+                     v10 = cf[15 + d], v12 = cf[18 + d], v13 = cf[21 + d];
+        A[d]  = v1 + z * v10;
+        B[d]  = v4 + z * v13;
+        R1[d] = (v3 + z * v12) + x * B[d];
+        Cc[d] = v9 + x * v10;
+        Dd[d] = v12 + x * v13;
+      }
+    BP4_UNROLL
+    for (int q = 0; q < Q; ++q)
+      {
+        const double y = tb.xq[q];
+        double       r0[3], r2[3];
+        BP4_UNROLL
+        for (int d = 0; d < 3; ++d)
+          {
+            r0[d] = A[d] + y * B[d];
+            r2[d] = Cc[d] + y * Dd[d];
+          }
+        // columns of adj: k0 = r1 x r2, k1 = r2 x r0, k2 = r0 x r1;  det = r0 . k0
+        // (the cofactor inverse of poisson_operator.h:41-63 without the division)
+        double k0[3], k1[3], k2[3];
+        k0[0] = R1[1] * r2[2] - R1[2] * r2[1];
+        k0[1] = R1[2] * r2[0] - R1[0] * r2[2];
+        k0[2] = R1[0] * r2[1] - R1[1] * r2[0];
+        k1[0] = r2[1] * r0[2] - r2[2] * r0[1];
+        k1[1] = r2[2] * r0[0] - r2[0] * r0[2];
+        k1[2] = r2[0] * r0[1] - r2[1] * r0[0];
+        k2[0] = r0[1] * R1[2] - r0[2] * R1[1];
+        k2[1] = r0[2] * R1[0] - r0[0] * R1[2];
+        k2[2] = r0[0] * R1[1] - r0[1] * R1[0];
+        const double det = r0[0] * k0[0] + r0[1] * k0[1] + r0[2] * k0[2];
+        // G = (w / det) K^T K  == det * w * J^-1 J^-T  (poisson_operator.h:604-625)
+        const double sc  = (wxz * tb.wq[q]) / det;
+        const double g00 = sc * (k0[0] * k0[0] + k0[1] * k0[1] + k0[2] * k0[2]);
+        const double g01 = sc * (k0[0] * k1[0] + k0[1] * k1[1] + k0[2] * k1[2]);
+        const double g02 = sc * (k0[0] * k2[0] + k0[1] * k2[1] + k0[2] * k2[2]);
+        const double g11 = sc * (k1[0] * k1[0] + k1[1] * k1[1] + k1[2] * k1[2]);
+        const double g12 = sc * (k1[0] * k2[0] + k1[1] * k2[1] + k1[2] * k2[2]);
+        const double g22 = sc * (k2[0] * k2[0] + k2[1] * k2[1] + k2[2] * k2[2]);
+        BP4_UNROLL
+        for (int c = 0; c < 3; ++c)
+          {
+            const double a = gr[c][0][q], b = gr[c][1][q], e = gr[c][2][q];
+            gr[c][0][q] = g00 * a + g01 * b + g02 * e;
+            gr[c][1][q] = g01 * a + g11 * b + g12 * e;
+            gr[c][2][q] = g02 * a + g12 * b + g22 * e;
+          }
+      }
+    // integrate: d/deta^T on the eta-flux, then y-back-interpolation of the three arrays
+    BP4_UNROLL
+    for (int c = 0; c < 3; ++c)
+      {
+        double v[Q];
+        BP4_UNROLL
+        for (int i = 0; i < Q; ++i)
+          {
+            double s = tb.D[i][0] * gr[c][1][0];
+            BP4_UNROLL
+            for (int q = 1; q < Q; ++q)
+              s += tb.D[i][q] * gr[c][1][q];
+            v[i] = s;
+          }
+        BP4_UNROLL
+        for (int a = 0; a < 3; ++a)
+          {
+            BP4_UNROLL
+            for (int j = 0; j < N; ++j)
+              {
+                double s = 0.;
+                BP4_UNROLL
+                for (int q = 0; q < Q; ++q)
+                  s += tb.S[j][q] * (a == 0 ? v[q] : (a == 1 ? gr[c][0][q] : gr[c][2][q]));
+                base[c * G::WC + a * G::WA + j * G::WJ] = s;
+              }
+          }
+      }
+  }
+
+  // ---------------------------------------------------------------------------------------
+  // phase 3: item = (c, j).  work[c][{0,1,2}][qz][j][qx] -> dofs[c][k][j][i]
+  // ---------------------------------------------------------------------------------------
+  template <int P>
+  BP4_HD void phase3(const Tab<P> &tb, const double *work, double *dofs, const int c, const int j)
+  {
+    using G         = Geom<P>;
+    constexpr int N = G::N, Q = G::Q;
+    const double *in = work + c * G::WC + j * G::WJ;
+    double        t[N][Q];
+    BP4_UNROLL
+    for (int k = 0; k < N; ++k)
+      BP4_UNROLL
+    for (int q = 0; q < Q; ++q)
+      t[k][q] = 0.;
+    BP4_UNROLL
+    for (int qz = 0; qz < Q; ++qz)
+      {
+        double v[Q], fx[Q], fz[Q];
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            v[q]  = in[0 * G::WA + qz * G::WZ + q];
+            fx[q] = in[1 * G::WA + qz * G::WZ + q];
+            fz[q] = in[2 * G::WA + qz * G::WZ + q];
+          }
+        BP4_UNROLL
+        for (int i = 0; i < Q; ++i)
+          {
+            double s = v[i];
+            BP4_UNROLL
+            for (int q = 0; q < Q; ++q)
+              s += tb.D[i][q] * fx[q];
+            v[i] = s;
+          }
+        BP4_UNROLL
+        for (int k = 0; k < N; ++k)
+          BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          t[k][q] += tb.S[k][qz] * v[q] + tb.Dn[k][qz] * fz[q];
+      }
+    double *out = dofs + c * G::N3 + j * N;
+    BP4_UNROLL
+    for (int k = 0; k < N; ++k)
+      BP4_UNROLL
+    for (int i = 0; i < N; ++i)
+      {
+        double s = tb.S[i][0] * t[k][0];
+        BP4_UNROLL
+        for (int q = 1; q < Q; ++q)
+          s += tb.S[i][q] * t[k][q];
+        out[k * N * N + i] = s;
+      }
+  }
+} // namespace bp4

@@ -1,0 +1,550 @@
+// bp4_kernels.cu -- kernel definitions and launchers (sm_100a, FP64).  See bp4_kernels.cuh.
+#include <algorithm>
+#include <cstdio>
+
+#include "bp4_kernels.cuh"
+#include "bp4_launch.h"
+#include "bp4_tables.h"
+
+namespace bp4
+{
+  // one table per degree in the constant bank: with fully unrolled contractions every
+  // matrix entry becomes a c[bank][offset] operand of a DFMA, no load instruction
+  template <int P>
+  __constant__ Tab<P> c_tab;
+
+  // ---------------------------------------------------------------------------------------
+  // cell kernel
+  // ---------------------------------------------------------------------------------------
+  template <int P, int CPB>
+  __global__ void __launch_bounds__(kThreads, 1) cell_kernel_plain(const CellArgs a)
+  {
+    using G         = Geom<P>;
+    constexpr int N3 = G::N3, Q = G::Q, N = G::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
+    const int         tid = threadIdx.x;
+    const Tab<P>     &tb  = c_tab<P>;
+
+    for (int i = tid; i < N3; i += kThreads)
+      sm.walk[i] = a.walk[i];
+    if (tid < Q)
+      {
+        sm.xq[tid] = tb.xq[tid];
+        sm.wq[tid] = tb.wq[tid];
+      }
+
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    for (uint64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x)
+      {
+        const uint64_t cell0 = batch * CPB;
+        const int      nc    = (int)min((uint64_t)CPB, a.n_cells - cell0);
+        for (int i = tid; i < nc * 27; i += kThreads)
+          sm.eidx[i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
+        for (int i = tid; i < nc * 24; i += kThreads)
+          sm.coef[i / 24][i % 24] = a.coef[cell0 * 24 + i];
+        __syncthreads();
+
+        // gather (vector_access_reduced.h:175-258): coalesced along each entity segment
+        for (int m = tid; m < nc * G::DOF; m += kThreads)
+          {
+            const int      cell = m / G::DOF, r = m % G::DOF;
+            const int      w = r / 3, c = r % 3;
+            const uint32_t pk   = sm.walk[w];
+            const uint32_t base = sm.eidx[cell][(pk >> 10) & 31u];
+            double         v    = 0.;
+            if (base != 0xFFFFFFFFu)
+              v = __ldg(a.src + (size_t)base + 3u * (pk >> 15) + c);
+            sm.dofs[cell][c * N3 + (pk & 1023u)] = v;
+          }
+        __syncthreads();
+
+        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+          {
+            const int cell = it / G::ITEMS13, r = it % G::ITEMS13;
+            phase1<P>(tb, sm.dofs[cell], sm.work[cell], r / N, r % N);
+          }
+        __syncthreads();
+
+        for (int it = tid; it < nc * G::ITEMS2; it += kThreads)
+          {
+            const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
+            const int qz = r / Q, qx = r % Q;
+            phase2<P>(tb, sm.coef[cell], sm.work[cell], qx, qz, sm.xq[qx], sm.xq[qz],
+                      sm.wq[qx] * sm.wq[qz]);
+          }
+        __syncthreads();
+
+        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+          {
+            const int cell = it / G::ITEMS13, r = it % G::ITEMS13;
+            phase3<P>(tb, sm.work[cell], sm.dofs[cell], r / N, r % N);
+          }
+        __syncthreads();
+
+        // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13)
+        // is touched by this cell only -> plain store
+        for (int m = tid; m < nc * G::DOF; m += kThreads)
+          {
+            const int      cell = m / G::DOF, r = m % G::DOF;
+            const int      w = r / 3, c = r % 3;
+            const uint32_t pk   = sm.walk[w];
+            const uint32_t ent  = (pk >> 10) & 31u;
+            const uint32_t base = sm.eidx[cell][ent];
+            if (base != 0xFFFFFFFFu)
+              {
+                const double v = sm.dofs[cell][c * N3 + (pk & 1023u)];
+                double      *p = a.dst + (size_t)base + 3u * (pk >> 15) + c;
+                if (ent == 13u)
+                  *p = v;
+                else
+                  atomicAdd(p, v);
+              }
+          }
+        __syncthreads();
+      }
+  }
+
+  // ---------------------------------------------------------------------------------------
+  // streaming kernels
+  // ---------------------------------------------------------------------------------------
+  __device__ __forceinline__ double warp_sum(double v)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+
+  // block-reduce K partial sums and atomically add them to acc[0..K)
+  template <int K>
+  __device__ __forceinline__ void block_accumulate(double (&s)[K], double *acc)
+  {
+    __shared__ double red[K][32];
+    const int         lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int         nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      {
+        s[k] = warp_sum(s[k]);
+        if (lane == 0)
+          red[k][warp] = s[k];
+      }
+    __syncthreads();
+    if (warp == 0)
+      {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          {
+            double v = lane < nw ? red[k][lane] : 0.;
+            v        = warp_sum(v);
+            if (lane == 0)
+              atomicAdd(acc + k, v);
+          }
+      }
+  }
+
+  // do_cg_update4b<3,double,true>, solver_cg_optimized.h:65-161, over [0,n)
+  __global__ void __launch_bounds__(256) pre_kernel(const uint64_t n, double *__restrict__ h,
+                                                    double *__restrict__ x, double *__restrict__ r,
+                                                    double *__restrict__ p,
+                                                    const double *__restrict__ prec,
+                                                    const double alpha, const double beta,
+                                                    const double alpha_old, const double beta_old)
+  {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const double   c1 = alpha_old != 0. ? alpha + alpha_old / beta_old : 0.;
+    const double   c2 = alpha_old != 0. ? alpha_old / beta_old : 0.;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      {
+        const double pr = prec[i / 3];
+        if (alpha == 0.)
+          p[i] = -pr * r[i];
+        else
+          {
+            double       ri = r[i];
+            const double pi = p[i];
+            if (alpha_old != 0.)
+              x[i] += c1 * pi + c2 * pr * ri;
+            ri += alpha * h[i];
+            r[i] = ri;
+            p[i] = beta * pi - pr * ri;
+          }
+        h[i] = 0.;
+      }
+  }
+
+  // do_cg_update3b<3,double>, solver_cg_optimized.h:12-61, over [0,n) -> acc[7]
+  __global__ void __launch_bounds__(256) post_kernel(const uint64_t n, const double *__restrict__ r,
+                                                     const double *__restrict__ d,
+                                                     const double *__restrict__ h,
+                                                     const double *__restrict__ prec, double *acc)
+  {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double         s[7]   = {0., 0., 0., 0., 0., 0., 0.};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      {
+        const double pr = prec[i / 3], ri = r[i], di = d[i], hi = h[i];
+        const double zi = pr * hi;
+        s[0] += di * hi;
+        s[1] += hi * hi;
+        s[2] += ri * hi;
+        s[3] += ri * ri;
+        s[4] += ri * zi;
+        s[5] += hi * zi;
+        s[6] += ri * pr * ri;
+      }
+    block_accumulate<7>(s, acc);
+  }
+
+  __global__ void __launch_bounds__(256) fixup_kernel(const uint64_t n, const uint32_t *__restrict__ con,
+                                                      double *__restrict__ dst,
+                                                      const double *__restrict__ src)
+  {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+      dst[con[i]] = src[con[i]];
+  }
+
+  // dst = s*dst + a*src   (s == 0: dst = a*src without reading dst)
+  __global__ void __launch_bounds__(256) sadd_kernel(const uint64_t n, double *__restrict__ dst,
+                                                     const double s, const double a,
+                                                     const double *__restrict__ src)
+  {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      dst[i] = (s == 0. ? 0. : s * dst[i]) + a * src[i];
+  }
+
+  __global__ void __launch_bounds__(256) dot_kernel(const uint64_t n, const double *__restrict__ a,
+                                                    const double *__restrict__ b, double *acc)
+  {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double         s[1]   = {0.};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      s[0] += a[i] * b[i];
+    block_accumulate<1>(s, acc);
+  }
+
+  // g += a*h ; acc += g.w   (w may alias g)
+  __global__ void __launch_bounds__(256) add_and_dot_kernel(const uint64_t n, double *g, const double a,
+                                                            const double *__restrict__ h,
+                                                            const double *w, double *acc)
+  {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double         s[1]   = {0.};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      {
+        const double gi = g[i] + a * h[i];
+        const double wi = (w == g) ? gi : w[i];
+        g[i]            = gi;
+        s[0] += gi * wi;
+      }
+    block_accumulate<1>(s, acc);
+  }
+
+  __global__ void __launch_bounds__(256) nonzero_kernel(const uint64_t n, const double *__restrict__ v,
+                                                        int *flag)
+  {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    int            nz     = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      nz |= (v[i] != 0.);
+    if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0)
+      atomicOr(flag, 1);
+  }
+
+  // dst[3i+c] = diag[i]*src[3i+c]   (diagonal_matrix_blocked.h:21-26)
+  __global__ void __launch_bounds__(256) jacobi_kernel(const uint64_t n, double *__restrict__ dst,
+                                                       const double *__restrict__ src,
+                                                       const double *__restrict__ diag)
+  {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      dst[i] = diag[i / 3] * src[i];
+  }
+
+  // x += c1*d + c2*prec*g   (solver_cg_optimized.h:260-288)
+  __global__ void __launch_bounds__(256) xfinal_kernel(const uint64_t n, double *__restrict__ x,
+                                                       const double *__restrict__ d,
+                                                       const double *__restrict__ g,
+                                                       const double *__restrict__ prec, const double c1,
+                                                       const double c2)
+  {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      x[i] += c1 * d[i] + c2 * prec[i / 3] * g[i];
+  }
+
+  // inverse diagonal of the scalar GLL(p+1) Laplacian (poisson_operator.h:392-426): one
+  // thread per (cell, node); collocation makes the unit-vector gradient non-zero only on
+  // the three grid lines through the node.  gll holds x[N], w[N], Dg[N][N] (Dg[i][q]=l_i'(x_q)).
+  __device__ __forceinline__ void metric_at(const double *cf, double x, double y, double z, double w,
+                                            double &g00, double &g01, double &g02, double &g11,
+                                            double &g12, double &g22)
+  {
+    double r0[3], r1[3], r2[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      {
+        const double v1 = cf[3 + d], v3 = cf[6 + d], v4 = cf[9 + d], v9 = cf[12 + d],
+                     v10 = cf[15 + d], v12 = cf[18 + d], v13 = cf[21 + d];
+        r0[d] = (v1 + z * v10) + y * (v4 + z * v13);
+        r1[d] = (v3 + z * v12) + x * (v4 + z * v13);
+        r2[d] = (v9 + y * v12) + x * (v10 + y * v13);
+      }
+    double k0[3], k1[3], k2[3];
+    k0[0] = r1[1] * r2[2] - r1[2] * r2[1];
+    k0[1] = r1[2] * r2[0] - r1[0] * r2[2];
+    k0[2] = r1[0] * r2[1] - r1[1] * r2[0];
+    k1[0] = r2[1] * r0[2] - r2[2] * r0[1];
+    k1[1] = r2[2] * r0[0] - r2[0] * r0[2];
+    k1[2] = r2[0] * r0[1] - r2[1] * r0[0];
+    k2[0] = r0[1] * r1[2] - r0[2] * r1[1];
+    k2[1] = r0[2] * r1[0] - r0[0] * r1[2];
+    k2[2] = r0[0] * r1[1] - r0[1] * r1[0];
+    const double det = r0[0] * k0[0] + r0[1] * k0[1] + r0[2] * k0[2];
+    const double sc  = w / det;
+    g00 = sc * (k0[0] * k0[0] + k0[1] * k0[1] + k0[2] * k0[2]);
+    g01 = sc * (k0[0] * k1[0] + k0[1] * k1[1] + k0[2] * k1[2]);
+    g02 = sc * (k0[0] * k2[0] + k0[1] * k2[1] + k0[2] * k2[2]);
+    g11 = sc * (k1[0] * k1[0] + k1[1] * k1[1] + k1[2] * k1[2]);
+    g12 = sc * (k1[0] * k2[0] + k1[1] * k2[1] + k1[2] * k2[2]);
+    g22 = sc * (k2[0] * k2[0] + k2[1] * k2[1] + k2[2] * k2[2]);
+  }
+
+  __global__ void __launch_bounds__(128) diag_kernel(const int p, const uint64_t n_cells,
+                                                     const uint32_t *__restrict__ entity_index,
+                                                     const double *__restrict__ coef,
+                                                     const double *__restrict__ gll, double *diag)
+  {
+    const int      N  = p + 1, N3 = N * N * N;
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_cells * N3)
+      return;
+    const uint64_t cell = id / N3;
+    const int      l = (int)(id % N3), i = l % N, j = (l / N) % N, k = l / (N * N);
+    const int      ex = i == 0 ? 0 : (i == p ? 2 : 1), ey = j == 0 ? 0 : (j == p ? 2 : 1),
+              ez = k == 0 ? 0 : (k == p ? 2 : 1);
+    const uint32_t base = entity_index[cell * 27 + ex + 3 * ey + 9 * ez];
+    if (base == 0xFFFFFFFFu)
+      return;
+    const int oi = ex == 1 ? i - 1 : 0, oj = ey == 1 ? j - 1 : 0, ok = ez == 1 ? k - 1 : 0;
+    const int sx = ex == 1 ? p - 1 : 1, sy = ey == 1 ? p - 1 : 1;
+    const int pos = oi + sx * (oj + sy * ok);
+    const double *x = gll, *w = gll + N, *Dg = gll + 2 * N;
+    const double *cf = coef + cell * 24;
+    double        s = 0., g00, g01, g02, g11, g12, g22;
+    for (int q = 0; q < N; ++q)
+      {
+        const double dx = Dg[i * N + q], dy = Dg[j * N + q], dz = Dg[k * N + q];
+        metric_at(cf, x[q], x[j], x[k], w[q] * w[j] * w[k], g00, g01, g02, g11, g12, g22);
+        s += dx * dx * g00;
+        metric_at(cf, x[i], x[q], x[k], w[i] * w[q] * w[k], g00, g01, g02, g11, g12, g22);
+        s += dy * dy * g11;
+        metric_at(cf, x[i], x[j], x[q], w[i] * w[j] * w[q], g00, g01, g02, g11, g12, g22);
+        s += dz * dz * g22;
+      }
+    metric_at(cf, x[i], x[j], x[k], w[i] * w[j] * w[k], g00, g01, g02, g11, g12, g22);
+    const double di = Dg[i * N + i], dj = Dg[j * N + j], dk = Dg[k * N + k];
+    s += 2. * (di * dj * g01 + di * dk * g02 + dj * dk * g12);
+    atomicAdd(diag + (size_t)base / 3 + pos, s);
+  }
+
+  __global__ void __launch_bounds__(256) invert_diag_kernel(const uint64_t n, double *d)
+  {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+      d[i] = d[i] == 0. ? 1. : 1. / d[i];
+  }
+
+  // ---------------------------------------------------------------------------------------
+  // launchers
+  // ---------------------------------------------------------------------------------------
+  static inline int stream_grid(uint64_t n, int sms)
+  {
+    const uint64_t blocks = (n + 255) / 256;
+    return (int)std::min<uint64_t>(std::max<uint64_t>(blocks, 1), (uint64_t)sms * 8);
+  }
+
+  template <int P>
+  static cudaError_t init_degree(std::vector<uint32_t> &walk)
+  {
+    Tab<P> tb;
+    fill_tab<P>(tb);
+    walk.resize(Geom<P>::N3);
+    build_walk<P>(walk.data());
+    cudaError_t e = cudaMemcpyToSymbol(c_tab<P>, &tb, sizeof(tb));
+    if (e != cudaSuccess)
+      return e;
+    constexpr int CPB = Cfg<P>::CPB;
+    return cudaFuncSetAttribute(cell_kernel_plain<P, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(CellSmem<P, CPB>));
+  }
+
+  template <int P>
+  static cudaError_t run_cell_plain(const CellArgs &a, int sms, cudaStream_t st)
+  {
+    constexpr int  CPB       = Cfg<P>::CPB;
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms);
+    if (grid == 0)
+      return cudaSuccess;
+    cell_kernel_plain<P, CPB><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
+    return cudaGetLastError();
+  }
+
+#define BP4_DISPATCH(p, CALL)                    \
+  switch (p)                                     \
+    {                                            \
+      case 2: { constexpr int P = 2; CALL; } break; \
+      case 3: { constexpr int P = 3; CALL; } break; \
+      case 4: { constexpr int P = 4; CALL; } break; \
+      case 5: { constexpr int P = 5; CALL; } break; \
+      case 6: { constexpr int P = 6; CALL; } break; \
+      case 7: { constexpr int P = 7; CALL; } break; \
+      case 8: { constexpr int P = 8; CALL; } break; \
+      default: return cudaErrorInvalidValue;     \
+    }
+
+  cudaError_t launch_init_degree(int degree, std::vector<uint32_t> &walk)
+  {
+    BP4_DISPATCH(degree, return init_degree<P>(walk));
+    return cudaSuccess;
+  }
+
+  cudaError_t launch_cell_plain(int degree, const CellArgs &a, int sms, cudaStream_t st)
+  {
+    BP4_DISPATCH(degree, return run_cell_plain<P>(a, sms, st));
+    return cudaSuccess;
+  }
+
+  int cells_per_block(int degree)
+  {
+    switch (degree)
+      {
+        case 2: return Cfg<2>::CPB;
+        case 3: return Cfg<3>::CPB;
+        case 4: return Cfg<4>::CPB;
+        case 5: return Cfg<5>::CPB;
+        case 6: return Cfg<6>::CPB;
+        case 7: return Cfg<7>::CPB;
+        case 8: return Cfg<8>::CPB;
+      }
+    return 0;
+  }
+
+  cudaError_t launch_pre(uint64_t n, double *h, double *x, double *r, double *p, const double *prec,
+                         double alpha, double beta, double alpha_old, double beta_old, int sms,
+                         cudaStream_t st)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    pre_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, h, x, r, p, prec, alpha, beta, alpha_old,
+                                                     beta_old);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_post(uint64_t n, const double *r, const double *d, const double *h,
+                          const double *prec, double *acc, int sms, cudaStream_t st)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    post_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, r, d, h, prec, acc);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_fixup(uint64_t n, const uint32_t *con, double *dst, const double *src,
+                           cudaStream_t st)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    fixup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, con, dst, src);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_sadd(uint64_t n, double *dst, double s, double a, const double *src, int sms,
+                          cudaStream_t st)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    sadd_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, dst, s, a, src);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_dot(uint64_t n, const double *a, const double *b, double *acc, int sms,
+                         cudaStream_t st)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    dot_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, a, b, acc);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_add_and_dot(uint64_t n, double *g, double a, const double *h, const double *w,
+                                 double *acc, int sms, cudaStream_t st)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    add_and_dot_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, g, a, h, w, acc);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_nonzero(uint64_t n, const double *v, int *flag, int sms, cudaStream_t st)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    nonzero_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, v, flag);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_jacobi(uint64_t n, double *dst, const double *src, const double *diag, int sms,
+                            cudaStream_t st)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    jacobi_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, dst, src, diag);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_xfinal(uint64_t n, double *x, const double *d, const double *g, const double *prec,
+                            double c1, double c2, int sms, cudaStream_t st)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    xfinal_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, x, d, g, prec, c1, c2);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_diag(int degree, uint64_t n_cells, const uint32_t *entity_index, const double *coef,
+                          const double *gll, double *diag, uint64_t n_nodes, cudaStream_t st)
+  {
+    const int      N3 = (degree + 1) * (degree + 1) * (degree + 1);
+    const uint64_t n  = n_cells * N3;
+    if (n > 0)
+      diag_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(degree, n_cells, entity_index, coef, gll,
+                                                                diag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return e;
+    if (n_nodes > 0)
+      invert_diag_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, st>>>(n_nodes, diag);
+    return cudaGetLastError();
+  }
+
+  // host table for the diagonal kernel: x[N], w[N], Dg[N][N]
+  void gll_table(int degree, std::vector<double> &out)
+  {
+    const int           N = degree + 1;
+    std::vector<double> x, w;
+    gauss_lobatto_01(N, x, w);
+    out.assign(2 * N + N * N, 0.);
+    for (int i = 0; i < N; ++i)
+      {
+        out[i]     = x[i];
+        out[N + i] = w[i];
+        for (int q = 0; q < N; ++q)
+          out[2 * N + i * N + q] = lagrange_deriv(x, i, x[q]);
+      }
+  }
+} // namespace bp4

@@ -1,0 +1,149 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/bp4.h) against the CPU
+oracle on the same inputs.  Tolerances are BASELINE.json north_star's: operator apply
+rel-L2 <= 1e-12, CG iteration count +-1, solution rel diff <= 1e-8."""
+import numpy as np
+import pytest
+
+from oracle import bp4_oracle as O
+
+from helpers import gpu_cg_merged, gpu_cg_plain, make_ctx, rel_l2, single
+
+pytestmark = pytest.mark.gpu
+
+VMULT_CASES = [(2, 3), (2, 7), (3, 3), (3, 6), (3, 10), (4, 4), (4, 9), (4, 11), (5, 5), (5, 7), (6, 3),
+               (6, 8), (7, 4), (7, 6), (8, 3), (8, 7)]
+
+
+@pytest.mark.parametrize("p,s", VMULT_CASES)
+def test_vmult_matches_oracle(p, s, bp4_lib, c_oracle_lib):
+    rd, co = single(p, s)
+    ctx = make_ctx(rd)
+    rng = np.random.default_rng(100 * p + s)
+    v = rng.standard_normal(rd.n_owned)
+    src, dst = ctx.vector(data=v), ctx.vector()
+    ctx.vmult(dst, src)
+    got = dst.download()
+    want = co.vmult(v)
+    assert rel_l2(got, want) <= 1e-12
+    # constrained rows are the identity (poisson_operator.h:311-312)
+    assert np.array_equal(got[rd.constrained], v[rd.constrained])
+    ctx.close()
+
+
+def test_vmult_zero_and_linearity(bp4_lib):
+    rd, co = single(4, 6)
+    ctx = make_ctx(rd)
+    rng = np.random.default_rng(1)
+    a, b = rng.standard_normal(rd.n_owned), rng.standard_normal(rd.n_owned)
+    va, vb, vab, out = ctx.vector(data=a), ctx.vector(data=b), ctx.vector(data=2 * a - 3 * b), ctx.vector()
+    ctx.vmult(out, va)
+    ya = out.download()
+    ctx.vmult(out, vb)
+    yb = out.download()
+    ctx.vmult(out, vab)
+    yab = out.download()
+    assert rel_l2(yab, 2 * ya - 3 * yb) <= 1e-12
+    z = ctx.vector()
+    ctx.vmult(out, z)
+    assert not out.download().any()
+    # symmetry u^T A v = v^T A u
+    assert abs(a @ yb - b @ ya) <= 1e-11 * abs(a @ yb)
+    ctx.close()
+
+
+@pytest.mark.parametrize("p,s", [(2, 6), (3, 6), (4, 6), (5, 4), (6, 5), (8, 3)])
+def test_inverse_diagonal(p, s, bp4_lib):
+    rd, _ = single(p, s)
+    ctx = make_ctx(rd)
+    got = ctx.inverse_diagonal().download()
+    want = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    assert rel_l2(got, want) <= 1e-12
+    ctx.close()
+
+
+def test_blas1(bp4_lib):
+    rd, _ = single(3, 6)
+    ctx = make_ctx(rd)
+    n = rd.n_owned
+    rng = np.random.default_rng(7)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    va, vb, vc = ctx.vector(data=a), ctx.vector(data=b), ctx.vector()
+    assert abs(ctx.dot(va, vb) - a @ b) <= 1e-12 * np.linalg.norm(a) * np.linalg.norm(b)
+    assert abs(ctx.l2_norm(va) - np.linalg.norm(a)) <= 1e-13 * np.linalg.norm(a)
+    ctx.equ(vc, -1.5, va)
+    assert np.array_equal(vc.download(), -1.5 * a)
+    ctx.add(vc, 0.25, vb)
+    np.testing.assert_allclose(vc.download(), -1.5 * a + 0.25 * b, rtol=1e-15, atol=1e-15)
+    ctx.sadd(vc, 2.0, -1.0, va)
+    np.testing.assert_allclose(vc.download(), 2.0 * (-1.5 * a + 0.25 * b) - a, rtol=1e-14, atol=1e-14)
+    assert ctx.all_zero(ctx.vector()) and not ctx.all_zero(va)
+    g = ctx.vector(data=a)
+    r = ctx.add_and_dot(g, 0.5, vb, g)
+    assert abs(r - (a + 0.5 * b) @ (a + 0.5 * b)) <= 1e-12 * r
+    np.testing.assert_allclose(g.download(), a + 0.5 * b, rtol=1e-15, atol=1e-15)
+    diag = rng.standard_normal(n // 3)
+    vd = ctx.vector(n // 3, data=diag)
+    ctx.jacobi_vmult(vc, va, vd)
+    np.testing.assert_allclose(vc.download(), np.repeat(diag, 3) * a, rtol=1e-15)
+    ctx.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("p,s", [(3, 6), (4, 7), (6, 4)])
+def test_merged_sums_match_oracle(p, s, variant, bp4_lib, c_oracle_lib):
+    """one vmult_with_merged_sums call in each of the three do_cg_update4b regimes"""
+    rd, co = single(p, s)
+    ctx = make_ctx(rd)
+    ctx.set_merged_variant(variant)
+    n = rd.n_owned
+    rng = np.random.default_rng(3)
+    free = np.ones(n)
+    free[rd.constrained] = 0.0
+    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    prec3 = np.repeat(prec, 3)
+    vp = ctx.vector(n // 3, data=prec)
+    for (alpha, beta, alpha_old, beta_old) in [(0.0, 0.0, 0.0, 0.0), (0.7, 0.3, 0.0, 0.2), (0.7, 0.3, 0.4, 0.2)]:
+        x, g, d, h = (rng.standard_normal(n) * free for _ in range(4))
+        vx, vg, vd, vh = (ctx.vector(data=a) for a in (x, g, d, h))
+        S = ctx.vmult_merged(vx, vg, vd, vh, vp, alpha, beta, alpha_old, beta_old)
+        O.cg_update4b(h, x, g, d, prec3, alpha, beta, alpha_old, beta_old)
+        h[:] = co.vmult_cells(d)
+        want = O.cg_update3b(g, d, h, prec3)
+        np.testing.assert_allclose(S, want, rtol=1e-11)
+        for got, ref in ((vx, x), (vg, g), (vd, d), (vh, h)):
+            assert rel_l2(got.download(), ref) <= 1e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("p,s", [(3, 6), (4, 6), (2, 9)])
+def test_cg_merged_parity(p, s, variant, bp4_lib, c_oracle_lib):
+    rd, co = single(p, s)
+    ctx = make_ctx(rd)
+    ctx.set_merged_variant(variant)
+    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    vp = ctx.vector(rd.n_owned // 3, data=prec)
+    for reduce in (1e-8, 1e-10):
+        ctl = O.ReductionControl(100, 1e-15, reduce)
+        x = gpu_cg_merged(ctx, rd.rhs, vp, ctl).download()
+        xo, ito, hist = co.cg(rd.rhs, prec, merged=True, reduce=reduce)
+        assert abs(ctl.last_step - ito) <= 1
+        if ito < 100:
+            assert rel_l2(x, xo) <= 1e-8
+        else:
+            assert rel_l2(x, xo) <= 1e-6
+    ctx.close()
+
+
+@pytest.mark.parametrize("p,s", [(3, 6), (4, 6)])
+def test_cg_plain_parity(p, s, bp4_lib, c_oracle_lib):
+    rd, co = single(p, s)
+    ctx = make_ctx(rd)
+    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    vp = ctx.vector(rd.n_owned // 3, data=prec)
+    ctl = O.ReductionControl(100, 1e-15, 1e-8)
+    x = gpu_cg_plain(ctx, rd.rhs, vp, ctl).download()
+    xo, ito, hist = co.cg(rd.rhs, prec, merged=False)
+    assert abs(ctl.last_step - ito) <= 1
+    assert rel_l2(x, xo) <= (1e-8 if ito < 100 else 1e-6)
+    ctx.close()
