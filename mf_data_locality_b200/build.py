@@ -49,18 +49,29 @@ def build_cuda(force=False, verbose=False):
 
 
 def build_host(force=False):
-    if not os.path.isdir(HOST):
-        return None
-    srcs = _sources(HOST, (".cc",))
-    if not srcs:
-        return None
-    deps = _sources(HOST, (".cc", ".h")) + [os.path.join(ROOT, "include", "bp4.h")]
-    if not force and not _newer(HOSTLIB, deps):
-        return HOSTLIB
-    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-Wall", "-o", HOSTLIB] + srcs + \
-          ["-I", os.path.join(ROOT, "include"), "-L", HERE, "-lbp4", "-Wl,-rpath,$ORIGIN"]
-    subprocess.check_call(cmd)
-    return HOSTLIB
+    """the C++ host mirror: one shared library per run_cg_solver plugin + the two CLI executables"""
+    inc = os.path.join(ROOT, "include")
+    deps = _sources(HOST, (".cc", ".h")) + [os.path.join(inc, "bp4.h"),
+                                            os.path.join(HERE, "benchmark_precond", "bench.cc"),
+                                            os.path.join(HERE, "benchmark_precond_merged", "bench.cc")]
+    common = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-I", inc]
+    link = ["-L", HERE, "-lbp4", "-Wl,-rpath,$ORIGIN"]
+    outs = []
+    jobs = []
+    for name, macro, plug in (("plain", [], "benchmark_precond"), ("merged", ["-DBP4_PLUGIN_MERGED"], "benchmark_precond_merged")):
+        lib = os.path.join(HERE, f"libbp4_host_{name}.so")
+        exe = os.path.join(HERE, plug, "bench")
+        outs += [lib, exe]
+        if force or _newer(lib, deps):
+            jobs.append(common + macro + ["-shared", "-o", lib, os.path.join(HOST, "host_capi.cc")] + link)
+        if force or _newer(exe, deps):
+            jobs.append(common + ["-o", exe, os.path.join(HERE, plug, "bench.cc")] +
+                        ["-L", HERE, "-lbp4", "-Wl,-rpath,$ORIGIN/.."])
+    procs = [(j, subprocess.Popen(j)) for j in jobs]
+    for j, p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("host build failed: " + " ".join(j))
+    return outs
 
 
 def build_all(force=False, verbose=False):

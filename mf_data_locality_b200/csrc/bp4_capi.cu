@@ -75,7 +75,9 @@ struct bp4_ctx
   int         *d_flag = nullptr;
   double      *h_acc  = nullptr; // pinned [8]
   int         *h_flag = nullptr; // pinned
-  int          merged_variant = 0;
+  int          merged_variant = 1;
+  uint8_t     *d_meta = nullptr;     // fused kernel: per-cell entity meta bytes [n_cells][28]
+  uint32_t    *d_counters = nullptr; // fused kernel: arrival counters [n_nodes]
   // multi-GPU
   ncclComm_t            comm = nullptr;
   int                   rank = 0, n_ranks = 1;
@@ -277,6 +279,8 @@ int bp4_ctx_destroy(bp4_ctx *c)
   cudaFree(c->d_gll);
   cudaFree(c->d_acc);
   cudaFree(c->d_flag);
+  cudaFree(c->d_meta);
+  cudaFree(c->d_counters);
   cudaFree(c->d_export);
   cudaFree(c->d_sendbuf);
   cudaFree(c->d_recvbuf);
@@ -394,7 +398,7 @@ static int cell_loop(bp4_ctx *c, double *dst, const double *src, bool zero_dst)
   bp4::CellArgs a;
   a.entity_index = c->d_entity;
   a.coef         = c->d_coef;
-  a.walk         = c->d_walk;
+  a.dtab         = c->d_walk;
   a.n_cells      = c->n_cells;
   a.src          = src;
   a.dst          = dst;
@@ -450,6 +454,56 @@ int bp4_vmult_merged(bp4_ctx *c, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h,
   if (!prec || prec->n < c->n_owned / 3)
     return fail(BP4_ERR_ARG, "prec needs n_owned/3 entries");
   const uint64_t n = c->n_owned;
+  if (c->merged_variant == 1 && c->n_ghost == 0)
+    {
+      // single fused kernel; g, d, h ping-pong between two buffers each
+      if (!c->d_meta)
+        {
+          const uint64_t n_nodes = n / 3 ? n / 3 : 1;
+          uint32_t      *owner   = nullptr;
+          CU(cudaMalloc(&c->d_meta, 28 * (c->n_cells ? c->n_cells : 1)));
+          CU(cudaMalloc(&c->d_counters, sizeof(uint32_t) * n_nodes));
+          CU(cudaMalloc(&owner, sizeof(uint32_t) * n_nodes));
+          c->launches += 2;
+          CU(bp4::launch_build_meta(c->n_cells, n_nodes, c->d_entity, c->d_counters, owner, c->d_meta,
+                                    c->stream));
+          CU(cudaStreamSynchronize(c->stream));
+          CU(cudaFree(owner));
+        }
+      for (bp4_vec *v : {g, d, h})
+        if (int e = ensure_second(c, v))
+          return e;
+      CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 7, c->stream));
+      bp4::MergedArgs a;
+      a.entity_index = c->d_entity;
+      a.coef         = c->d_coef;
+      a.dtab         = c->d_walk;
+      a.meta         = c->d_meta;
+      a.counters     = c->d_counters;
+      a.n_cells      = c->n_cells;
+      a.r_old        = g->buf[g->cur];
+      a.p_old        = d->buf[d->cur];
+      a.h_old        = h->buf[h->cur];
+      a.r_new        = g->buf[g->cur ^ 1];
+      a.p_new        = d->buf[d->cur ^ 1];
+      a.h_new        = h->buf[h->cur ^ 1];
+      a.x            = x->p();
+      a.prec         = prec->p();
+      a.alpha        = alpha;
+      a.beta         = beta;
+      a.update_x     = (alpha != 0. && alpha_old != 0.) ? 1 : 0;
+      a.c1           = a.update_x ? alpha + alpha_old / beta_old : 0.;
+      a.c2           = a.update_x ? alpha_old / beta_old : 0.;
+      a.acc          = c->d_acc;
+      {
+        Timed t(c, BP4_K_MERGED);
+        CU(bp4::launch_cell_merged(c->degree, a, c->sms, c->stream));
+      }
+      g->cur ^= 1;
+      d->cur ^= 1;
+      h->cur ^= 1;
+      return reduce_to_host(c, 7, out);
+    }
   // three-kernel variant: pre sweep, cell loop, post sweep
   {
     Timed t(c, BP4_K_PRE);

@@ -54,14 +54,19 @@ namespace bp4
     static constexpr int N   = P + 1;
     static constexpr int Q   = P + 2;
     static constexpr int N3  = N * N * N;
-    static constexpr int DOF = 3 * N3;             // staged cell DoFs   [c][k][j][i]
-    // work[c][a][qz][j][qx], a = 0 value, 1 xi-derivative/flux, 2 zeta-derivative/flux
-    static constexpr int WJ  = Q;                  // stride of j
-    static constexpr int WZ  = N * Q;              // stride of qz
-    static constexpr int WA  = Q * N * Q;          // stride of a
-    static constexpr int WC  = 3 * WA;             // stride of c
-    static constexpr int WORK = 3 * WC;
-    static constexpr int ITEMS13 = 3 * N;          // phase 1/3 items per cell
+    static constexpr int ROWS = 3 * N;             // rows (c, j) per cell = phase 1/3 items
+    // Both staging arrays are organised as one row per phase-1/3 item (cell, c, j) with an
+    // ODD row stride: consecutive lanes of phase 1/3 then hit an arithmetic progression with
+    // odd stride (a bijection modulo the 16 eight-byte banks) and the (qz, qx) lanes of
+    // phase 2 hit consecutive addresses -> no shared-memory bank conflicts in any phase.
+    //   dofs[row][k][i]            staged cell DoFs
+    //   work[row][a][qz][qx]       a = 0 value, 1 xi-derivative/flux, 2 zeta-derivative/flux
+    static constexpr int RD  = (N * N) | 1;
+    static constexpr int RW  = (3 * Q * Q) | 1;
+    static constexpr int DOF = 3 * N3;             // DoFs of a cell
+    static constexpr int DOFS = ROWS * RD;         // doubles of the dofs staging per cell
+    static constexpr int WORK = ROWS * RW;         // doubles of the work staging per cell
+    static constexpr int ITEMS13 = ROWS;           // phase 1/3 items per cell
     static constexpr int ITEMS2  = Q * Q;          // phase 2 items per cell
   };
 
@@ -72,9 +77,11 @@ namespace bp4
     return i == 0 ? 0 : (i == P ? 2 : 1);
   }
 
-  // packed (lexicographic node | entity << 10 | position-in-entity << 15) of the w-th node
-  // in entity-major order; entity a = ex + 3 ey + 9 ez, nodes lexicographic inside the
-  // entity (vector_access_reduced.h:176-258: idx[a] + 3 * position + component)
+  // w-th node of a cell in entity-major order (entity a = ex + 3 ey + 9 ez ascending, nodes
+  // lexicographic inside the entity: vector_access_reduced.h:176-258 addresses node `pos` of
+  // entity a at idx[a] + 3 * pos + component), packed as
+  //   bits 0-6  k*N+i (position inside the staging row) | bits 7-10 j (row) |
+  //   bits 11-15 entity | bits 16-31 pos
   template <int P>
   inline void build_walk(uint32_t *walk)
   {
@@ -93,19 +100,45 @@ namespace bp4
         for (int k = lo[2]; k < hi[2]; ++k)
           for (int j = lo[1]; j < hi[1]; ++j)
             for (int i = lo[0]; i < hi[0]; ++i, ++pos, ++w)
-              walk[w] = uint32_t((k * N + j) * N + i) | (uint32_t(a) << 10) | (uint32_t(pos) << 15);
+              walk[w] = uint32_t(k * N + i) | (uint32_t(j) << 7) | (uint32_t(a) << 11) | (uint32_t(pos) << 16);
       }
   }
+  BP4_HD uint32_t walk_inrow(uint32_t pk) { return pk & 127u; }
+  BP4_HD uint32_t walk_j(uint32_t pk) { return (pk >> 7) & 15u; }
+  BP4_HD uint32_t walk_ent(uint32_t pk) { return (pk >> 11) & 31u; }
+  BP4_HD uint32_t walk_pos(uint32_t pk) { return pk >> 16; }
+  // staging offset of (component c, walk entry pk) inside a cell's dofs block
+  template <int P>
+  BP4_HD uint32_t dofs_offset(uint32_t pk, int c)
+  {
+    return (uint32_t(c) * Geom<P>::N + walk_j(pk)) * Geom<P>::RD + walk_inrow(pk);
+  }
+
+  // per-DoF gather/scatter table of a cell, r = 3 w + c in entity-major order (consecutive r
+  // = consecutive addresses inside an entity's segment):
+  //   bits 0-11 offset in the cell's dofs staging | bits 12-16 entity | bits 17-31 3*pos + c
+  template <int P>
+  inline void build_dof_table(uint32_t *tab)
+  {
+    uint32_t walk[Geom<P>::N3];
+    build_walk<P>(walk);
+    for (int w = 0; w < Geom<P>::N3; ++w)
+      for (int c = 0; c < 3; ++c)
+        tab[3 * w + c] = dofs_offset<P>(walk[w], c) | (walk_ent(walk[w]) << 12) |
+                         ((3u * walk_pos(walk[w]) + c) << 17);
+  }
+  BP4_HD uint32_t dtab_off(uint32_t t) { return t & 4095u; }
+  BP4_HD uint32_t dtab_ent(uint32_t t) { return (t >> 12) & 31u; }
+  BP4_HD uint32_t dtab_rel(uint32_t t) { return t >> 17; }
 
   // ---------------------------------------------------------------------------------------
-  // phase 1: item = (c, j).  dofs[c][k][j][i] -> work[c][{0,1,2}][qz][j][qx]
+  // phase 1: item = row (c, j).  dofs_row[k][i] -> work_row[{0,1,2}][qz][qx]
   // ---------------------------------------------------------------------------------------
   template <int P>
-  BP4_HD void phase1(const Tab<P> &tb, const double *dofs, double *work, const int c, const int j)
+  BP4_HD void phase1(const Tab<P> &tb, const double *in, double *out)
   {
     using G         = Geom<P>;
     constexpr int N = G::N, Q = G::Q;
-    const double *in = dofs + c * G::N3 + j * N;
     double        t[N][Q];
     BP4_UNROLL
     for (int k = 0; k < N; ++k)
@@ -113,7 +146,7 @@ namespace bp4
         double r[N];
         BP4_UNROLL
         for (int i = 0; i < N; ++i)
-          r[i] = in[k * N * N + i];
+          r[i] = in[k * N + i];
         BP4_UNROLL
         for (int q = 0; q < Q; ++q)
           {
@@ -124,7 +157,6 @@ namespace bp4
             t[k][q] = s;
           }
       }
-    double *out = work + c * G::WC + j * G::WJ;
     BP4_UNROLL
     for (int qz = 0; qz < Q; ++qz)
       {
@@ -150,9 +182,9 @@ namespace bp4
             BP4_UNROLL
             for (int i = 1; i < Q; ++i)
               sx += tb.D[i][q] * u[i];
-            out[0 * G::WA + qz * G::WZ + q] = u[q];
-            out[1 * G::WA + qz * G::WZ + q] = sx;
-            out[2 * G::WA + qz * G::WZ + q] = wz[q];
+            out[0 * Q * Q + qz * Q + q] = u[q];
+            out[1 * Q * Q + qz * Q + q] = sx;
+            out[2 * Q * Q + qz * Q + q] = wz[q];
           }
       }
   }
@@ -169,42 +201,49 @@ namespace bp4
     using G         = Geom<P>;
     constexpr int N = G::N, Q = G::Q;
     double        gr[3][3][Q]; // [c][direction][qy]
-    double       *base = work + qz * G::WZ + qx;
+    double       *base = work + qz * Q + qx; // work = first row of the cell
+    // y-interpolation of the nine (component, array) lines at once: every S[j][q] is
+    // fetched once (uniform register) and feeds nine consecutive FMAs.  Array a = 0 (value)
+    // is parked in direction slot 1 until its eta-derivative replaces it.
     BP4_UNROLL
-    for (int c = 0; c < 3; ++c)
+    for (int j = 0; j < N; ++j)
       {
+        double r[3][3];
         BP4_UNROLL
+        for (int c = 0; c < 3; ++c)
+          BP4_UNROLL
         for (int a = 0; a < 3; ++a)
-          {
-            double r[N];
-            BP4_UNROLL
-            for (int j = 0; j < N; ++j)
-              r[j] = base[c * G::WC + a * G::WA + j * G::WJ];
-            BP4_UNROLL
-            for (int q = 0; q < Q; ++q)
-              {
-                double s = tb.S[0][q] * r[0];
-                BP4_UNROLL
-                for (int j = 1; j < N; ++j)
-                  s += tb.S[j][q] * r[j];
-                gr[c][a == 0 ? 1 : (a == 1 ? 0 : 2)][q] = s; // a=0: value, parked in slot 1
-              }
-          }
-        // d/deta from the values parked in slot 1
-        double v[Q];
-        BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          v[q] = gr[c][1][q];
+          r[c][a == 0 ? 1 : (a == 1 ? 0 : 2)] = base[(c * N + j) * G::RW + a * Q * Q];
         BP4_UNROLL
         for (int q = 0; q < Q; ++q)
           {
-            double s = tb.D[0][q] * v[0];
+            const double sjq = tb.S[j][q];
             BP4_UNROLL
-            for (int i = 1; i < Q; ++i)
-              s += tb.D[i][q] * v[i];
-            gr[c][1][q] = s;
+            for (int c = 0; c < 3; ++c)
+              BP4_UNROLL
+            for (int e = 0; e < 3; ++e)
+              gr[c][e][q] = j == 0 ? sjq * r[c][e] : gr[c][e][q] + sjq * r[c][e];
           }
       }
+    // d/deta of the three components
+    {
+      double v[3][Q];
+      BP4_UNROLL
+      for (int c = 0; c < 3; ++c)
+        BP4_UNROLL
+      for (int q = 0; q < Q; ++q)
+        v[c][q] = gr[c][1][q];
+      BP4_UNROLL
+      for (int i = 0; i < Q; ++i)
+        BP4_UNROLL
+      for (int q = 0; q < Q; ++q)
+        {
+          const double d = tb.D[i][q];
+          BP4_UNROLL
+          for (int c = 0; c < 3; ++c)
+            gr[c][1][q] = i == 0 ? d * v[c][0] : gr[c][1][q] + d * v[c][i];
+        }
+    }
     // geometry along the line: rows of dX/dxi_e (poisson_operator.h:577-602)
     //   r0 = dX/dxi   = (v1 + z v10) + y (v4 + z v13)
     //   r1 = dX/deta  = (v3 + z v12) + x (v4 + z v13)      (constant along the line)
@@ -262,45 +301,56 @@ namespace bp4
             gr[c][2][q] = g02 * a + g12 * b + g22 * e;
           }
       }
-    // integrate: d/deta^T on the eta-flux, then y-back-interpolation of the three arrays
+    // integrate: d/deta^T on the eta-flux (result parked in slot 1 = "value" array), then
+    // y-back-interpolation of the nine lines, again with each matrix entry used nine times
+    {
+      double v[3][Q];
+      BP4_UNROLL
+      for (int q = 0; q < Q; ++q)
+        BP4_UNROLL
+      for (int i = 0; i < Q; ++i)
+        {
+          const double d = tb.D[i][q];
+          BP4_UNROLL
+          for (int c = 0; c < 3; ++c)
+            v[c][i] = q == 0 ? d * gr[c][1][0] : v[c][i] + d * gr[c][1][q];
+        }
+      BP4_UNROLL
+      for (int c = 0; c < 3; ++c)
+        BP4_UNROLL
+      for (int q = 0; q < Q; ++q)
+        gr[c][1][q] = v[c][q];
+    }
     BP4_UNROLL
-    for (int c = 0; c < 3; ++c)
+    for (int j = 0; j < N; ++j)
       {
-        double v[Q];
+        double acc[3][3];
         BP4_UNROLL
-        for (int i = 0; i < Q; ++i)
+        for (int q = 0; q < Q; ++q)
           {
-            double s = tb.D[i][0] * gr[c][1][0];
+            const double sjq = tb.S[j][q];
             BP4_UNROLL
-            for (int q = 1; q < Q; ++q)
-              s += tb.D[i][q] * gr[c][1][q];
-            v[i] = s;
+            for (int c = 0; c < 3; ++c)
+              BP4_UNROLL
+            for (int e = 0; e < 3; ++e)
+              acc[c][e] = q == 0 ? sjq * gr[c][e][0] : acc[c][e] + sjq * gr[c][e][q];
           }
         BP4_UNROLL
+        for (int c = 0; c < 3; ++c)
+          BP4_UNROLL
         for (int a = 0; a < 3; ++a)
-          {
-            BP4_UNROLL
-            for (int j = 0; j < N; ++j)
-              {
-                double s = 0.;
-                BP4_UNROLL
-                for (int q = 0; q < Q; ++q)
-                  s += tb.S[j][q] * (a == 0 ? v[q] : (a == 1 ? gr[c][0][q] : gr[c][2][q]));
-                base[c * G::WC + a * G::WA + j * G::WJ] = s;
-              }
-          }
+          base[(c * N + j) * G::RW + a * Q * Q] = acc[c][a == 0 ? 1 : (a == 1 ? 0 : 2)];
       }
   }
 
   // ---------------------------------------------------------------------------------------
-  // phase 3: item = (c, j).  work[c][{0,1,2}][qz][j][qx] -> dofs[c][k][j][i]
+  // phase 3: item = row (c, j).  work_row[{0,1,2}][qz][qx] -> dofs_row[k][i]
   // ---------------------------------------------------------------------------------------
   template <int P>
-  BP4_HD void phase3(const Tab<P> &tb, const double *work, double *dofs, const int c, const int j)
+  BP4_HD void phase3(const Tab<P> &tb, const double *in, double *out)
   {
     using G         = Geom<P>;
     constexpr int N = G::N, Q = G::Q;
-    const double *in = work + c * G::WC + j * G::WJ;
     double        t[N][Q];
     BP4_UNROLL
     for (int k = 0; k < N; ++k)
@@ -314,9 +364,9 @@ namespace bp4
         BP4_UNROLL
         for (int q = 0; q < Q; ++q)
           {
-            v[q]  = in[0 * G::WA + qz * G::WZ + q];
-            fx[q] = in[1 * G::WA + qz * G::WZ + q];
-            fz[q] = in[2 * G::WA + qz * G::WZ + q];
+            v[q]  = in[0 * Q * Q + qz * Q + q];
+            fx[q] = in[1 * Q * Q + qz * Q + q];
+            fz[q] = in[2 * Q * Q + qz * Q + q];
           }
         BP4_UNROLL
         for (int i = 0; i < Q; ++i)
@@ -333,7 +383,6 @@ namespace bp4
         for (int q = 0; q < Q; ++q)
           t[k][q] += tb.S[k][qz] * v[q] + tb.Dn[k][qz] * fz[q];
       }
-    double *out = dofs + c * G::N3 + j * N;
     BP4_UNROLL
     for (int k = 0; k < N; ++k)
       BP4_UNROLL
@@ -343,7 +392,7 @@ namespace bp4
         BP4_UNROLL
         for (int q = 1; q < Q; ++q)
           s += tb.S[i][q] * t[k][q];
-        out[k * N * N + i] = s;
+        out[k * N + i] = s;
       }
   }
 } // namespace bp4

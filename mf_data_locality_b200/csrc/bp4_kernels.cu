@@ -14,25 +14,55 @@ namespace bp4
   __constant__ Tab<P> c_tab;
 
   // ---------------------------------------------------------------------------------------
-  // cell kernel
+  // cell kernels
   // ---------------------------------------------------------------------------------------
+  constexpr int kGatherUnroll = 4;
+  constexpr int kPlainUnroll  = 9;
+
   template <int P, int CPB>
-  __global__ void __launch_bounds__(kThreads, 1) cell_kernel_plain(const CellArgs a)
+  __device__ __forceinline__ void load_tables(CellSmem<P, CPB> &sm, const uint32_t *dtab)
   {
-    using G         = Geom<P>;
-    constexpr int N3 = G::N3, Q = G::Q, N = G::N;
+    for (int i = threadIdx.x; i < Geom<P>::DOF; i += kThreads)
+      sm.dtab[i] = dtab[i];
+    if (threadIdx.x < Geom<P>::Q)
+      {
+        sm.xq[threadIdx.x] = c_tab<P>.xq[threadIdx.x];
+        sm.wq[threadIdx.x] = c_tab<P>.wq[threadIdx.x];
+      }
+  }
+
+  // phases 1-3 on the nc cells staged in sm.dofs (in place), with the barriers between them
+  template <int P, int CPB>
+  __device__ __forceinline__ void apply_staged(CellSmem<P, CPB> &sm, const int nc)
+  {
+    using G          = Geom<P>;
+    constexpr int Q  = G::Q;
+    const Tab<P> &tb = c_tab<P>;
+    const int     tid = threadIdx.x;
+    for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+      phase1<P>(tb, sm.dofs + it * G::RD, sm.work + it * G::RW);
+    __syncthreads();
+    for (int it = tid; it < nc * G::ITEMS2; it += kThreads)
+      {
+        const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
+        const int qz = r / Q, qx = r % Q;
+        phase2<P>(tb, sm.coef[cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
+                  sm.wq[qx] * sm.wq[qz]);
+      }
+    __syncthreads();
+    for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+      phase3<P>(tb, sm.work + it * G::RW, sm.dofs + it * G::RD);
+    __syncthreads();
+  }
+
+  template <int P, int CPB>
+  __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_plain(const CellArgs a)
+  {
+    using G = Geom<P>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
     const int         tid = threadIdx.x;
-    const Tab<P>     &tb  = c_tab<P>;
-
-    for (int i = tid; i < N3; i += kThreads)
-      sm.walk[i] = a.walk[i];
-    if (tid < Q)
-      {
-        sm.xq[tid] = tb.xq[tid];
-        sm.wq[tid] = tb.wq[tid];
-      }
+    load_tables<P, CPB>(sm, a.dtab);
 
     const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
     for (uint64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x)
@@ -45,69 +75,64 @@ namespace bp4
           sm.coef[i / 24][i % 24] = a.coef[cell0 * 24 + i];
         __syncthreads();
 
-        // gather (vector_access_reduced.h:175-258): coalesced along each entity segment
-        for (int m = tid; m < nc * G::DOF; m += kThreads)
+        // gather (vector_access_reduced.h:175-258): consecutive threads walk an entity's
+        // contiguous DoF segment; kPlainUnroll independent loads in flight per thread
+        const int total = nc * G::DOF;
+        for (int m0 = tid; m0 < total; m0 += kThreads * kPlainUnroll)
           {
-            const int      cell = m / G::DOF, r = m % G::DOF;
-            const int      w = r / 3, c = r % 3;
-            const uint32_t pk   = sm.walk[w];
-            const uint32_t base = sm.eidx[cell][(pk >> 10) & 31u];
-            double         v    = 0.;
-            if (base != 0xFFFFFFFFu)
-              v = __ldg(a.src + (size_t)base + 3u * (pk >> 15) + c);
-            sm.dofs[cell][c * N3 + (pk & 1023u)] = v;
-          }
-        __syncthreads();
-
-        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-          {
-            const int cell = it / G::ITEMS13, r = it % G::ITEMS13;
-            phase1<P>(tb, sm.dofs[cell], sm.work[cell], r / N, r % N);
-          }
-        __syncthreads();
-
-        for (int it = tid; it < nc * G::ITEMS2; it += kThreads)
-          {
-            const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
-            const int qz = r / Q, qx = r % Q;
-            phase2<P>(tb, sm.coef[cell], sm.work[cell], qx, qz, sm.xq[qx], sm.xq[qz],
-                      sm.wq[qx] * sm.wq[qz]);
-          }
-        __syncthreads();
-
-        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-          {
-            const int cell = it / G::ITEMS13, r = it % G::ITEMS13;
-            phase3<P>(tb, sm.work[cell], sm.dofs[cell], r / N, r % N);
-          }
-        __syncthreads();
-
-        // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13)
-        // is touched by this cell only -> plain store
-        for (int m = tid; m < nc * G::DOF; m += kThreads)
-          {
-            const int      cell = m / G::DOF, r = m % G::DOF;
-            const int      w = r / 3, c = r % 3;
-            const uint32_t pk   = sm.walk[w];
-            const uint32_t ent  = (pk >> 10) & 31u;
-            const uint32_t base = sm.eidx[cell][ent];
-            if (base != 0xFFFFFFFFu)
+            double   v[kPlainUnroll];
+            uint32_t off[kPlainUnroll];
+#pragma unroll
+            for (int u = 0; u < kPlainUnroll; ++u)
               {
-                const double v = sm.dofs[cell][c * N3 + (pk & 1023u)];
-                double      *p = a.dst + (size_t)base + 3u * (pk >> 15) + c;
-                if (ent == 13u)
-                  *p = v;
-                else
-                  atomicAdd(p, v);
+                const int m = m0 + u * kThreads;
+                v[u]        = 0.;
+                off[u]      = 0;
+                if (m < total)
+                  {
+                    const int      cell = m / G::DOF;
+                    const uint32_t t    = sm.dtab[m - cell * G::DOF];
+                    const uint32_t base = sm.eidx[cell][dtab_ent(t)];
+                    off[u]              = cell * G::DOFS + dtab_off(t);
+                    if (base != 0xFFFFFFFFu)
+                      v[u] = __ldg(a.src + (size_t)base + dtab_rel(t));
+                  }
+              }
+#pragma unroll
+            for (int u = 0; u < kPlainUnroll; ++u)
+              if (m0 + u * kThreads < total)
+                sm.dofs[off[u]] = v[u];
+          }
+        __syncthreads();
+
+        apply_staged<P, CPB>(sm, nc);
+
+        // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13) is
+        // touched by this cell only -> plain store
+        for (int cell = 0; cell < nc; ++cell)
+          {
+            const uint32_t *eidx = sm.eidx[cell];
+            const double   *dofs = sm.dofs + cell * G::DOFS;
+            for (int r = tid; r < G::DOF; r += kThreads)
+              {
+                const uint32_t t    = sm.dtab[r];
+                const uint32_t ent  = dtab_ent(t);
+                const uint32_t base = eidx[ent];
+                if (base != 0xFFFFFFFFu)
+                  {
+                    const double v = dofs[dtab_off(t)];
+                    double      *p = a.dst + (size_t)base + dtab_rel(t);
+                    if (ent == 13u)
+                      *p = v;
+                    else
+                      atomicAdd(p, v);
+                  }
               }
           }
         __syncthreads();
       }
   }
 
-  // ---------------------------------------------------------------------------------------
-  // streaming kernels
-  // ---------------------------------------------------------------------------------------
   __device__ __forceinline__ double warp_sum(double v)
   {
 #pragma unroll
@@ -144,6 +169,277 @@ namespace bp4
       }
   }
 
+  // the seven merged sums of do_cg_update3b (solver_cg_optimized.h:37-44) for one entry
+  __device__ __forceinline__ void post_terms(double (&s)[7], const double ri, const double di,
+                                             const double hi, const double pr)
+  {
+    const double zi = pr * hi;
+    s[0] += di * hi;
+    s[1] += hi * hi;
+    s[2] += ri * hi;
+    s[3] += ri * ri;
+    s[4] += ri * zi;
+    s[5] += hi * zi;
+    s[6] += ri * pr * ri;
+  }
+
+  // Fused merged kernel = LaplaceOperator::vmult_with_merged_sums (poisson_operator.h:327-377)
+  // in ONE launch.  The reference runs do_cg_update4b on a DoF range "before its first
+  // touch" and do_cg_update3b "after its last touch" of a sequential cell loop; thread blocks
+  // have no such order, so
+  //   pre : every cell recomputes r' = r + alpha h, p' = beta p - P r' for the DoFs it gathers
+  //         from read-only old buffers; the entity's OWNER cell writes r', p' (to the ping-pong
+  //         partners) and x (in place).
+  //   post: cells scatter-add into h'; after a __threadfence each cell bumps one arrival
+  //         counter per shared entity; the cell that completes an entity (last toucher) reads
+  //         h', r', p' back through L2, accumulates the seven sums and zeroes the entity's
+  //         slots in the old h buffer, which is next iteration's h'.  Cell-interior DoFs
+  //         (touched once) are plain-stored and summed straight from shared memory.
+  template <int P, int CPB>
+  __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_merged(const MergedArgs a)
+  {
+    using G = Geom<P>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
+    const int         tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    load_tables<P, CPB>(sm, a.dtab);
+    double     s[7]     = {0., 0., 0., 0., 0., 0., 0.};
+    const bool first_it = a.alpha == 0.;
+
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    for (uint64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x)
+      {
+        const uint64_t cell0 = batch * CPB;
+        const int      nc    = (int)min((uint64_t)CPB, a.n_cells - cell0);
+        for (int i = tid; i < nc * 27; i += kThreads)
+          {
+            sm.eidx[i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
+            sm.meta[i / 27][i % 27] = a.meta[cell0 * 28 + (i / 27) * 28 + i % 27];
+          }
+        for (int i = tid; i < nc * 24; i += kThreads)
+          sm.coef[i / 24][i % 24] = a.coef[cell0 * 24 + i];
+        if (tid == 0)
+          sm.n_chunks = 0;
+        __syncthreads();
+
+        // gather + do_cg_update4b (solver_cg_optimized.h:65-161)
+        for (int cell = 0; cell < nc; ++cell)
+          {
+            const uint32_t *eidx = sm.eidx[cell];
+            const uint8_t  *meta = sm.meta[cell];
+            double         *dofs = sm.dofs + cell * G::DOFS;
+            for (int r0 = tid; r0 < G::DOF; r0 += kThreads * kGatherUnroll)
+              {
+                double   rv[kGatherUnroll], pv[kGatherUnroll], hv[kGatherUnroll], dv[kGatherUnroll];
+                uint32_t t[kGatherUnroll], adr[kGatherUnroll];
+                bool     own[kGatherUnroll];
+#pragma unroll
+                for (int u = 0; u < kGatherUnroll; ++u)
+                  {
+                    const int r = r0 + u * kThreads;
+                    adr[u]      = 0xFFFFFFFFu;
+                    own[u]      = false;
+                    rv[u] = pv[u] = hv[u] = dv[u] = 0.;
+                    if (r < G::DOF)
+                      {
+                        t[u]                = sm.dtab[r];
+                        const uint32_t ent  = dtab_ent(t[u]);
+                        const uint32_t base = eidx[ent];
+                        if (base != 0xFFFFFFFFu)
+                          {
+                            adr[u] = base + dtab_rel(t[u]);
+                            own[u] = (meta[ent] & kMetaOwner) != 0;
+                            rv[u]  = a.r_old[adr[u]];
+                            dv[u]  = a.prec[adr[u] / 3u];
+                            if (!first_it)
+                              {
+                                pv[u] = a.p_old[adr[u]];
+                                hv[u] = a.h_old[adr[u]];
+                              }
+                          }
+                      }
+                  }
+#pragma unroll
+                for (int u = 0; u < kGatherUnroll; ++u)
+                  if (r0 + u * kThreads < G::DOF)
+                    {
+                      double pn = 0.;
+                      if (adr[u] != 0xFFFFFFFFu)
+                        {
+                          const double pr = dv[u];
+                          double       ri = rv[u];
+                          if (own[u] && a.update_x)
+                            a.x[adr[u]] += a.c1 * pv[u] + a.c2 * pr * ri;
+                          if (first_it)
+                            pn = -pr * ri;
+                          else
+                            {
+                              ri += a.alpha * hv[u];
+                              pn = a.beta * pv[u] - pr * ri;
+                            }
+                          if (own[u])
+                            {
+                              a.r_new[adr[u]] = ri;
+                              a.p_new[adr[u]] = pn;
+                            }
+                        }
+                      dofs[dtab_off(t[u])] = pn;
+                    }
+              }
+          }
+        __syncthreads();
+
+        apply_staged<P, CPB>(sm, nc);
+
+        // scatter: shared entities through L2 atomics, the interior entity by plain store
+        // with its do_cg_update3b terms taken on the spot
+        for (int cell = 0; cell < nc; ++cell)
+          {
+            const uint32_t *eidx = sm.eidx[cell];
+            const double   *dofs = sm.dofs + cell * G::DOFS;
+            for (int r0 = tid; r0 < G::DOF; r0 += kThreads * kGatherUnroll)
+              {
+                double rv[kGatherUnroll], pv[kGatherUnroll], dv[kGatherUnroll], hv[kGatherUnroll];
+                bool   inner[kGatherUnroll];
+#pragma unroll
+                for (int u = 0; u < kGatherUnroll; ++u)
+                  {
+                    const int r = r0 + u * kThreads;
+                    inner[u]    = false;
+                    if (r < G::DOF)
+                      {
+                        const uint32_t t    = sm.dtab[r];
+                        const uint32_t ent  = dtab_ent(t);
+                        const uint32_t base = eidx[ent];
+                        if (base != 0xFFFFFFFFu)
+                          {
+                            const double   v   = dofs[dtab_off(t)];
+                            const uint32_t adr = base + dtab_rel(t);
+                            if (ent == 13u)
+                              {
+                                a.h_new[adr] = v;
+                                inner[u]     = true;
+                                hv[u]        = v;
+                                rv[u]        = __ldcg(a.r_new + adr);
+                                pv[u]        = __ldcg(a.p_new + adr);
+                                dv[u]        = a.prec[adr / 3u];
+                              }
+                            else
+                              atomicAdd(a.h_new + adr, v);
+                          }
+                      }
+                  }
+#pragma unroll
+                for (int u = 0; u < kGatherUnroll; ++u)
+                  if (inner[u])
+                    post_terms(s, rv[u], pv[u], hv[u], dv[u]);
+              }
+          }
+        __threadfence();
+        __syncthreads();
+
+        // arrival counters: one per shared entity, wrapping at the number of touching cells
+        for (int i = tid; i < nc * 27; i += kThreads)
+          {
+            const int      cell = i / 27, ent = i % 27;
+            const uint32_t base = sm.eidx[cell][ent];
+            if (ent == 13 || base == 0xFFFFFFFFu)
+              continue;
+            const uint32_t nt   = (sm.meta[cell][ent] & 15u); // touching cells - 1
+            bool           last = true;
+            if (nt > 0)
+              {
+                last = atomicInc(a.counters + base / 3u, nt) == nt;
+                if (last)
+                  __threadfence();
+              }
+            if (last)
+              {
+                const int ex = ent % 3, ey = (ent / 3) % 3, ez = ent / 9;
+                const int nd = 3 * (ex == 1 ? P - 1 : 1) * (ey == 1 ? P - 1 : 1) * (ez == 1 ? P - 1 : 1);
+                const int nch  = (nd + 31) >> 5;
+                const uint32_t slot = atomicAdd(&sm.n_chunks, (uint32_t)nch);
+                for (int k = 0; k < nch; ++k)
+                  {
+                    sm.chunk_base[slot + k] = base + 32u * k;
+                    sm.chunk_len[slot + k]  = (uint8_t)min(32, nd - 32 * k);
+                  }
+              }
+          }
+        __syncthreads();
+
+        // do_cg_update3b (solver_cg_optimized.h:12-61) on the entities completed by this block
+        const int n_chunks = (int)sm.n_chunks;
+        for (int ch0 = warp; ch0 < n_chunks; ch0 += 4 * (kThreads / 32))
+          {
+            double rv[4], pv[4], hv[4], dv[4];
+            bool   ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              {
+                const int ch = ch0 + u * (kThreads / 32);
+                ok[u]        = ch < n_chunks && lane < (int)sm.chunk_len[ch < n_chunks ? ch : 0];
+                if (ok[u])
+                  {
+                    const uint32_t adr = sm.chunk_base[ch] + lane;
+                    hv[u]              = __ldcg(a.h_new + adr);
+                    rv[u]              = __ldcg(a.r_new + adr);
+                    pv[u]              = __ldcg(a.p_new + adr);
+                    dv[u]              = a.prec[adr / 3u];
+                    a.h_old[adr]       = 0.;
+                  }
+              }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (ok[u])
+                post_terms(s, rv[u], pv[u], hv[u], dv[u]);
+          }
+        __syncthreads();
+      }
+    block_accumulate<7>(s, a.acc);
+  }
+
+  // entity meta data of the fused kernel, built on the device from the entity table alone:
+  // touch[first node of entity] = number of local cells holding it, owner = lowest such cell
+  __global__ void __launch_bounds__(256) meta_count_kernel(const uint64_t n_cells,
+                                                           const uint32_t *__restrict__ entity_index,
+                                                           uint32_t *touch, uint32_t *owner)
+  {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells * 27)
+      return;
+    const uint32_t base = entity_index[i];
+    if (base == 0xFFFFFFFFu)
+      return;
+    atomicAdd(touch + base / 3u, 1u);
+    atomicMin(owner + base / 3u, (uint32_t)(i / 27));
+  }
+
+  __global__ void __launch_bounds__(256) meta_fill_kernel(const uint64_t n_cells,
+                                                          const uint32_t *__restrict__ entity_index,
+                                                          const uint32_t *__restrict__ touch,
+                                                          const uint32_t *__restrict__ owner,
+                                                          uint8_t *meta)
+  {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells * 27)
+      return;
+    const uint64_t cell = i / 27;
+    const int      ent  = (int)(i % 27);
+    const uint32_t base = entity_index[i];
+    uint8_t        m    = 0;
+    if (base != 0xFFFFFFFFu)
+      {
+        m = (uint8_t)((touch[base / 3u] - 1u) & 15u);
+        if (owner[base / 3u] == (uint32_t)cell)
+          m |= kMetaOwner;
+      }
+    meta[cell * 28 + ent] = m;
+  }
+
+  // ---------------------------------------------------------------------------------------
+  // streaming kernels
+  // ---------------------------------------------------------------------------------------
   // do_cg_update4b<3,double,true>, solver_cg_optimized.h:65-161, over [0,n)
   __global__ void __launch_bounds__(256) pre_kernel(const uint64_t n, double *__restrict__ h,
                                                     double *__restrict__ x, double *__restrict__ r,
@@ -372,13 +668,17 @@ namespace bp4
   {
     Tab<P> tb;
     fill_tab<P>(tb);
-    walk.resize(Geom<P>::N3);
-    build_walk<P>(walk.data());
+    walk.resize(Geom<P>::DOF);
+    build_dof_table<P>(walk.data());
     cudaError_t e = cudaMemcpyToSymbol(c_tab<P>, &tb, sizeof(tb));
     if (e != cudaSuccess)
       return e;
     constexpr int CPB = Cfg<P>::CPB;
-    return cudaFuncSetAttribute(cell_kernel_plain<P, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(cell_kernel_plain<P, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CellSmem<P, CPB>));
+    if (e != cudaSuccess)
+      return e;
+    return cudaFuncSetAttribute(cell_kernel_merged<P, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(CellSmem<P, CPB>));
   }
 
@@ -387,10 +687,22 @@ namespace bp4
   {
     constexpr int  CPB       = Cfg<P>::CPB;
     const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms);
+    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
     if (grid == 0)
       return cudaSuccess;
     cell_kernel_plain<P, CPB><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
+    return cudaGetLastError();
+  }
+
+  template <int P>
+  static cudaError_t run_cell_merged(const MergedArgs &a, int sms, cudaStream_t st)
+  {
+    constexpr int  CPB       = Cfg<P>::CPB;
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
+    if (grid == 0)
+      return cudaSuccess;
+    cell_kernel_merged<P, CPB><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
     return cudaGetLastError();
   }
 
@@ -417,6 +729,36 @@ namespace bp4
   {
     BP4_DISPATCH(degree, return run_cell_plain<P>(a, sms, st));
     return cudaSuccess;
+  }
+
+  cudaError_t launch_cell_merged(int degree, const MergedArgs &a, int sms, cudaStream_t st)
+  {
+    BP4_DISPATCH(degree, return run_cell_merged<P>(a, sms, st));
+    return cudaSuccess;
+  }
+
+  // touch/owner: scratch arrays of n_nodes entries; touch is left ZEROED for use as the
+  // arrival counters of the fused kernel
+  cudaError_t launch_build_meta(uint64_t n_cells, uint64_t n_nodes, const uint32_t *entity_index,
+                                uint32_t *touch, uint32_t *owner, uint8_t *meta, cudaStream_t st)
+  {
+    cudaError_t e = cudaMemsetAsync(touch, 0, sizeof(uint32_t) * n_nodes, st);
+    if (e != cudaSuccess)
+      return e;
+    e = cudaMemsetAsync(owner, 0xFF, sizeof(uint32_t) * n_nodes, st);
+    if (e != cudaSuccess)
+      return e;
+    const uint64_t n = n_cells * 27;
+    if (n)
+      {
+        meta_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_cells, entity_index, touch, owner);
+        meta_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_cells, entity_index, touch, owner,
+                                                                      meta);
+      }
+    e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return e;
+    return cudaMemsetAsync(touch, 0, sizeof(uint32_t) * n_nodes, st);
   }
 
   int cells_per_block(int degree)

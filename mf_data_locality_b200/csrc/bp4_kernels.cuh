@@ -1,7 +1,7 @@
 // bp4_kernels.cuh -- sm_100a kernels of the BP4 hot path (FP64).
-//   cell kernel, MODE_PLAIN : dst += A src                      (a1/a3/a6/a7 of SURVEY 8a)
-//   cell kernel, MODE_MERGED: do_cg_update4b fused into the gather, do_cg_update3b fused
-//                             into the scatter through a last-toucher protocol (a2/a8/a9)
+//   cell kernel, plain : dst += A src                              (a1/a3/a6/a7 of SURVEY 8a)
+//   cell kernel, merged: do_cg_update4b fused into the gather, do_cg_update3b fused into
+//                        the scatter through a last-toucher protocol        (a2/a8/a9)
 //   streaming kernels for the unfused variant, the plain-CG BLAS-1 and the Jacobi apply.
 #pragma once
 #include <cuda_runtime.h>
@@ -11,41 +11,70 @@
 
 namespace bp4
 {
-  constexpr int kThreads = 256;
+  // 128 threads (one warp per SM sub-partition) and two resident blocks per SM: the block
+  // may use up to 255 registers per thread (phase 2 keeps 9*Q doubles live), and while one
+  // block waits on its gather or a barrier the other keeps the FP64 pipe busy.
+  constexpr int kThreads     = 128;
+  constexpr int kBlocksPerSM = 2;
+  constexpr int kSmemBudget  = 113 * 1024; // per block, two blocks per SM
 
-  // cells per thread block: Q^2 * CPB close to (but not above) kThreads so that phase 2,
-  // which carries ~2/3 of the FP64 work, fills the block's eight warps
   template <int P>
   struct Cfg
   {
-    static constexpr int Q   = P + 2;
-    static constexpr int CPB = (kThreads / (Q * Q)) > 0 ? (kThreads / (Q * Q)) : 1;
+    using G = Geom<P>;
+    static constexpr int per_cell = (G::WORK + G::DOFS + 24) * 8 + 28 * 4 + 28 + 64 * 5 + 16;
+    static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 256) / per_cell;
+    // phase 2 carries ~2/3 of the FP64 work: prefer Q^2*CPB close to a multiple of the block
+    static constexpr int want = (2 * kThreads) / (G::Q * G::Q) > 0 ? (2 * kThreads) / (G::Q * G::Q) : 1;
+    static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
   };
 
   template <int P, int CPB>
   struct alignas(16) CellSmem
   {
     using G = Geom<P>;
-    double   work[CPB][G::WORK];
-    double   dofs[CPB][G::DOF];
+    double   work[CPB * G::WORK];
+    double   dofs[CPB * G::DOFS];
     double   coef[CPB][24];
     double   xq[G::Q];
     double   wq[G::Q];
     uint32_t eidx[CPB][28];
-    uint32_t walk[G::N3];
+    uint32_t dtab[G::DOF];
+    // merged kernel only
+    uint8_t  meta[CPB][28];
+    uint32_t chunk_base[CPB * 64];
+    uint8_t  chunk_len[CPB * 64];
+    uint32_t n_chunks;
   };
 
   struct CellArgs
   {
     const uint32_t *entity_index; // [n_cells][27]
     const double   *coef;         // [n_cells][24] tri-linear coefficients
-    const uint32_t *walk;         // [N^3] packed entity walk (build_walk)
+    const uint32_t *dtab;         // [3 N^3] gather/scatter table (build_dof_table)
     uint64_t        n_cells;
     const double   *src;
     double         *dst;
   };
 
-  template <int P>
-  struct TabSym; // per-degree __constant__ table, defined in bp4_kernels.cu
+  // entity meta byte: bits 0-3 = (number of local cells touching the entity) - 1,
+  // bit 7 = this cell is the entity's owner (the one that writes r, p, x in the fused pre)
+  constexpr uint8_t kMetaOwner = 0x80;
 
+  struct MergedArgs
+  {
+    const uint32_t *entity_index;
+    const double   *coef;
+    const uint32_t *dtab;
+    const uint8_t  *meta;     // [n_cells][28]
+    uint32_t       *counters; // [n_nodes] arrival counters, indexed by first node of the entity
+    uint64_t        n_cells;
+    const double   *r_old, *p_old;
+    double         *h_old;    // read in the pre, zeroed on shared entities after their post
+    double         *r_new, *p_new, *h_new, *x;
+    const double   *prec;
+    double          alpha, beta, c1, c2; // c1 = alpha + alpha_old/beta_old, c2 = alpha_old/beta_old
+    int             update_x;            // alpha_old != 0
+    double         *acc;                 // [7]
+  };
 } // namespace bp4

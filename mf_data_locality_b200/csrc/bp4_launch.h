@@ -12,6 +12,9 @@ namespace bp4
   cudaError_t launch_init_degree(int degree, std::vector<uint32_t> &walk);
   int         cells_per_block(int degree);
   cudaError_t launch_cell_plain(int degree, const CellArgs &a, int sms, cudaStream_t st);
+  cudaError_t launch_cell_merged(int degree, const MergedArgs &a, int sms, cudaStream_t st);
+  cudaError_t launch_build_meta(uint64_t n_cells, uint64_t n_nodes, const uint32_t *entity_index,
+                                uint32_t *touch, uint32_t *owner, uint8_t *meta, cudaStream_t st);
   cudaError_t launch_pre(uint64_t n, double *h, double *x, double *r, double *p, const double *prec,
                          double alpha, double beta, double alpha_old, double beta_old, int sms,
                          cudaStream_t st);

@@ -1,0 +1,296 @@
+// dealii_standin.h -- the handful of deal.II roles the BP4 hot path of mf_data_locality
+// consumes, re-created for the one mesh family the benchmark uses (a refined, deformed
+// box; benchmark.h:66-102).  These are NOT deal.II re-implementations: each class offers
+// just the members the reference's own headers call, so that the host-side mirror
+// (poisson_operator.h, renumber_dofs_for_mf.h, solver_cg_optimized.h, benchmark.h in this
+// directory) reads like the reference and a maintainer can swap real deal.II back in.
+//
+// deal.II behaviours that are not visible in the reference tree (cell traversal order,
+// SIMD batch width, cell-batch ranges, p4est partition, ownership of interface DoFs) are
+// explicit parameters (MatrixFree::AdditionalData, Triangulation), see SURVEY App. B.
+//
+// Every rank process holds the whole (structured, cheap) lattice description and derives
+// ownership geometrically, so no host-side message passing is needed during setup.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#define AssertThrow(cond, msg)         \
+  do                                   \
+    {                                  \
+      if (!(cond))                     \
+        throw std::runtime_error(msg); \
+    }                                  \
+  while (0)
+
+namespace dealii
+{
+  namespace types
+  {
+    using global_dof_index = std::uint64_t;
+  }
+  namespace numbers
+  {
+    constexpr unsigned int invalid_unsigned_int = 0xFFFFFFFFu;
+    constexpr double       PI                   = 3.14159265358979323846;
+  } // namespace numbers
+
+  inline std::string ExcMessage(const std::string &s) { return s; }
+
+  using Point3 = std::array<double, 3>;
+
+  // contiguous index range [first, last) -- all the reference needs of IndexSet
+  struct IndexSet
+  {
+    types::global_dof_index first = 0, last = 0;
+    types::global_dof_index n_elements() const { return last - first; }
+    bool is_element(types::global_dof_index i) const { return i >= first && i < last; }
+    types::global_dof_index index_within_set(types::global_dof_index i) const { return i - first; }
+    types::global_dof_index nth_index_in_set(types::global_dof_index n) const { return first + n; }
+  };
+
+  // ---------------------------------------------------------------------------------------
+  // Triangulation: refine_global()-ed subdivided_hyper_rectangle transformed by a chart
+  // (benchmark.h:78-88).  Active cells are kept in deal.II's traversal order: coarse cells
+  // x-fastest, children by child index cx + 2 cy + 4 cz (Morton order inside a coarse cell).
+  // Ranks own equal contiguous chunks of that order (p4est space-filling curve).
+  // ---------------------------------------------------------------------------------------
+  class Triangulation
+  {
+  public:
+    Triangulation(unsigned int n_ranks = 1, unsigned int this_rank = 0)
+      : n_ranks(n_ranks), this_rank(this_rank)
+    {}
+
+    void build(const std::array<unsigned int, 3> &subdivisions, const unsigned int n_refine,
+               std::function<Point3(const Point3 &)> push_forward)
+    {
+      sub         = subdivisions;
+      refinements = n_refine;
+      chart       = std::move(push_forward);
+      for (int d = 0; d < 3; ++d)
+        n_cells_dir[d] = subdivisions[d] << n_refine;
+      const std::uint64_t per_coarse = std::uint64_t(1) << (3 * n_refine);
+      cells.resize(per_coarse * sub[0] * sub[1] * sub[2]);
+      std::uint64_t idx = 0;
+      for (unsigned int kz = 0; kz < sub[2]; ++kz)
+        for (unsigned int ky = 0; ky < sub[1]; ++ky)
+          for (unsigned int kx = 0; kx < sub[0]; ++kx)
+            for (std::uint64_t m = 0; m < per_coarse; ++m, ++idx)
+              {
+                std::uint32_t l[3] = {0, 0, 0};
+                for (unsigned int b = 0; b < n_refine; ++b)
+                  for (int d = 0; d < 3; ++d)
+                    l[d] |= std::uint32_t((m >> (3 * b + d)) & 1u) << b;
+                cells[idx] = {{l[0] + (kx << n_refine), l[1] + (ky << n_refine), l[2] + (kz << n_refine)}};
+              }
+    }
+
+    std::uint64_t n_global_active_cells() const { return cells.size(); }
+    std::uint64_t cells_per_rank() const { return cells.size() / n_ranks; }
+    unsigned int  subdomain_id(std::uint64_t cell) const
+    {
+      const std::uint64_t chunk = cells_per_rank();
+      return (unsigned int)std::min<std::uint64_t>(cell / (chunk ? chunk : 1), n_ranks - 1);
+    }
+    // active-cell index of the cell at lattice position c (inverse of the traversal order)
+    std::uint64_t cell_index(const std::array<std::uint32_t, 3> &c) const
+    {
+      const std::uint32_t side = 1u << refinements;
+      const std::uint32_t k[3] = {c[0] >> refinements, c[1] >> refinements, c[2] >> refinements};
+      std::uint64_t       m    = 0;
+      for (unsigned int b = 0; b < refinements; ++b)
+        for (int d = 0; d < 3; ++d)
+          m |= std::uint64_t(((c[d] & (side - 1)) >> b) & 1u) << (3 * b + d);
+      return ((std::uint64_t(k[2]) * sub[1] + k[1]) * sub[0] + k[0]) * (std::uint64_t(1) << (3 * refinements)) + m;
+    }
+    // vertex v = x + 2y + 4z of a cell (poisson_operator.h:153-160)
+    Point3 vertex(std::uint64_t cell, unsigned int v) const
+    {
+      const double h = 1.0 / double(1u << refinements);
+      Point3       p;
+      for (int d = 0; d < 3; ++d)
+        p[d] = double(cells[cell][d] + ((v >> d) & 1u)) * h;
+      return chart(p);
+    }
+
+    std::vector<std::array<std::uint32_t, 3>> cells; // lattice position per active cell
+    std::array<unsigned int, 3>               sub{{1, 1, 1}};
+    std::array<unsigned int, 3>               n_cells_dir{{1, 1, 1}};
+    unsigned int                              refinements = 0;
+    unsigned int                              n_ranks, this_rank;
+    std::function<Point3(const Point3 &)>     chart;
+  };
+
+  // FESystem(FE_Q(degree), n_components): only the sizes are needed
+  struct FESystem
+  {
+    unsigned int degree = 1, n_comp = 3;
+    unsigned int n_components() const { return n_comp; }
+    unsigned int n_base_elements() const { return 1; }
+    unsigned int dofs_per_cell() const { return n_comp * (degree + 1) * (degree + 1) * (degree + 1); }
+  };
+
+  // ---------------------------------------------------------------------------------------
+  // DoFHandler: Q_p^3 DoFs on the node lattice; a DoF is (lattice node, component) and its
+  // global number is 3 * node_number + component.  node_number[] is what
+  // Renumber::renumber rewrites (for ALL ranks, see renumber_dofs_for_mf.h here).
+  // ---------------------------------------------------------------------------------------
+  class DoFHandler
+  {
+  public:
+    explicit DoFHandler(const Triangulation &tria) : tria(&tria) {}
+
+    // initial numbering: rank by rank (owner = lowest rank among the cells touching a node,
+    // SURVEY App. B4), lattice order inside a rank, so that every rank owns a contiguous range
+    void distribute_dofs(const FESystem &fe_)
+    {
+      fe = fe_;
+      const unsigned int p = fe.degree;
+      for (int d = 0; d < 3; ++d)
+        nn[d] = std::uint64_t(tria->n_cells_dir[d]) * p + 1;
+      n_nodes = nn[0] * nn[1] * nn[2];
+      AssertThrow(n_nodes < 0xFFFFFFFFull, "node lattice exceeds 32-bit node numbers");
+      owner.assign(n_nodes, (unsigned char)255);
+      shared.assign(n_nodes, 0);
+      AssertThrow(tria->n_ranks <= 255, "at most 255 ranks");
+      const std::uint64_t n_cells = tria->n_global_active_cells();
+      // owner = min rank over touching cells; shared = touched by more than one rank
+      for (std::uint64_t c = 0; c < n_cells; ++c)
+        {
+          const unsigned char r = (unsigned char)tria->subdomain_id(c);
+          for_each_cell_node(c, [&](std::uint64_t node, int, int, int) {
+            if (owner[node] == 255)
+              owner[node] = r;
+            else if (owner[node] != r)
+              {
+                shared[node] = 1;
+                owner[node]  = std::min(owner[node], r);
+              }
+          });
+        }
+      rank_offset.assign(tria->n_ranks + 1, 0);
+      for (std::uint64_t n = 0; n < n_nodes; ++n)
+        ++rank_offset[owner[n] + 1];
+      for (unsigned int r = 0; r < tria->n_ranks; ++r)
+        rank_offset[r + 1] += rank_offset[r];
+      node_number.resize(n_nodes);
+      std::vector<std::uint64_t> next(rank_offset.begin(), rank_offset.end() - 1);
+      for (std::uint64_t n = 0; n < n_nodes; ++n)
+        node_number[n] = (std::uint32_t)next[owner[n]]++;
+    }
+
+    const FESystem      &get_fe() const { return fe; }
+    const Triangulation &get_triangulation() const { return *tria; }
+    types::global_dof_index n_dofs() const { return 3 * n_nodes; }
+    IndexSet                locally_owned_dofs(unsigned int rank) const
+    {
+      return IndexSet{3 * rank_offset[rank], 3 * rank_offset[rank + 1]};
+    }
+    IndexSet locally_owned_dofs() const { return locally_owned_dofs(tria->this_rank); }
+
+    template <typename F>
+    void for_each_cell_node(std::uint64_t cell, F &&f) const
+    {
+      const unsigned int  p = fe.degree;
+      const auto         &c = tria->cells[cell];
+      const std::uint64_t I0 = std::uint64_t(c[0]) * p, J0 = std::uint64_t(c[1]) * p,
+                          K0 = std::uint64_t(c[2]) * p;
+      for (unsigned int k = 0; k <= p; ++k)
+        for (unsigned int j = 0; j <= p; ++j)
+          for (unsigned int i = 0; i <= p; ++i)
+            f(((K0 + k) * nn[1] + (J0 + j)) * nn[0] + (I0 + i), (int)i, (int)j, (int)k);
+    }
+    std::uint64_t cell_node(std::uint64_t cell, unsigned int i, unsigned int j, unsigned int k) const
+    {
+      const unsigned int p = fe.degree;
+      const auto        &c = tria->cells[cell];
+      return ((std::uint64_t(c[2]) * p + k) * nn[1] + (std::uint64_t(c[1]) * p + j)) * nn[0] +
+             (std::uint64_t(c[0]) * p + i);
+    }
+    bool node_on_boundary(std::uint64_t node) const
+    {
+      const std::uint64_t I = node % nn[0], J = (node / nn[0]) % nn[1], K = node / (nn[0] * nn[1]);
+      return I == 0 || I == nn[0] - 1 || J == 0 || J == nn[1] - 1 || K == 0 || K == nn[2] - 1;
+    }
+    types::global_dof_index dof_number(std::uint64_t node, unsigned int c) const
+    {
+      return 3 * types::global_dof_index(node_number[node]) + c;
+    }
+
+    std::array<std::uint64_t, 3> nn{{1, 1, 1}};
+    std::uint64_t                n_nodes = 0;
+    std::vector<unsigned char>   owner;       // [n_nodes] owning rank
+    std::vector<unsigned char>   shared;      // [n_nodes] touched by cells of several ranks
+    std::vector<std::uint32_t>   node_number; // [n_nodes] current global node number
+    std::vector<std::uint64_t>   rank_offset; // [n_ranks+1] first node number of each rank
+
+  private:
+    const Triangulation *tria;
+    FESystem             fe;
+  };
+
+  // all boundary DoFs constrained to zero (VectorTools::interpolate_boundary_values with a
+  // ZeroFunction, benchmark.h:96-102).  Geometric, hence independent of the numbering.
+  class AffineConstraints
+  {
+  public:
+    void reinit(const DoFHandler &dh) { dof_handler = &dh; }
+    void clear() {}
+    void close() {}
+    bool node_is_constrained(std::uint64_t node) const { return dof_handler->node_on_boundary(node); }
+    const DoFHandler *dof_handler = nullptr;
+  };
+
+  namespace VectorTools
+  {
+    inline void interpolate_boundary_values(const DoFHandler &dof_handler, AffineConstraints &constraints)
+    {
+      constraints.reinit(dof_handler);
+    }
+  } // namespace VectorTools
+
+  namespace Utilities
+  {
+    namespace MPI
+    {
+      // layout of LinearAlgebra::distributed::Vector: owned range, then ghosts sorted by
+      // global index, plus the point-to-point exchange plan
+      struct Partitioner
+      {
+        IndexSet                   owned;       // global DoF range
+        std::vector<std::uint32_t> ghost_nodes; // global node numbers of the ghosts, sorted
+        unsigned int locally_owned_size() const { return (unsigned int)owned.n_elements(); }
+        unsigned int n_ghost_indices() const { return 3u * (unsigned int)ghost_nodes.size(); }
+        unsigned int global_to_local(types::global_dof_index g) const
+        {
+          if (owned.is_element(g))
+            return (unsigned int)(g - owned.first);
+          const std::uint32_t node = (std::uint32_t)(g / 3);
+          const auto          it   = std::lower_bound(ghost_nodes.begin(), ghost_nodes.end(), node);
+          AssertThrow(it != ghost_nodes.end() && *it == node, "global index is neither owned nor ghost");
+          return locally_owned_size() + 3u * (unsigned int)(it - ghost_nodes.begin()) + (unsigned int)(g % 3);
+        }
+        types::global_dof_index local_to_global(unsigned int l) const
+        {
+          if (l < locally_owned_size())
+            return owned.first + l;
+          const unsigned int g = l - locally_owned_size();
+          return 3 * types::global_dof_index(ghost_nodes[g / 3]) + g % 3;
+        }
+        std::vector<int>           peers;         // ranks I exchange with, ascending
+        std::vector<std::uint64_t> import_offset; // [peers+1] DoF offsets into the ghost range
+        std::vector<std::uint64_t> export_offset; // [peers+1]
+        std::vector<std::uint32_t> export_index;  // owned local DoFs each peer ghosts
+      };
+    } // namespace MPI
+  }   // namespace Utilities
+} // namespace dealii

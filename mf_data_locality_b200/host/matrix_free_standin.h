@@ -1,0 +1,151 @@
+// matrix_free_standin.h -- the MatrixFree<dim,double> roles used by the reference's
+// Renumber (renumber_dofs_for_mf.h:115-124, :320-331, :601-669) and LaplaceOperator
+// (poisson_operator.h:108-135, :188-196, :311): cell batches in loop order, the task_info
+// range tables, the vector partitioner, constrained DoFs.  Behaviour recalled from deal.II
+// 9.3 with the non-observable choices exposed in AdditionalData.
+#pragma once
+#include "dealii_standin.h"
+
+namespace dealii
+{
+  struct MatrixFreeAdditionalData
+  {
+    unsigned int n_lanes            = 8;    // VectorizedArray<double>::size(), AVX-512
+    unsigned int batches_per_range  = 1;    // cell batches per cell_partition_data range
+    bool         initialize_mapping = true; // unused: geometry is evaluated on the fly
+  };
+
+  class MatrixFree
+  {
+  public:
+    using AdditionalData = MatrixFreeAdditionalData;
+    struct TaskInfo
+    {
+      std::vector<unsigned int> partition_row_index; // ranges per partition (+2 trailing entries)
+      std::vector<unsigned int> cell_partition_data; // first batch of every range (+ sentinel)
+    };
+    struct DoFInfo
+    {
+      std::shared_ptr<const Utilities::MPI::Partitioner> vector_partitioner;
+    };
+
+    // `rank` defaults to the triangulation's own rank; Renumber also builds the object for the
+    // other ranks (every process derives the whole numbering, no host message passing)
+    void reinit(const DoFHandler &dh, const AffineConstraints &con, const unsigned int n_q_points_1d_,
+                const AdditionalData &ad = AdditionalData(), const int rank_ = -1)
+    {
+      dof_handler   = &dh;
+      constraints   = &con;
+      n_q_points_1d = n_q_points_1d_;
+      data          = ad;
+      const Triangulation &tria = dh.get_triangulation();
+      rank = rank_ < 0 ? tria.this_rank : (unsigned int)rank_;
+      const std::uint64_t chunk = tria.cells_per_rank();
+      const std::uint64_t c0 = chunk * rank,
+                          c1 = rank + 1 == tria.n_ranks ? tria.n_global_active_cells() : c0 + chunk;
+      // cells that touch a node owned elsewhere go to the middle partition (they read ghost
+      // values / write ghost contributions); the others are split around it
+      std::vector<std::uint64_t> inner, comm;
+      for (std::uint64_t c = c0; c < c1; ++c)
+        {
+          bool needs_comm = false;
+          if (tria.n_ranks > 1)
+            dh.for_each_cell_node(c, [&](std::uint64_t node, int, int, int) {
+              needs_comm |= dh.owner[node] != rank;
+            });
+          (needs_comm ? comm : inner).push_back(c);
+        }
+      const unsigned int L = ad.n_lanes;
+      cell_order.clear();
+      batch_start.assign(1, 0);
+      task_info.partition_row_index.assign(1, 0);
+      task_info.cell_partition_data.assign(1, 0);
+      auto add_partition = [&](const std::uint64_t *first, const std::uint64_t *last) {
+        const unsigned int b0 = (unsigned int)batch_start.size() - 1;
+        for (const std::uint64_t *c = first; c < last; c += L)
+          {
+            const std::uint64_t *e = std::min(c + L, last);
+            cell_order.insert(cell_order.end(), c, e);
+            batch_start.push_back((unsigned int)cell_order.size());
+          }
+        const unsigned int b1 = (unsigned int)batch_start.size() - 1;
+        for (unsigned int b = b0; b < b1; b += ad.batches_per_range)
+          task_info.cell_partition_data.push_back(std::min(b + ad.batches_per_range, b1));
+        task_info.partition_row_index.push_back((unsigned int)task_info.cell_partition_data.size() - 1);
+      };
+      if (tria.n_ranks > 1)
+        {
+          const std::size_t n_before = ((inner.size() / L) / 2) * L;
+          add_partition(inner.data(), inner.data() + n_before);
+          add_partition(comm.data(), comm.data() + comm.size());
+          add_partition(inner.data() + n_before, inner.data() + inner.size());
+        }
+      else
+        add_partition(inner.data(), inner.data() + inner.size());
+      // deal.II appends the ghost-face partitions; Renumber loops over size() - 2
+      task_info.partition_row_index.push_back(task_info.partition_row_index.back());
+
+      // vector partitioner: owned range + ghost nodes sorted by (current) global number
+      auto part   = std::make_shared<Utilities::MPI::Partitioner>();
+      part->owned = dh.locally_owned_dofs(rank);
+      if (tria.n_ranks > 1)
+        {
+          for (const std::uint64_t c : comm)
+            dh.for_each_cell_node(c, [&](std::uint64_t node, int, int, int) {
+              if (dh.owner[node] != rank)
+                part->ghost_nodes.push_back(dh.node_number[node]);
+            });
+          std::sort(part->ghost_nodes.begin(), part->ghost_nodes.end());
+          part->ghost_nodes.erase(std::unique(part->ghost_nodes.begin(), part->ghost_nodes.end()),
+                                  part->ghost_nodes.end());
+        }
+      dof_info.vector_partitioner = part;
+
+      // owned constrained DoFs, local indices ascending (get_constrained_dofs)
+      constrained_dofs.clear();
+      {
+        std::vector<std::uint32_t> nodes;
+        for (std::uint64_t c = c0; c < c1; ++c)
+          dh.for_each_cell_node(c, [&](std::uint64_t node, int, int, int) {
+            if (dh.owner[node] == rank && con.node_is_constrained(node))
+              nodes.push_back(dh.node_number[node]);
+          });
+        std::sort(nodes.begin(), nodes.end());
+        nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+        const std::uint64_t first = dh.rank_offset[rank];
+        for (const std::uint32_t n : nodes)
+          for (unsigned int c = 0; c < 3; ++c)
+            constrained_dofs.push_back((unsigned int)(3 * (n - first) + c));
+      }
+    }
+
+    unsigned int n_cell_batches() const { return (unsigned int)batch_start.size() - 1; }
+    unsigned int n_active_entries_per_cell_batch(unsigned int b) const
+    {
+      return batch_start[b + 1] - batch_start[b];
+    }
+    unsigned int  n_physical_cells() const { return (unsigned int)cell_order.size(); }
+    // active-cell index of lane l of batch b (get_cell_iterator(b, l))
+    std::uint64_t get_cell(unsigned int b, unsigned int l) const { return cell_order[batch_start[b] + l]; }
+    const TaskInfo                  &get_task_info() const { return task_info; }
+    const DoFInfo                   &get_dof_info() const { return dof_info; }
+    const DoFHandler                &get_dof_handler() const { return *dof_handler; }
+    const AffineConstraints         &get_constraints() const { return *constraints; }
+    const std::vector<unsigned int> &get_constrained_dofs() const { return constrained_dofs; }
+    unsigned int                     get_rank() const { return rank; }
+    const AdditionalData            &get_additional_data() const { return data; }
+
+    std::vector<std::uint64_t> cell_order;  // active-cell index per physical cell, loop order
+    std::vector<unsigned int>  batch_start; // first physical cell of every batch (+ sentinel)
+    unsigned int               n_q_points_1d = 0;
+
+  private:
+    const DoFHandler         *dof_handler = nullptr;
+    const AffineConstraints  *constraints = nullptr;
+    AdditionalData            data;
+    TaskInfo                  task_info;
+    DoFInfo                   dof_info;
+    std::vector<unsigned int> constrained_dofs;
+    unsigned int              rank = 0;
+  };
+} // namespace dealii

@@ -1,0 +1,154 @@
+// poisson_operator.h -- host-side mirror of the reference's Poisson::LaplaceOperator
+// (poisson_operator.h:67-695): same template parameters, same public members
+// (initialize, initialize_dof_vector, vmult, Tvmult, vmult_with_merged_sums,
+// compute_inverse_diagonal, n_components, value_type, size_type).  All arithmetic runs on
+// the B200 through the C ABI of include/bp4.h; this class only builds the two per-cell
+// tables of LaplaceOperator::initialize -- the 27 compressed entity indices
+// (poisson_operator.h:183-267) and the 8 vertices behind the tri-linear coefficients
+// (:153-178) -- checks the "contiguous numbering" contract the renumbering must deliver,
+// and hands them to bp4_ctx_create.
+#pragma once
+#include <array>
+#include <memory>
+
+#include "device_vector.h"
+#include "diagonal_matrix_blocked.h"
+#include "matrix_free_standin.h"
+
+namespace Poisson
+{
+  using namespace dealii;
+
+  template <int dim, int fe_degree, int n_q_points_1d = fe_degree + 1, int n_components_ = 1,
+            typename Number = double, typename VectorType = LinearAlgebra::distributed::Vector<Number>>
+  class LaplaceOperator
+  {
+  public:
+    typedef Number                  value_type;
+    typedef types::global_dof_index size_type;
+    static constexpr unsigned int   n_components = n_components_;
+    static_assert(dim == 3 && n_components_ == 3, "BP4: three components in three dimensions");
+
+    LaplaceOperator() = default;
+    LaplaceOperator(const LaplaceOperator &) = delete;
+    ~LaplaceOperator()
+    {
+      if (ctx)
+        bp4_ctx_destroy(ctx);
+    }
+
+    void initialize(std::shared_ptr<const MatrixFree> data_, const AffineConstraints &constraints,
+                    const int device = 0)
+    {
+      data = data_;
+      const DoFHandler &dh = data->get_dof_handler();
+      AssertThrow(dh.get_fe().n_components() == n_components, "n_components mismatch");
+      AssertThrow(dh.get_fe().degree == fe_degree, "fe_degree mismatch");
+      const Utilities::MPI::Partitioner &part = *data->get_dof_info().vector_partitioner;
+      const unsigned int                 n_cells = data->n_physical_cells();
+      compressed_dof_indices.assign(std::size_t(27) * n_cells, numbers::invalid_unsigned_int);
+      cell_vertices.resize(std::size_t(24) * n_cells);
+      constexpr unsigned int p = fe_degree;
+      const unsigned int lo[3] = {0, 1, p}, hi[3] = {1, p, p + 1};
+      for (unsigned int b = 0, cell_no = 0; b < data->n_cell_batches(); ++b)
+        for (unsigned int l = 0; l < data->n_active_entries_per_cell_batch(b); ++l, ++cell_no)
+          {
+            const std::uint64_t cell = data->get_cell(b, l);
+            for (unsigned int v = 0; v < 8; ++v)
+              {
+                const Point3 x = dh.get_triangulation().vertex(cell, v);
+                for (unsigned int d = 0; d < 3; ++d)
+                  cell_vertices[24 * std::size_t(cell_no) + 3 * v + d] = x[d];
+              }
+            for (unsigned int a = 0; a < 27; ++a)
+              {
+                const unsigned int ex = a % 3, ey = (a / 3) % 3, ez = a / 9;
+                const std::uint64_t n0 = dh.cell_node(cell, lo[ex], lo[ey], lo[ez]);
+                if (constraints.node_is_constrained(n0))
+                  continue; // entity stays invalid: read as 0, never written (:194, :205)
+                const types::global_dof_index g0 = dh.dof_number(n0, 0);
+                // contract of the renumbering: the entity's DoFs are contiguous, nodes
+                // lexicographic, components interleaved (:197-199, :207-211, :224-239, :251-255)
+                types::global_dof_index expect = g0;
+                for (unsigned int k = lo[ez]; k < hi[ez]; ++k)
+                  for (unsigned int j = lo[ey]; j < hi[ey]; ++j)
+                    for (unsigned int i = lo[ex]; i < hi[ex]; ++i, expect += n_components)
+                      AssertThrow(dh.dof_number(dh.cell_node(cell, i, j, k), 0) == expect,
+                                  ExcMessage("Expected contiguous numbering"));
+                compressed_dof_indices[27 * std::size_t(cell_no) + a] = part.global_to_local(g0);
+              }
+          }
+
+      bp4_desc desc{};
+      desc.degree        = fe_degree;
+      desc.device        = device;
+      desc.n_cells       = n_cells;
+      desc.n_owned       = part.locally_owned_size();
+      desc.n_ghost       = part.n_ghost_indices();
+      desc.entity_index  = compressed_dof_indices.data();
+      desc.vertices      = cell_vertices.data();
+      desc.n_constrained = data->get_constrained_dofs().size();
+      desc.constrained   = data->get_constrained_dofs().data();
+      desc.n_peers       = (int)part.peers.size();
+      desc.peer_rank     = part.peers.data();
+      desc.import_offset = part.import_offset.data();
+      desc.export_offset = part.export_offset.data();
+      desc.export_index  = part.export_index.data();
+      if (ctx)
+        bp4_ctx_destroy(ctx);
+      ctx = nullptr;
+      if (device >= 0) // device < 0: tables only (host-side checks without a GPU)
+        bp4_check(bp4_ctx_create(&desc, &ctx));
+    }
+
+    void initialize_dof_vector(VectorType &vec) const
+    {
+      const Utilities::MPI::Partitioner &part = *data->get_dof_info().vector_partitioner;
+      vec.reinit(ctx, part.locally_owned_size(), part.n_ghost_indices(), data->get_dof_handler().n_dofs());
+    }
+
+    // dst = A src, identity on Dirichlet rows (poisson_operator.h:307-313)
+    void vmult(VectorType &dst, const VectorType &src) const
+    {
+      bp4_check(bp4_vmult(ctx, dst.handle(), src.handle()));
+    }
+    void Tvmult(VectorType &dst, const VectorType &src) const { vmult(dst, src); }
+
+    // pre-update of x, g, d, h; h = A d; the seven merged sums over all ranks
+    // (poisson_operator.h:327-377; Tensor<1,7> becomes std::array<double,7>)
+    std::array<Number, 7> vmult_with_merged_sums(VectorType &x, VectorType &g, VectorType &d, VectorType &h,
+                                                 const DiagonalMatrixBlocked<n_components, Number> &prec,
+                                                 const Number alpha, const Number beta,
+                                                 const Number alpha_old, const Number beta_old) const
+    {
+      std::array<Number, 7> sums;
+      bp4_check(bp4_vmult_merged(ctx, x.handle(), g.handle(), d.handle(), h.handle(),
+                                 prec.diagonal.handle(), alpha, beta, alpha_old, beta_old, sums.data()));
+      return sums;
+    }
+
+    // Inverse diagonal of the scalar Laplacian under the quadrature this operator was set up
+    // with (the reference instantiates it with GLL(p+1), benchmark.h:128-140), 1 where the
+    // diagonal is 0.  The reference returns a DoF-sized vector whose every third entry is
+    // then copied into the blocked diagonal (poisson_operator.h:392-426, benchmark.h:141-147);
+    // here the per-node values are produced directly in that final layout.
+    void compute_inverse_diagonal(VectorType &per_node) const
+    {
+      const Utilities::MPI::Partitioner &part = *data->get_dof_info().vector_partitioner;
+      per_node.reinit(ctx, part.locally_owned_size() / n_components, 0,
+                      data->get_dof_handler().n_dofs() / n_components);
+      bp4_check(bp4_inverse_diagonal(ctx, per_node.handle()));
+    }
+
+    bp4_ctx                          *context() const { return ctx; }
+    const std::vector<unsigned int>  &get_compressed_dof_indices() const { return compressed_dof_indices; }
+    const std::vector<double>        &get_cell_vertices() const { return cell_vertices; }
+    const MatrixFree                 &get_matrix_free() const { return *data; }
+
+  private:
+    std::shared_ptr<const MatrixFree> data;
+    std::vector<unsigned int>         compressed_dof_indices; // [cell][27], one lane per cell
+    std::vector<double>               cell_vertices;          // [cell][8][3]
+    bp4_ctx                          *ctx = nullptr;
+  };
+} // namespace Poisson

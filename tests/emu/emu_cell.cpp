@@ -14,9 +14,9 @@ static void run(long n_cells, const uint32_t *eidx, const double *verts, const d
   using G = bp4::Geom<P>;
   bp4::Tab<P> tb;
   bp4::fill_tab<P>(tb);
-  std::vector<uint32_t> walk(G::N3);
-  bp4::build_walk<P>(walk.data());
-  std::vector<double> dofs(G::DOF), work(G::WORK);
+  std::vector<uint32_t> dtab(G::DOF);
+  bp4::build_dof_table<P>(dtab.data());
+  std::vector<double> dofs(G::DOFS), work(G::WORK);
   for (long cell = 0; cell < n_cells; ++cell)
     {
       const uint32_t *e = eidx + 27 * cell;
@@ -36,25 +36,23 @@ static void run(long n_cells, const uint32_t *eidx, const double *verts, const d
         }
       for (int m = 0; m < G::DOF; ++m)
         {
-          const int      w = m / 3, c = m % 3;
-          const uint32_t pk = walk[w], base = e[(pk >> 10) & 31u];
-          dofs[c * G::N3 + (pk & 1023u)] = base != 0xFFFFFFFFu ? src[(size_t)base + 3u * (pk >> 15) + c] : 0.;
+          const uint32_t t = dtab[m], base = e[bp4::dtab_ent(t)];
+          dofs[bp4::dtab_off(t)] = base != 0xFFFFFFFFu ? src[(size_t)base + bp4::dtab_rel(t)] : 0.;
         }
       for (int it = 0; it < G::ITEMS13; ++it)
-        bp4::phase1<P>(tb, dofs.data(), work.data(), it / G::N, it % G::N);
+        bp4::phase1<P>(tb, dofs.data() + it * G::RD, work.data() + it * G::RW);
       for (int it = 0; it < G::ITEMS2; ++it)
         {
           const int qz = it / G::Q, qx = it % G::Q;
           bp4::phase2<P>(tb, cf, work.data(), qx, qz, tb.xq[qx], tb.xq[qz], tb.wq[qx] * tb.wq[qz]);
         }
       for (int it = 0; it < G::ITEMS13; ++it)
-        bp4::phase3<P>(tb, work.data(), dofs.data(), it / G::N, it % G::N);
+        bp4::phase3<P>(tb, work.data() + it * G::RW, dofs.data() + it * G::RD);
       for (int m = 0; m < G::DOF; ++m)
         {
-          const int      w = m / 3, c = m % 3;
-          const uint32_t pk = walk[w], base = e[(pk >> 10) & 31u];
+          const uint32_t t = dtab[m], base = e[bp4::dtab_ent(t)];
           if (base != 0xFFFFFFFFu)
-            dst[(size_t)base + 3u * (pk >> 15) + c] += dofs[c * G::N3 + (pk & 1023u)];
+            dst[(size_t)base + bp4::dtab_rel(t)] += dofs[bp4::dtab_off(t)];
         }
     }
 }
