@@ -104,7 +104,7 @@ int bp4_vmult_merged(bp4_ctx *ctx, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *
                      const bp4_vec *prec, double alpha, double beta, double alpha_old,
                      double beta_old, double out[7]);
 /* which merged implementation bp4_vmult_merged runs: 0 = three kernels (pre, cells, post),
- * 1 = single fused kernel (default).  Both give the same sums up to rounding.              */
+ * 1 = single fused kernel; default 0 until the fused kernel is the faster one.  Both give the same sums up to rounding.              */
 int bp4_set_merged_variant(bp4_ctx *ctx, int variant);
 /* 1/diag of the scalar GLL(p+1) Laplacian per node, 1 where 0:
  * LaplaceOperator::compute_inverse_diagonal + extraction (poisson_operator.h:392-426,

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -75,7 +76,7 @@ struct bp4_ctx
   int         *d_flag = nullptr;
   double      *h_acc  = nullptr; // pinned [8]
   int         *h_flag = nullptr; // pinned
-  int          merged_variant = 1;
+  int          merged_variant = 0;
   uint8_t     *d_meta = nullptr;     // fused kernel: per-cell entity meta bytes [n_cells][28]
   uint32_t    *d_counters = nullptr; // fused kernel: arrival counters [n_nodes]
   // multi-GPU
@@ -85,6 +86,9 @@ struct bp4_ctx
   std::vector<uint64_t> import_off, export_off;
   uint32_t             *d_export = nullptr;
   double               *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+  // freed vector buffers kept for reuse, keyed by size: plays the role of deal.II's
+  // GrowingVectorMemory pool behind SolverCGFullMerge's temporaries (solver_cg_optimized.h:201)
+  std::multimap<uint64_t, double *> pool;
   // measurement
   bool                   profile = false;
   std::vector<ProfEvent> events;
@@ -138,13 +142,25 @@ namespace
     return 0;
   }
 
+  // zero-initialised buffer of n doubles, from the pool when one of that size is cached
+  int pooled_alloc(bp4_ctx *c, uint64_t n, double **out)
+  {
+    auto it = c->pool.find(n);
+    if (it != c->pool.end())
+      {
+        *out = it->second;
+        c->pool.erase(it);
+      }
+    else
+      CU(cudaMalloc(out, sizeof(double) * (n ? n : 1)));
+    CU(cudaMemsetAsync(*out, 0, sizeof(double) * n, c->stream));
+    return 0;
+  }
+
   int ensure_second(bp4_ctx *c, bp4_vec *v)
   {
     if (!v->buf[1])
-      {
-        CU(cudaMalloc(&v->buf[1], sizeof(double) * (v->n ? v->n : 1)));
-        CU(cudaMemsetAsync(v->buf[1], 0, sizeof(double) * v->n, c->stream));
-      }
+      return pooled_alloc(c, v->n, &v->buf[1]);
     return 0;
   }
 
@@ -272,6 +288,8 @@ int bp4_ctx_destroy(bp4_ctx *c)
   drain_events(c);
   if (c->comm)
     ncclCommDestroy(c->comm);
+  for (auto &kv : c->pool)
+    cudaFree(kv.second);
   cudaFree(c->d_entity);
   cudaFree(c->d_constrained);
   cudaFree(c->d_walk);
@@ -314,8 +332,11 @@ int bp4_vec_alloc(bp4_ctx *c, uint64_t n, bp4_vec **out)
   CU(cudaSetDevice(c->device));
   bp4_vec *v = new bp4_vec;
   v->n       = n;
-  CU(cudaMalloc(&v->buf[0], sizeof(double) * (n ? n : 1)));
-  CU(cudaMemsetAsync(v->buf[0], 0, sizeof(double) * n, c->stream));
+  if (int e = pooled_alloc(c, n, &v->buf[0]))
+    {
+      delete v;
+      return e;
+    }
   *out = v;
   return 0;
 }
@@ -324,10 +345,14 @@ int bp4_vec_free(bp4_ctx *c, bp4_vec *v)
 {
   if (!v)
     return 0;
-  if (c)
-    cudaStreamSynchronize(c->stream);
-  cudaFree(v->buf[0]);
-  cudaFree(v->buf[1]);
+  for (double *b : v->buf)
+    if (b)
+      {
+        if (c) // stream order makes reuse safe: the next user's memset is queued behind our work
+          c->pool.emplace(v->n, b);
+        else
+          cudaFree(b);
+      }
   delete v;
   return 0;
 }

@@ -1,0 +1,67 @@
+"""CPU tests of the C++ host mirror (Renumber, MatrixFree stand-in, LaplaceOperator::initialize
+tables) against the numpy oracle: the DoF renumbering permutation, ghost index sets, entity
+indices and constrained lists must be BIT-EXACT (north_star), for 1, 2, 4 and 8 virtual ranks."""
+import numpy as np
+import pytest
+
+from oracle import bp4_oracle as O
+
+
+@pytest.fixture(scope="module")
+def host():
+    from mf_data_locality_b200 import build, host
+    build.build_all()
+    return host
+
+
+CASES = [(2, 5, 1), (3, 6, 1), (4, 7, 1), (5, 4, 1), (6, 6, 1), (7, 3, 1), (8, 4, 1), (4, 9, 1),
+         (3, 6, 2), (4, 6, 4), (2, 9, 8), (4, 9, 2), (3, 7, 4), (5, 6, 2)]
+
+
+@pytest.mark.parametrize("p,s,n_ranks", CASES)
+def test_tables_bit_exact(host, p, s, n_ranks):
+    rds = O.build_problem(p, s, n_ranks=n_ranks)
+    for r, rd in enumerate(rds):
+        pr = host.Problem(p, s, device=-1, n_ranks=n_ranks, rank=r)
+        assert (pr.n_cells, pr.n_owned, pr.n_ghost) == (rd.n_cells, rd.n_owned, rd.n_ghost)
+        assert pr.n_dofs == O.n_dofs_total(p, s)
+        assert np.array_equal(pr.node_of_local(), rd.node_of_local.astype(np.uint64))   # permutation + ghosts
+        assert np.array_equal(pr.entity_index(), rd.entity_index)
+        assert np.array_equal(pr.constrained(), rd.constrained)
+        assert np.allclose(pr.vertices(), rd.vertices, rtol=0, atol=1e-15)
+        assert pr.n_batches == len(rd.batch_start) - 1 and pr.n_ranges == len(rd.range_start) - 1
+        pr.close()
+
+
+@pytest.mark.parametrize("lanes,bpr", [(4, 1), (8, 3), (2, 5)])
+def test_batch_model_parameters(host, lanes, bpr):
+    """the deal.II behaviours that are not in the reference tree are explicit parameters"""
+    rd = O.build_problem(3, 7, lanes=lanes, batches_per_range=bpr)[0]
+    pr = host.Problem(3, 7, device=-1, n_lanes=lanes, batches_per_range=bpr)
+    assert np.array_equal(pr.node_of_local(), rd.node_of_local.astype(np.uint64))
+    assert np.array_equal(pr.entity_index(), rd.entity_index)
+    pr.close()
+
+
+def test_renumber_strategies(host):
+    """base numbering is rejected by the compressed operator, like the reference's AssertThrow
+    "Expected contiguous numbering" (poisson_operator.h:198); first/last touch and the three
+    groupings all deliver contiguous entities"""
+    with pytest.raises(host.HostError, match="contiguous"):
+        host.Problem(3, 5, device=-1, renumber=(0, 0, 0))
+    with pytest.raises(host.HostError, match="cellbatch assembly"):
+        host.Problem(3, 5, device=-1, renumber=(1, 1, 2))
+    seen = set()
+    for r in (1, 2):
+        for g in (0, 1, 2):
+            pr = host.Problem(3, 6, device=-1, renumber=(0, r, g))
+            nl = pr.node_of_local()
+            assert len(np.unique(nl)) == len(nl) == pr.n_owned // 3
+            seen.add(nl.tobytes())
+            pr.close()
+    assert len(seen) >= 4          # the strategies really are different numberings
+
+
+def test_unsupported_degree(host):
+    with pytest.raises(host.HostError, match="degrees 2 to 8"):
+        host.Problem(9, 3, device=-1)
