@@ -76,7 +76,8 @@ struct bp4_ctx
   int         *d_flag = nullptr;
   double      *h_acc  = nullptr; // pinned [8]
   int         *h_flag = nullptr; // pinned
-  int          merged_variant = 0;
+  int          merged_variant = 0; // 0 three kernels, 1 fused, 2 fused + warp-specialised
+  int          cell_variant   = 0; // plain cell kernel: 0 classic, 1 warp-specialised
   uint8_t     *d_meta = nullptr;     // fused kernel: per-cell entity meta bytes [n_cells][28]
   uint32_t    *d_counters = nullptr; // fused kernel: arrival counters [n_nodes]
   // multi-GPU
@@ -428,7 +429,10 @@ static int cell_loop(bp4_ctx *c, double *dst, const double *src, bool zero_dst)
   a.src          = src;
   a.dst          = dst;
   Timed t(c, BP4_K_VMULT);
-  CU(bp4::launch_cell_plain(c->degree, a, c->sms, c->stream));
+  if (c->cell_variant == 1)
+    CU(bp4::launch_cell_ws(c->degree, nullptr, &a, c->sms, c->stream));
+  else
+    CU(bp4::launch_cell_plain(c->degree, a, c->sms, c->stream));
   return 0;
 }
 
@@ -461,9 +465,11 @@ int bp4_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src)
 
 int bp4_set_merged_variant(bp4_ctx *c, int variant)
 {
-  if (!c || variant < 0 || variant > 1)
+  if (!c || variant < 0 || variant > 5)
     return fail(BP4_ERR_ARG, "bad variant");
-  c->merged_variant = variant;
+  // 0 three kernels, 1 fused, 2 fused + warp-specialised; +3: plain cell kernel warp-specialised
+  c->merged_variant = variant % 3;
+  c->cell_variant   = variant / 3;
   return 0;
 }
 
@@ -479,7 +485,7 @@ int bp4_vmult_merged(bp4_ctx *c, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h,
   if (!prec || prec->n < c->n_owned / 3)
     return fail(BP4_ERR_ARG, "prec needs n_owned/3 entries");
   const uint64_t n = c->n_owned;
-  if (c->merged_variant == 1 && c->n_ghost == 0)
+  if (c->merged_variant >= 1 && c->n_ghost == 0)
     {
       // single fused kernel; g, d, h ping-pong between two buffers each
       if (!c->d_meta)
@@ -522,7 +528,10 @@ int bp4_vmult_merged(bp4_ctx *c, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h,
       a.acc          = c->d_acc;
       {
         Timed t(c, BP4_K_MERGED);
-        CU(bp4::launch_cell_merged(c->degree, a, c->sms, c->stream));
+        if (c->merged_variant == 2)
+          CU(bp4::launch_cell_ws(c->degree, &a, nullptr, c->sms, c->stream));
+        else
+          CU(bp4::launch_cell_merged(c->degree, a, c->sms, c->stream));
       }
       g->cur ^= 1;
       d->cur ^= 1;

@@ -116,7 +116,8 @@ namespace bp4
 
   // per-DoF gather/scatter table of a cell, r = 3 w + c in entity-major order (consecutive r
   // = consecutive addresses inside an entity's segment):
-  //   bits 0-11 offset in the cell's dofs staging | bits 12-16 entity | bits 17-31 3*pos + c
+  //   bits 0-6 k*N+i (position in the staging row) | bits 7-11 row c*N+j | bits 12-16 entity |
+  //   bits 17-31 3*pos + c (offset from the entity's first DoF)
   template <int P>
   inline void build_dof_table(uint32_t *tab)
   {
@@ -124,12 +125,25 @@ namespace bp4
     build_walk<P>(walk);
     for (int w = 0; w < Geom<P>::N3; ++w)
       for (int c = 0; c < 3; ++c)
-        tab[3 * w + c] = dofs_offset<P>(walk[w], c) | (walk_ent(walk[w]) << 12) |
-                         ((3u * walk_pos(walk[w]) + c) << 17);
+        tab[3 * w + c] = walk_inrow(walk[w]) | ((uint32_t(c) * Geom<P>::N + walk_j(walk[w])) << 7) |
+                         (walk_ent(walk[w]) << 12) | ((3u * walk_pos(walk[w]) + c) << 17);
   }
-  BP4_HD uint32_t dtab_off(uint32_t t) { return t & 4095u; }
+  BP4_HD uint32_t dtab_inrow(uint32_t t) { return t & 127u; }
+  BP4_HD uint32_t dtab_row(uint32_t t) { return (t >> 7) & 31u; }
   BP4_HD uint32_t dtab_ent(uint32_t t) { return (t >> 12) & 31u; }
   BP4_HD uint32_t dtab_rel(uint32_t t) { return t >> 17; }
+  // offset inside a cell's dofs staging block (row stride RD) ...
+  template <int P>
+  BP4_HD uint32_t dtab_off(uint32_t t)
+  {
+    return dtab_row(t) * Geom<P>::RD + dtab_inrow(t);
+  }
+  // ... and inside its work block (row stride RW), where phase 3 may leave its result in place
+  template <int P>
+  BP4_HD uint32_t dtab_off_work(uint32_t t)
+  {
+    return dtab_row(t) * Geom<P>::RW + dtab_inrow(t);
+  }
 
   // ---------------------------------------------------------------------------------------
   // phase 1: item = row (c, j).  dofs_row[k][i] -> work_row[{0,1,2}][qz][qx]
@@ -200,146 +214,121 @@ namespace bp4
   {
     using G         = Geom<P>;
     constexpr int N = G::N, Q = G::Q;
-    double        gr[3][3][Q]; // [c][direction][qy]
-    double       *base = work + qz * Q + qx; // work = first row of the cell
-    // y-interpolation of the nine (component, array) lines at once: every S[j][q] is
-    // fetched once (uniform register) and feeds nine consecutive FMAs.  Array a = 0 (value)
-    // is parked in direction slot 1 until its eta-derivative replaces it.
-    BP4_UNROLL
-    for (int j = 0; j < N; ++j)
-      {
-        double r[3][3];
-        BP4_UNROLL
-        for (int c = 0; c < 3; ++c)
-          BP4_UNROLL
-        for (int a = 0; a < 3; ++a)
-          r[c][a == 0 ? 1 : (a == 1 ? 0 : 2)] = base[(c * N + j) * G::RW + a * Q * Q];
-        BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          {
-            const double sjq = tb.S[j][q];
-            BP4_UNROLL
-            for (int c = 0; c < 3; ++c)
-              BP4_UNROLL
-            for (int e = 0; e < 3; ++e)
-              gr[c][e][q] = j == 0 ? sjq * r[c][e] : gr[c][e][q] + sjq * r[c][e];
-          }
-      }
-    // d/deta of the three components
-    {
-      double v[3][Q];
-      BP4_UNROLL
-      for (int c = 0; c < 3; ++c)
-        BP4_UNROLL
-      for (int q = 0; q < Q; ++q)
-        v[c][q] = gr[c][1][q];
-      BP4_UNROLL
-      for (int i = 0; i < Q; ++i)
-        BP4_UNROLL
-      for (int q = 0; q < Q; ++q)
-        {
-          const double d = tb.D[i][q];
-          BP4_UNROLL
-          for (int c = 0; c < 3; ++c)
-            gr[c][1][q] = i == 0 ? d * v[c][0] : gr[c][1][q] + d * v[c][i];
-        }
-    }
-    // geometry along the line: rows of dX/dxi_e (poisson_operator.h:577-602)
+    // --- geometry of the whole y-line first: G = (w / det) K^T K, six entries per point.
+    // rows of dX/dxi_e (poisson_operator.h:577-602):
     //   r0 = dX/dxi   = (v1 + z v10) + y (v4 + z v13)
     //   r1 = dX/deta  = (v3 + z v12) + x (v4 + z v13)      (constant along the line)
     //   r2 = dX/dzeta = (v9 + x v10) + y (v12 + x v13)
-    double A[3], B[3], R1[3], Cc[3], Dd[3];
-    BP4_UNROLL
-    for (int d = 0; d < 3; ++d)
-      {
-        const double v1 = cf[3 + d], v3 = cf[6 + d], v4 = cf[9 + d], v9 = cf[12 + d],
-                     v10 = cf[15 + d], v12 = cf[18 + d], v13 = cf[21 + d];
-        A[d]  = v1 + z * v10;
-        B[d]  = v4 + z * v13;
-        R1[d] = (v3 + z * v12) + x * B[d];
-        Cc[d] = v9 + x * v10;
-        Dd[d] = v12 + x * v13;
-      }
-    BP4_UNROLL
-    for (int q = 0; q < Q; ++q)
-      {
-        const double y = tb.xq[q];
-        double       r0[3], r2[3];
-        BP4_UNROLL
-        for (int d = 0; d < 3; ++d)
-          {
-            r0[d] = A[d] + y * B[d];
-            r2[d] = Cc[d] + y * Dd[d];
-          }
-        // columns of adj: k0 = r1 x r2, k1 = r2 x r0, k2 = r0 x r1;  det = r0 . k0
-        // (the cofactor inverse of poisson_operator.h:41-63 without the division)
-        double k0[3], k1[3], k2[3];
-        k0[0] = R1[1] * r2[2] - R1[2] * r2[1];
-        k0[1] = R1[2] * r2[0] - R1[0] * r2[2];
-        k0[2] = R1[0] * r2[1] - R1[1] * r2[0];
-        k1[0] = r2[1] * r0[2] - r2[2] * r0[1];
-        k1[1] = r2[2] * r0[0] - r2[0] * r0[2];
-        k1[2] = r2[0] * r0[1] - r2[1] * r0[0];
-        k2[0] = r0[1] * R1[2] - r0[2] * R1[1];
-        k2[1] = r0[2] * R1[0] - r0[0] * R1[2];
-        k2[2] = r0[0] * R1[1] - r0[1] * R1[0];
-        const double det = r0[0] * k0[0] + r0[1] * k0[1] + r0[2] * k0[2];
-        // G = (w / det) K^T K  == det * w * J^-1 J^-T  (poisson_operator.h:604-625)
-        const double sc  = (wxz * tb.wq[q]) / det;
-        const double g00 = sc * (k0[0] * k0[0] + k0[1] * k0[1] + k0[2] * k0[2]);
-        const double g01 = sc * (k0[0] * k1[0] + k0[1] * k1[1] + k0[2] * k1[2]);
-        const double g02 = sc * (k0[0] * k2[0] + k0[1] * k2[1] + k0[2] * k2[2]);
-        const double g11 = sc * (k1[0] * k1[0] + k1[1] * k1[1] + k1[2] * k1[2]);
-        const double g12 = sc * (k1[0] * k2[0] + k1[1] * k2[1] + k1[2] * k2[2]);
-        const double g22 = sc * (k2[0] * k2[0] + k2[1] * k2[1] + k2[2] * k2[2]);
-        BP4_UNROLL
-        for (int c = 0; c < 3; ++c)
-          {
-            const double a = gr[c][0][q], b = gr[c][1][q], e = gr[c][2][q];
-            gr[c][0][q] = g00 * a + g01 * b + g02 * e;
-            gr[c][1][q] = g01 * a + g11 * b + g12 * e;
-            gr[c][2][q] = g02 * a + g12 * b + g22 * e;
-          }
-      }
-    // integrate: d/deta^T on the eta-flux (result parked in slot 1 = "value" array), then
-    // y-back-interpolation of the nine lines, again with each matrix entry used nine times
+    double g00[Q], g01[Q], g02[Q], g11[Q], g12[Q], g22[Q];
     {
-      double v[3][Q];
+      double A[3], B[3], R1[3], Cc[3], Dd[3];
       BP4_UNROLL
-      for (int q = 0; q < Q; ++q)
-        BP4_UNROLL
-      for (int i = 0; i < Q; ++i)
+      for (int d = 0; d < 3; ++d)
         {
-          const double d = tb.D[i][q];
-          BP4_UNROLL
-          for (int c = 0; c < 3; ++c)
-            v[c][i] = q == 0 ? d * gr[c][1][0] : v[c][i] + d * gr[c][1][q];
+          const double v1 = cf[3 + d], v3 = cf[6 + d], v4 = cf[9 + d], v9 = cf[12 + d],
+                       v10 = cf[15 + d], v12 = cf[18 + d], v13 = cf[21 + d];
+          A[d]  = v1 + z * v10;
+          B[d]  = v4 + z * v13;
+          R1[d] = (v3 + z * v12) + x * B[d];
+          Cc[d] = v9 + x * v10;
+          Dd[d] = v12 + x * v13;
         }
       BP4_UNROLL
-      for (int c = 0; c < 3; ++c)
-        BP4_UNROLL
       for (int q = 0; q < Q; ++q)
-        gr[c][1][q] = v[c][q];
+        {
+          const double y = tb.xq[q];
+          double       r0[3], r2[3];
+          BP4_UNROLL
+          for (int d = 0; d < 3; ++d)
+            {
+              r0[d] = A[d] + y * B[d];
+              r2[d] = Cc[d] + y * Dd[d];
+            }
+          // columns of adj: k0 = r1 x r2, k1 = r2 x r0, k2 = r0 x r1;  det = r0 . k0
+          // (the cofactor inverse of poisson_operator.h:41-63 without the division)
+          double k0[3], k1[3], k2[3];
+          k0[0] = R1[1] * r2[2] - R1[2] * r2[1];
+          k0[1] = R1[2] * r2[0] - R1[0] * r2[2];
+          k0[2] = R1[0] * r2[1] - R1[1] * r2[0];
+          k1[0] = r2[1] * r0[2] - r2[2] * r0[1];
+          k1[1] = r2[2] * r0[0] - r2[0] * r0[2];
+          k1[2] = r2[0] * r0[1] - r2[1] * r0[0];
+          k2[0] = r0[1] * R1[2] - r0[2] * R1[1];
+          k2[1] = r0[2] * R1[0] - r0[0] * R1[2];
+          k2[2] = r0[0] * R1[1] - r0[1] * R1[0];
+          const double det = r0[0] * k0[0] + r0[1] * k0[1] + r0[2] * k0[2];
+          // == det * w * J^-1 J^-T  (poisson_operator.h:604-625)
+          const double sc = (wxz * tb.wq[q]) / det;
+          g00[q]          = sc * (k0[0] * k0[0] + k0[1] * k0[1] + k0[2] * k0[2]);
+          g01[q]          = sc * (k0[0] * k1[0] + k0[1] * k1[1] + k0[2] * k1[2]);
+          g02[q]          = sc * (k0[0] * k2[0] + k0[1] * k2[1] + k0[2] * k2[2]);
+          g11[q]          = sc * (k1[0] * k1[0] + k1[1] * k1[1] + k1[2] * k1[2]);
+          g12[q]          = sc * (k1[0] * k2[0] + k1[1] * k2[1] + k1[2] * k2[2]);
+          g22[q]          = sc * (k2[0] * k2[0] + k2[1] * k2[1] + k2[2] * k2[2]);
+        }
     }
-    BP4_UNROLL
-    for (int j = 0; j < N; ++j)
+    // --- the three components one after the other (a rolled loop: the unrolled body of one
+    // component is ~1/3 of the instruction footprint, which matters with two warps per
+    // scheduler and a 32 KB instruction cache)
+#ifdef __CUDACC__
+#  pragma unroll 1
+#endif
+    for (int c = 0; c < 3; ++c)
       {
-        double acc[3][3];
+        double *base = work + (c * N) * G::RW + qz * Q + qx; // rows (c, j), j = 0..N-1
+        double  gx[Q], gy[Q], gz[Q], v[Q];
+        // y-interpolation of value, xi-derivative and zeta-derivative lines
+        BP4_UNROLL
+        for (int j = 0; j < N; ++j)
+          {
+            const double r0 = base[j * G::RW], r1 = base[j * G::RW + Q * Q], r2 = base[j * G::RW + 2 * Q * Q];
+            BP4_UNROLL
+            for (int q = 0; q < Q; ++q)
+              {
+                const double sjq = tb.S[j][q];
+                v[q]  = j == 0 ? sjq * r0 : v[q] + sjq * r0;
+                gx[q] = j == 0 ? sjq * r1 : gx[q] + sjq * r1;
+                gz[q] = j == 0 ? sjq * r2 : gz[q] + sjq * r2;
+              }
+          }
+        // d/deta
+        BP4_UNROLL
+        for (int i = 0; i < Q; ++i)
+          BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          gy[q] = i == 0 ? tb.D[0][q] * v[0] : gy[q] + tb.D[i][q] * v[i];
+        // flux = G grad
         BP4_UNROLL
         for (int q = 0; q < Q; ++q)
           {
-            const double sjq = tb.S[j][q];
-            BP4_UNROLL
-            for (int c = 0; c < 3; ++c)
-              BP4_UNROLL
-            for (int e = 0; e < 3; ++e)
-              acc[c][e] = q == 0 ? sjq * gr[c][e][0] : acc[c][e] + sjq * gr[c][e][q];
+            const double a = gx[q], b = gy[q], e = gz[q];
+            gx[q] = g00[q] * a + g01[q] * b + g02[q] * e;
+            gy[q] = g01[q] * a + g11[q] * b + g12[q] * e;
+            gz[q] = g02[q] * a + g12[q] * b + g22[q] * e;
           }
+        // d/deta^T on the eta-flux -> value-like line
         BP4_UNROLL
-        for (int c = 0; c < 3; ++c)
+        for (int q = 0; q < Q; ++q)
           BP4_UNROLL
-        for (int a = 0; a < 3; ++a)
-          base[(c * N + j) * G::RW + a * Q * Q] = acc[c][a == 0 ? 1 : (a == 1 ? 0 : 2)];
+        for (int i = 0; i < Q; ++i)
+          v[i] = q == 0 ? tb.D[i][0] * gy[0] : v[i] + tb.D[i][q] * gy[q];
+        // y-back-interpolation of the three lines
+        BP4_UNROLL
+        for (int j = 0; j < N; ++j)
+          {
+            double o0, o1, o2;
+            BP4_UNROLL
+            for (int q = 0; q < Q; ++q)
+              {
+                const double sjq = tb.S[j][q];
+                o0 = q == 0 ? sjq * v[0] : o0 + sjq * v[q];
+                o1 = q == 0 ? sjq * gx[0] : o1 + sjq * gx[q];
+                o2 = q == 0 ? sjq * gz[0] : o2 + sjq * gz[q];
+              }
+            base[j * G::RW]             = o0;
+            base[j * G::RW + Q * Q]     = o1;
+            base[j * G::RW + 2 * Q * Q] = o2;
+          }
       }
   }
 

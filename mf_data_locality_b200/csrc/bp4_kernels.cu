@@ -31,7 +31,7 @@ namespace bp4
       }
   }
 
-  // phases 1-3 on the nc cells staged in sm.dofs (in place), with the barriers between them
+  // phases 1-3 on the nc cells staged in the work rows (in place), with the barriers between them
   template <int P, int CPB>
   __device__ __forceinline__ void apply_staged(CellSmem<P, CPB> &sm, const int nc)
   {
@@ -40,7 +40,7 @@ namespace bp4
     const Tab<P> &tb = c_tab<P>;
     const int     tid = threadIdx.x;
     for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-      phase1<P>(tb, sm.dofs + it * G::RD, sm.work + it * G::RW);
+      phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
     __syncthreads();
     for (int it = tid; it < nc * G::ITEMS2; it += kThreads)
       {
@@ -51,7 +51,7 @@ namespace bp4
       }
     __syncthreads();
     for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-      phase3<P>(tb, sm.work + it * G::RW, sm.dofs + it * G::RD);
+      phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
     __syncthreads();
   }
 
@@ -93,7 +93,7 @@ namespace bp4
                     const int      cell = m / G::DOF;
                     const uint32_t t    = sm.dtab[m - cell * G::DOF];
                     const uint32_t base = sm.eidx[cell][dtab_ent(t)];
-                    off[u]              = cell * G::DOFS + dtab_off(t);
+                    off[u]              = cell * G::WORK + dtab_off_work<P>(t);
                     if (base != 0xFFFFFFFFu)
                       v[u] = __ldg(a.src + (size_t)base + dtab_rel(t));
                   }
@@ -101,7 +101,7 @@ namespace bp4
 #pragma unroll
             for (int u = 0; u < kPlainUnroll; ++u)
               if (m0 + u * kThreads < total)
-                sm.dofs[off[u]] = v[u];
+                sm.work[off[u]] = v[u];
           }
         __syncthreads();
 
@@ -112,7 +112,7 @@ namespace bp4
         for (int cell = 0; cell < nc; ++cell)
           {
             const uint32_t *eidx = sm.eidx[cell];
-            const double   *dofs = sm.dofs + cell * G::DOFS;
+            const double   *dofs = sm.work + cell * G::WORK;
             for (int r = tid; r < G::DOF; r += kThreads)
               {
                 const uint32_t t    = sm.dtab[r];
@@ -120,7 +120,7 @@ namespace bp4
                 const uint32_t base = eidx[ent];
                 if (base != 0xFFFFFFFFu)
                   {
-                    const double v = dofs[dtab_off(t)];
+                    const double v = dofs[dtab_off_work<P>(t)];
                     double      *p = a.dst + (size_t)base + dtab_rel(t);
                     if (ent == 13u)
                       *p = v;
@@ -227,7 +227,7 @@ namespace bp4
           {
             const uint32_t *eidx = sm.eidx[cell];
             const uint8_t  *meta = sm.meta[cell];
-            double         *dofs = sm.dofs + cell * G::DOFS;
+            double         *dofs = sm.work + cell * G::WORK;
             for (int r0 = tid; r0 < G::DOF; r0 += kThreads * kGatherUnroll)
               {
                 double   rv[kGatherUnroll], pv[kGatherUnroll], hv[kGatherUnroll], dv[kGatherUnroll];
@@ -283,7 +283,7 @@ namespace bp4
                               a.p_new[adr[u]] = pn;
                             }
                         }
-                      dofs[dtab_off(t[u])] = pn;
+                      dofs[dtab_off_work<P>(t[u])] = pn;
                     }
               }
           }
@@ -296,7 +296,7 @@ namespace bp4
         for (int cell = 0; cell < nc; ++cell)
           {
             const uint32_t *eidx = sm.eidx[cell];
-            const double   *dofs = sm.dofs + cell * G::DOFS;
+            const double   *dofs = sm.work + cell * G::WORK;
             for (int r0 = tid; r0 < G::DOF; r0 += kThreads * kGatherUnroll)
               {
                 double rv[kGatherUnroll], pv[kGatherUnroll], dv[kGatherUnroll], hv[kGatherUnroll];
@@ -313,7 +313,7 @@ namespace bp4
                         const uint32_t base = eidx[ent];
                         if (base != 0xFFFFFFFFu)
                           {
-                            const double   v   = dofs[dtab_off(t)];
+                            const double   v   = dofs[dtab_off_work<P>(t)];
                             const uint32_t adr = base + dtab_rel(t);
                             if (ent == 13u)
                               {
@@ -397,6 +397,376 @@ namespace bp4
         __syncthreads();
       }
     block_accumulate<7>(s, a.acc);
+  }
+
+  // ---------------------------------------------------------------------------------------
+  // warp-specialised cell kernel (plain and merged)
+  // ---------------------------------------------------------------------------------------
+  enum : int
+  {
+    kBarInFull  = 1, // memory -> compute : dofs of batch i gathered
+    kBarInFree  = 2, // compute -> memory : phase 1 done, dofs may be overwritten
+    kBarOutFull = 3, // compute -> memory : phase 3 results of batch i are in the work rows
+    kBarOutFree = 4, // memory -> compute : results read, work rows may be overwritten
+    kBarCompute = 5, // compute warpgroup only
+    kBarMemory  = 6  // memory warpgroup only
+  };
+  __device__ __forceinline__ void bar_sync(const int id, const int n)
+  {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+  }
+  __device__ __forceinline__ void bar_arrive(const int id, const int n)
+  {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+  }
+
+  struct WsArgs
+  {
+    // mesh
+    const uint32_t *entity_index;
+    const double   *coef;
+    const uint32_t *dtab;
+    uint64_t        n_cells;
+    // plain: dst += A src
+    const double *src;
+    double       *dst;
+    // merged (see MergedArgs)
+    const uint8_t *meta;
+    uint32_t      *counters;
+    const double  *r_old, *p_old;
+    double        *h_old, *r_new, *p_new, *h_new, *x;
+    const double  *prec;
+    double         alpha, beta, c1, c2;
+    int            update_x;
+    double        *acc;
+  };
+
+  template <int P, int CPB, bool MERGED>
+  __global__ void __launch_bounds__(kWsThreads, kBlocksPerSM) cell_kernel_ws(const WsArgs a)
+  {
+    using G         = Geom<P>;
+    constexpr int Q = G::Q;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WsSmem<P, CPB> &sm  = *reinterpret_cast<WsSmem<P, CPB> *>(smem_raw);
+    const int       tid = threadIdx.x;
+    for (int i = tid; i < G::DOF; i += kWsThreads)
+      sm.dtab[i] = a.dtab[i];
+    if (tid < Q)
+      {
+        sm.xq[tid] = c_tab<P>.xq[tid];
+        sm.wq[tid] = c_tab<P>.wq[tid];
+      }
+    __syncthreads();
+
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    const int      my_n =
+      n_batches > blockIdx.x ? (int)((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    auto batch_cells = [&](const int i, uint64_t &cell0) {
+      cell0 = ((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x) * CPB;
+      return (int)min((uint64_t)CPB, a.n_cells - cell0);
+    };
+
+    if (tid >= 128)
+      {
+        // =========================== memory warpgroup ===================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsRegsMem));
+        const int  t = tid - 128, lane = t & 31, warp = t >> 5;
+        double     s[7]     = {0., 0., 0., 0., 0., 0., 0.};
+        const bool first_it = a.alpha == 0.;
+        constexpr int U     = MERGED ? 2 : 8;
+        for (int i = 0; i <= my_n; ++i)
+          {
+            if (i < my_n)
+              {
+                if (i > 0)
+                  bar_sync(kBarInFree, kWsThreads);
+                uint64_t  cell0;
+                const int nc = batch_cells(i, cell0);
+                const int bf = i & 1;
+                for (int k = t; k < nc * 27; k += 128)
+                  {
+                    sm.eidx[bf][k / 27][k % 27] = a.entity_index[cell0 * 27 + k];
+                    if (MERGED)
+                      sm.meta[bf][k / 27][k % 27] = a.meta[cell0 * 28 + (k / 27) * 28 + k % 27];
+                  }
+                for (int k = t; k < nc * 24; k += 128)
+                  sm.coef[bf][k / 24][k % 24] = a.coef[cell0 * 24 + k];
+                bar_sync(kBarMemory, 128);
+                // gather (+ do_cg_update4b, solver_cg_optimized.h:65-161)
+                const int total = nc * G::DOF;
+                for (int m0 = t; m0 < total; m0 += 128 * U)
+                  {
+                    if (!MERGED)
+                      {
+                        // asynchronous copies (LDGSTS): no registers held, every load of the
+                        // batch in flight at once; src-size 0 zero-fills Dirichlet entities
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                          {
+                            const int m = m0 + u * 128;
+                            if (m < total)
+                              {
+                                const int      cell = m / G::DOF;
+                                const uint32_t tb   = sm.dtab[m - cell * G::DOF];
+                                const uint32_t base = sm.eidx[bf][cell][dtab_ent(tb)];
+                                const bool     ok   = base != 0xFFFFFFFFu;
+                                const double  *g    = a.src + (ok ? (size_t)base + dtab_rel(tb) : 0);
+                                const uint32_t sa   = (uint32_t)__cvta_generic_to_shared(
+                                  sm.dofs + cell * G::DOFS + dtab_off<P>(tb));
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g),
+                                             "r"(ok ? 8 : 0)
+                                             : "memory");
+                              }
+                          }
+                      }
+                    else
+                      {
+                        double   rv[U], pv[U], hv[U], dv[U];
+                        uint32_t off[U], adr[U];
+                        bool     own[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                          {
+                            const int m = m0 + u * 128;
+                            adr[u]      = 0xFFFFFFFFu;
+                            own[u]      = false;
+                            off[u]      = 0;
+                            rv[u] = pv[u] = hv[u] = dv[u] = 0.;
+                            if (m < total)
+                              {
+                                const int      cell = m / G::DOF;
+                                const uint32_t tb   = sm.dtab[m - cell * G::DOF];
+                                const uint32_t ent  = dtab_ent(tb);
+                                const uint32_t base = sm.eidx[bf][cell][ent];
+                                off[u]              = cell * G::DOFS + dtab_off<P>(tb);
+                                if (base != 0xFFFFFFFFu)
+                                  {
+                                    adr[u] = base + dtab_rel(tb);
+                                    own[u] = (sm.meta[bf][cell][ent] & kMetaOwner) != 0;
+                                    rv[u]  = a.r_old[adr[u]];
+                                    dv[u]  = a.prec[adr[u] / 3u];
+                                    if (!first_it)
+                                      {
+                                        pv[u] = a.p_old[adr[u]];
+                                        hv[u] = a.h_old[adr[u]];
+                                      }
+                                  }
+                              }
+                          }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                          if (m0 + u * 128 < total)
+                            {
+                              double pn = 0.;
+                              if (adr[u] != 0xFFFFFFFFu)
+                                {
+                                  const double pr = dv[u];
+                                  double       ri = rv[u];
+                                  if (own[u] && a.update_x)
+                                    a.x[adr[u]] += a.c1 * pv[u] + a.c2 * pr * ri;
+                                  if (first_it)
+                                    pn = -pr * ri;
+                                  else
+                                    {
+                                      ri += a.alpha * hv[u];
+                                      pn = a.beta * pv[u] - pr * ri;
+                                    }
+                                  if (own[u])
+                                    {
+                                      a.r_new[adr[u]] = ri;
+                                      a.p_new[adr[u]] = pn;
+                                    }
+                                }
+                              sm.dofs[off[u]] = pn;
+                            }
+                      }
+                  }
+                if (!MERGED)
+                  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                bar_arrive(kBarInFull, kWsThreads);
+              }
+            if (i > 0)
+              {
+                bar_sync(kBarOutFull, kWsThreads);
+                uint64_t  cell0;
+                const int nc    = batch_cells(i - 1, cell0);
+                const int bf    = (i - 1) & 1;
+                const int total = nc * G::DOF;
+                // scatter-add (vector_access_reduced.h:437-521); cell-interior entity: plain store
+                for (int m0 = t; m0 < total; m0 += 128 * 4)
+                  {
+                    double rv[4], pv[4], dv[4], hv[4];
+                    bool   inner[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                      {
+                        const int m = m0 + u * 128;
+                        inner[u]    = false;
+                        if (m < total)
+                          {
+                            const int      cell = m / G::DOF;
+                            const uint32_t tb   = sm.dtab[m - cell * G::DOF];
+                            const uint32_t ent  = dtab_ent(tb);
+                            const uint32_t base = sm.eidx[bf][cell][ent];
+                            if (base != 0xFFFFFFFFu)
+                              {
+                                const double   v   = sm.work[cell * G::WORK + dtab_off_work<P>(tb)];
+                                const uint32_t adr = base + dtab_rel(tb);
+                                double        *dst = (MERGED ? a.h_new : a.dst) + adr;
+                                if (ent == 13u)
+                                  {
+                                    *dst = v;
+                                    if (MERGED)
+                                      {
+                                        inner[u] = true;
+                                        hv[u]    = v;
+                                        rv[u]    = __ldcg(a.r_new + adr);
+                                        pv[u]    = __ldcg(a.p_new + adr);
+                                        dv[u]    = a.prec[adr / 3u];
+                                      }
+                                  }
+                                else
+                                  atomicAdd(dst, v);
+                              }
+                          }
+                      }
+                    if (MERGED)
+                      {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                          if (inner[u])
+                            post_terms(s, rv[u], pv[u], hv[u], dv[u]);
+                      }
+                  }
+                __syncwarp();
+                if (i < my_n)
+                  bar_arrive(kBarOutFree, kWsThreads);
+                if (MERGED)
+                  {
+                    // last-toucher protocol, see cell_kernel_merged
+                    __threadfence();
+                    if (t == 0)
+                      sm.n_chunks = 0;
+                    bar_sync(kBarMemory, 128);
+                    for (int k = t; k < nc * 27; k += 128)
+                      {
+                        const int      cell = k / 27, ent = k % 27;
+                        const uint32_t base = sm.eidx[bf][cell][ent];
+                        if (ent == 13 || base == 0xFFFFFFFFu)
+                          continue;
+                        const uint32_t nt   = (sm.meta[bf][cell][ent] & 15u);
+                        bool           last = true;
+                        if (nt > 0)
+                          {
+                            last = atomicInc(a.counters + base / 3u, nt) == nt;
+                            if (last)
+                              __threadfence();
+                          }
+                        if (last)
+                          {
+                            const int ex = ent % 3, ey = (ent / 3) % 3, ez = ent / 9;
+                            const int nd =
+                              3 * (ex == 1 ? P - 1 : 1) * (ey == 1 ? P - 1 : 1) * (ez == 1 ? P - 1 : 1);
+                            const int      nch  = (nd + 31) >> 5;
+                            const uint32_t slot = atomicAdd(&sm.n_chunks, (uint32_t)nch);
+                            for (int q = 0; q < nch; ++q)
+                              {
+                                sm.chunk_base[slot + q] = base + 32u * q;
+                                sm.chunk_len[slot + q]  = (uint8_t)min(32, nd - 32 * q);
+                              }
+                          }
+                      }
+                    bar_sync(kBarMemory, 128);
+                    const int n_chunks = (int)sm.n_chunks;
+                    for (int ch0 = warp; ch0 < n_chunks; ch0 += 4 * 4)
+                      {
+                        double rv[4], pv[4], hv[4], dv[4];
+                        bool   ok[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                          {
+                            const int ch = ch0 + u * 4;
+                            ok[u]        = ch < n_chunks && lane < (int)sm.chunk_len[ch < n_chunks ? ch : 0];
+                            if (ok[u])
+                              {
+                                const uint32_t adr = sm.chunk_base[ch] + lane;
+                                hv[u]              = __ldcg(a.h_new + adr);
+                                rv[u]              = __ldcg(a.r_new + adr);
+                                pv[u]              = __ldcg(a.p_new + adr);
+                                dv[u]              = a.prec[adr / 3u];
+                                a.h_old[adr]       = 0.;
+                              }
+                          }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                          if (ok[u])
+                            post_terms(s, rv[u], pv[u], hv[u], dv[u]);
+                      }
+                    bar_sync(kBarMemory, 128); // chunk list is rewritten by the next batch
+                  }
+              }
+          }
+        if (MERGED)
+          {
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+              {
+                s[k] = warp_sum(s[k]);
+                if (lane == 0)
+                  sm.red[k][warp] = s[k];
+              }
+            bar_sync(kBarMemory, 128);
+            if (t < 7)
+              atomicAdd(a.acc + t, sm.red[t][0] + sm.red[t][1] + sm.red[t][2] + sm.red[t][3]);
+          }
+      }
+    else
+      {
+        // =========================== compute warpgroup ==================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsRegsComp));
+        const Tab<P> &tb = c_tab<P>;
+        for (int i = 0; i < my_n; ++i)
+          {
+            uint64_t  cell0;
+            const int nc = batch_cells(i, cell0);
+            const int bf = i & 1;
+            bar_sync(kBarInFull, kWsThreads);
+            if (i > 0)
+              bar_sync(kBarOutFree, kWsThreads);
+            // item -> thread maps are rotated by one warp per phase and batch so that the
+            // partially filled last round does not always land on the same warps (each warp
+            // owns one SM sub-partition's FP64 pipe)
+            const int r1 = (tid + 32 * (i & 3)) & 127, r2 = (tid + 32 * ((i + 1) & 3)) & 127,
+                      r3 = (tid + 32 * ((i + 2) & 3)) & 127;
+            for (int it = r1; it < nc * G::ITEMS13; it += 128)
+              phase1<P>(tb, sm.dofs + it * G::RD, sm.work + it * G::RW);
+            __syncwarp();
+            if (i + 1 < my_n)
+              bar_arrive(kBarInFree, kWsThreads);
+            bar_sync(kBarCompute, 128);
+            {
+              // full rounds first; the ragged tail goes to the rotated thread map
+              const int n2 = nc * G::ITEMS2, full = (n2 / 128) * 128;
+              for (int it = tid; it < full + 128; it += 128)
+                {
+                  const int item = it < full ? it : full + r2;
+                  if (item < n2)
+                    {
+                      const int cell = item / G::ITEMS2, r = item % G::ITEMS2;
+                      const int qz = r / Q, qx = r % Q;
+                      phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx],
+                                sm.xq[qz], sm.wq[qx] * sm.wq[qz]);
+                    }
+                }
+            }
+            bar_sync(kBarCompute, 128);
+            for (int it = r3; it < nc * G::ITEMS13; it += 128)
+              phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+            __syncwarp();
+            bar_arrive(kBarOutFull, kWsThreads);
+          }
+      }
   }
 
   // entity meta data of the fused kernel, built on the device from the entity table alone:
@@ -678,8 +1048,32 @@ namespace bp4
                              (int)sizeof(CellSmem<P, CPB>));
     if (e != cudaSuccess)
       return e;
-    return cudaFuncSetAttribute(cell_kernel_merged<P, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(CellSmem<P, CPB>));
+    e = cudaFuncSetAttribute(cell_kernel_merged<P, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CellSmem<P, CPB>));
+    if (e != cudaSuccess)
+      return e;
+    constexpr int WCPB = WsCfg<P>::CPB;
+    e = cudaFuncSetAttribute(cell_kernel_ws<P, WCPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(WsSmem<P, WCPB>));
+    if (e != cudaSuccess)
+      return e;
+    return cudaFuncSetAttribute(cell_kernel_ws<P, WCPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(WsSmem<P, WCPB>));
+  }
+
+  template <int P>
+  static cudaError_t run_cell_ws(const WsArgs &a, bool merged, int sms, cudaStream_t st)
+  {
+    constexpr int  CPB       = WsCfg<P>::CPB;
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
+    if (grid == 0)
+      return cudaSuccess;
+    if (merged)
+      cell_kernel_ws<P, CPB, true><<<grid, kWsThreads, sizeof(WsSmem<P, CPB>), st>>>(a);
+    else
+      cell_kernel_ws<P, CPB, false><<<grid, kWsThreads, sizeof(WsSmem<P, CPB>), st>>>(a);
+    return cudaGetLastError();
   }
 
   template <int P>
@@ -728,6 +1122,26 @@ namespace bp4
   cudaError_t launch_cell_plain(int degree, const CellArgs &a, int sms, cudaStream_t st)
   {
     BP4_DISPATCH(degree, return run_cell_plain<P>(a, sms, st));
+    return cudaSuccess;
+  }
+
+  cudaError_t launch_cell_ws(int degree, const MergedArgs *m, const CellArgs *p, int sms, cudaStream_t st)
+  {
+    WsArgs a{};
+    if (m)
+      {
+        a.entity_index = m->entity_index, a.coef = m->coef, a.dtab = m->dtab, a.n_cells = m->n_cells;
+        a.meta = m->meta, a.counters = m->counters, a.r_old = m->r_old, a.p_old = m->p_old;
+        a.h_old = m->h_old, a.r_new = m->r_new, a.p_new = m->p_new, a.h_new = m->h_new, a.x = m->x;
+        a.prec = m->prec, a.alpha = m->alpha, a.beta = m->beta, a.c1 = m->c1, a.c2 = m->c2;
+        a.update_x = m->update_x, a.acc = m->acc;
+      }
+    else
+      {
+        a.entity_index = p->entity_index, a.coef = p->coef, a.dtab = p->dtab, a.n_cells = p->n_cells;
+        a.src = p->src, a.dst = p->dst;
+      }
+    BP4_DISPATCH(degree, return run_cell_ws<P>(a, m != nullptr, sms, st));
     return cudaSuccess;
   }
 

@@ -22,7 +22,7 @@ namespace bp4
   struct Cfg
   {
     using G = Geom<P>;
-    static constexpr int per_cell = (G::WORK + G::DOFS + 24) * 8 + 28 * 4 + 28 + 64 * 5 + 16;
+    static constexpr int per_cell = (G::WORK + 24) * 8 + 28 * 4 + 28 + 64 * 5 + 16;
     static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 256) / per_cell;
     // phase 2 carries ~2/3 of the FP64 work: prefer Q^2*CPB close to a multiple of the block
     static constexpr int want = (2 * kThreads) / (G::Q * G::Q) > 0 ? (2 * kThreads) / (G::Q * G::Q) : 1;
@@ -33,8 +33,9 @@ namespace bp4
   struct alignas(16) CellSmem
   {
     using G = Geom<P>;
+    // the gathered DoFs, the three phases and the result all live in the work rows: gather
+    // fills the first N*N slots of each row, phases 1 and 3 run in place
     double   work[CPB * G::WORK];
-    double   dofs[CPB * G::DOFS];
     double   coef[CPB][24];
     double   xq[G::Q];
     double   wq[G::Q];
@@ -76,5 +77,41 @@ namespace bp4
     double          alpha, beta, c1, c2; // c1 = alpha + alpha_old/beta_old, c2 = alpha_old/beta_old
     int             update_x;            // alpha_old != 0
     double         *acc;                 // [7]
+  };
+
+  // ---- warp-specialised variant ------------------------------------------------------------
+  // 256 threads: warps 0-3 = compute warpgroup (phases 1-3, FP64 only), warps 4-7 = memory
+  // warpgroup (metadata, gather + fused pre, scatter + fused post).  setmaxnreg moves registers
+  // from the memory warps to the compute warps; two blocks per SM.
+  constexpr int kWsThreads  = 256;
+  constexpr int kWsRegsComp = 192;
+  constexpr int kWsRegsMem  = 64;
+
+  template <int P>
+  struct WsCfg
+  {
+    using G = Geom<P>;
+    static constexpr int per_cell = (G::WORK + G::DOFS + 2 * 24) * 8 + 2 * 28 * 4 + 2 * 28 + 64 * 5 + 16;
+    static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 512) / per_cell;
+    static constexpr int want = (2 * 128) / (G::Q * G::Q) > 0 ? (2 * 128) / (G::Q * G::Q) : 1;
+    static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
+  };
+
+  template <int P, int CPB>
+  struct alignas(16) WsSmem
+  {
+    using G = Geom<P>;
+    double   work[CPB * G::WORK]; // phase 3 leaves its result in the first N*N slots of each row
+    double   dofs[CPB * G::DOFS]; // gathered input
+    double   coef[2][CPB][24];
+    double   xq[G::Q];
+    double   wq[G::Q];
+    double   red[7][4];
+    uint32_t eidx[2][CPB][28];
+    uint32_t dtab[G::DOF];
+    uint32_t chunk_base[CPB * 64];
+    uint32_t n_chunks;
+    uint8_t  meta[2][CPB][28];
+    uint8_t  chunk_len[CPB * 64];
   };
 } // namespace bp4

@@ -12,6 +12,8 @@ namespace bp4
   cudaError_t launch_init_degree(int degree, std::vector<uint32_t> &walk);
   int         cells_per_block(int degree);
   cudaError_t launch_cell_plain(int degree, const CellArgs &a, int sms, cudaStream_t st);
+  // warp-specialised kernel: pass exactly one of m (merged) / p (plain)
+  cudaError_t launch_cell_ws(int degree, const MergedArgs *m, const CellArgs *p, int sms, cudaStream_t st);
   cudaError_t launch_cell_merged(int degree, const MergedArgs &a, int sms, cudaStream_t st);
   cudaError_t launch_build_meta(uint64_t n_cells, uint64_t n_nodes, const uint32_t *entity_index,
                                 uint32_t *touch, uint32_t *owner, uint8_t *meta, cudaStream_t st);

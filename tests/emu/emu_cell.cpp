@@ -37,7 +37,7 @@ static void run(long n_cells, const uint32_t *eidx, const double *verts, const d
       for (int m = 0; m < G::DOF; ++m)
         {
           const uint32_t t = dtab[m], base = e[bp4::dtab_ent(t)];
-          dofs[bp4::dtab_off(t)] = base != 0xFFFFFFFFu ? src[(size_t)base + bp4::dtab_rel(t)] : 0.;
+          dofs[bp4::dtab_off<P>(t)] = base != 0xFFFFFFFFu ? src[(size_t)base + bp4::dtab_rel(t)] : 0.;
         }
       for (int it = 0; it < G::ITEMS13; ++it)
         bp4::phase1<P>(tb, dofs.data() + it * G::RD, work.data() + it * G::RW);
@@ -52,7 +52,7 @@ static void run(long n_cells, const uint32_t *eidx, const double *verts, const d
         {
           const uint32_t t = dtab[m], base = e[bp4::dtab_ent(t)];
           if (base != 0xFFFFFFFFu)
-            dst[(size_t)base + bp4::dtab_rel(t)] += dofs[bp4::dtab_off(t)];
+            dst[(size_t)base + bp4::dtab_rel(t)] += dofs[bp4::dtab_off<P>(t)];
         }
     }
 }

@@ -14,10 +14,12 @@ VMULT_CASES = [(2, 3), (2, 7), (3, 3), (3, 6), (3, 10), (4, 4), (4, 9), (4, 11),
                (6, 8), (7, 4), (7, 6), (8, 3), (8, 7)]
 
 
+@pytest.mark.parametrize("ws", [0, 1])
 @pytest.mark.parametrize("p,s", VMULT_CASES)
-def test_vmult_matches_oracle(p, s, bp4_lib, c_oracle_lib):
+def test_vmult_matches_oracle(p, s, ws, bp4_lib, c_oracle_lib):
     rd, co = single(p, s)
     ctx = make_ctx(rd)
+    ctx.set_merged_variant(3 * ws)          # plain cell kernel: classic / warp-specialised
     rng = np.random.default_rng(100 * p + s)
     v = rng.standard_normal(rd.n_owned)
     src, dst = ctx.vector(data=v), ctx.vector()
@@ -88,7 +90,7 @@ def test_blas1(bp4_lib):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("p,s", [(3, 6), (4, 7), (6, 4)])
 def test_merged_sums_match_oracle(p, s, variant, bp4_lib, c_oracle_lib):
     """one vmult_with_merged_sums call in each of the three do_cg_update4b regimes"""
@@ -115,7 +117,7 @@ def test_merged_sums_match_oracle(p, s, variant, bp4_lib, c_oracle_lib):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("p,s", [(3, 6), (4, 6), (2, 9)])
 def test_cg_merged_parity(p, s, variant, bp4_lib, c_oracle_lib):
     rd, co = single(p, s)
