@@ -133,15 +133,18 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
-def workload_config(args, n_gpus):
-    nd, nc = n_dofs_of(args.degree, args.s)
+def workload_config(args, n_gpus, s_run=None):
+    s_run = args.s if s_run is None else s_run
+    nd, nc = n_dofs_of(args.degree, s_run)
     plug = "benchmark_precond_merged" if args.solver == "merged" else "benchmark_precond"
-    return {"workload": f"BP4 Q{args.degree} (q={args.degree + 2}) vector Laplace, curved mesh s={args.s}: "
-                        f"{nc} cells, {nd} DoFs per GPU, {plug} (ReductionControl(100,1e-15,1e-8), "
+    return {"workload": f"BP4 Q{args.degree} (q={args.degree + 2}) vector Laplace, curved mesh s={s_run}: "
+                        f"{nc} cells, {nd} DoFs on {n_gpus} GPU(s), {plug} (ReductionControl(100,1e-15,1e-8), "
                         f"Jacobi, RHS i%8), Renumber(0,1,2)",
-            "degree": args.degree, "s": args.s, "n_dofs_per_gpu": nd, "solver": args.solver,
-            "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} replicas (one partition-free problem per GPU)",
-            "l2": "vectors (%.0f MB each) exceed the 126 MB L2; no flush needed" % (nd * 8 / 1e6)}
+            "degree": args.degree, "s": s_run, "n_dofs": nd, "n_dofs_per_gpu": nd // n_gpus, "solver": args.solver,
+            "parallelism": "single GPU" if n_gpus == 1 else
+            f"domain decomposition over {n_gpus} GPUs (contiguous chunks of the cell order), NCCL ghost "
+            f"exchange + 7-double all-reduce per iteration; weak scaling s = {args.s} + log2(N)",
+            "l2": "vectors (%.0f MB per GPU each) exceed the 126 MB L2; no flush needed" % (nd * 8 / 1e6 / n_gpus)}
 
 
 def main():
@@ -178,9 +181,19 @@ def main():
     from mf_data_locality_b200 import capi, host
     import ctypes as C
 
-    prob = host.Problem(args.degree, args.s, plugin=args.solver, device=local_rank)
+    # weak scaling: the mesh grows with the GPU count (s + log2 N: twice the cells per doubling,
+    # SURVEY 8d config 5), partitioned along the renumbered cell order, one partition per GPU
+    s_run = args.s + max(0, world.bit_length() - 1)
+    prob = host.Problem(args.degree, s_run, plugin=args.solver, device=local_rank, n_ranks=world, rank=rank)
     ctx = C.c_void_p(prob.ctx_handle())
     L = capi.lib()
+    if world > 1:
+        idbuf = (C.c_ubyte * 128)()
+        if rank == 0:
+            capi._chk(L.bp4_comm_unique_id(idbuf))
+        idt = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, src=0)
+        prob.comm_init(rank, world, bytes(idt.cpu().tolist()))
     stream_ptr = C.c_void_p()
     L.bp4_ctx_stream(ctx, C.byref(stream_ptr))
     stream = torch.cuda.ExternalStream(stream_ptr.value or 0, device=local_rank)
@@ -218,7 +231,7 @@ def main():
     launches = C.c_uint64()
     L.bp4_launch_count(ctx, C.byref(launches))
     L.bp4_profile_enable(ctx, 0)
-    value = world * n_dofs * iters / (total_ms * 1e-3) * 1e-9
+    value = n_dofs * iters / (total_ms * 1e-3) * 1e-9      # n_dofs is the global count
 
     # ---- end to end: host buffers through the plugin call --------------------------------
     b_host = torch.from_numpy(prob.rhs()).pin_memory()
@@ -236,7 +249,7 @@ def main():
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_dofs * e2e_iters / float(dt.item()) * 1e-9
+    e2e_value = n_dofs * e2e_iters / float(dt.item()) * 1e-9
 
     if rank != 0:
         if world > 1:
@@ -245,8 +258,10 @@ def main():
 
     peak, peak_src = measured_peak()
     merged = args.solver == "merged"
-    alg_bytes = algorithmic_bytes_per_iteration(args.degree, args.s, merged) if merged else \
-        16.0 * n_dofs + 300.0 * (1 << args.s)
+    # per launch = per GPU: this rank's share of the DoFs and cells
+    share = prob.n_owned / n_dofs
+    alg_bytes = (algorithmic_bytes_per_iteration(args.degree, s_run, merged) if merged else
+                 16.0 * n_dofs + 300.0 * (1 << s_run)) * share
     avg_ms = kms.value / max(kcnt.value, 1)
     achieved = alg_bytes / (avg_ms * 1e-3) * 1e-9 if avg_ms > 0 else 0.0
     traffic = None
@@ -276,7 +291,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(args, world), "iterations_per_step": iters // args.steps,
+           "config": workload_config(args, world, s_run), "iterations_per_step": iters // args.steps,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(prob.n_owned * 8),
                    "d2h_bytes_per_step": int(prob.n_owned * 8)},
            "gpu_launches": int(launches.value), "clocks": clocks, "roofline": roofline,

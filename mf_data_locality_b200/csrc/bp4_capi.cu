@@ -448,12 +448,12 @@ int bp4_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src)
     return fail(BP4_ERR_ARG, "vmult: dst aliases src");
   // update_ghost_values / compress(add) around the cell loop (MatrixFree::cell_loop,
   // poisson_operator.h:310); no-ops on a single rank
-  if (c->n_ghost)
+  if (!c->peer.empty())
     if (int e = bp4_update_ghost_values(c, const_cast<bp4_vec *>(src)))
       return e;
   if (int e = cell_loop(c, dst->p(), src->p(), true))
     return e;
-  if (c->n_ghost)
+  if (!c->peer.empty())
     if (int e = bp4_compress_add(c, dst))
       return e;
   {
@@ -485,7 +485,7 @@ int bp4_vmult_merged(bp4_ctx *c, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h,
   if (!prec || prec->n < c->n_owned / 3)
     return fail(BP4_ERR_ARG, "prec needs n_owned/3 entries");
   const uint64_t n = c->n_owned;
-  if (c->merged_variant >= 1 && c->n_ghost == 0)
+  if (c->merged_variant >= 1 && c->peer.empty())
     {
       // single fused kernel; g, d, h ping-pong between two buffers each
       if (!c->d_meta)
@@ -544,7 +544,7 @@ int bp4_vmult_merged(bp4_ctx *c, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h,
     CU(bp4::launch_pre(n, h->p(), x->p(), g->p(), d->p(), prec->p(), alpha, beta, alpha_old, beta_old,
                        c->sms, c->stream));
   }
-  if (c->n_ghost)
+  if (!c->peer.empty())
     {
       if (int e = bp4_update_ghost_values(c, d))
         return e;
@@ -552,7 +552,7 @@ int bp4_vmult_merged(bp4_ctx *c, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h,
     }
   if (int e = cell_loop(c, h->p(), d->p(), false))
     return e;
-  if (c->n_ghost)
+  if (!c->peer.empty())
     if (int e = bp4_compress_add(c, h))
       return e;
   CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 7, c->stream));
@@ -567,23 +567,23 @@ int bp4_inverse_diagonal(bp4_ctx *c, bp4_vec *out)
 {
   if (!c || !out)
     return fail(BP4_ERR_ARG, "null argument");
-  const uint64_t n_nodes = (c->n_owned + c->n_ghost) / 3;
   if (out->n < c->n_owned / 3)
     return fail(BP4_ERR_ARG, "diagonal vector needs n_owned/3 entries");
-  // assemble over owned+ghost nodes, invert, keep the owned part
-  if (c->n_ghost)
-    return fail(BP4_ERR_STATE, "bp4_inverse_diagonal: partitioned meshes need compress(add) of the "
-                               "node-wise diagonal, not implemented yet");
+  // assemble DoF-wise into slot 3*node of a local vector so that the ordinary ghost
+  // compress(add) (poisson_operator.h:419) can be reused, then keep one entry per owned node
   bp4_vec *tmp = nullptr;
-  if (int e = bp4_vec_alloc(c, n_nodes, &tmp))
+  if (int e = bp4_vec_alloc(c, c->n_owned + c->n_ghost, &tmp))
     return e;
   {
-    Timed t(c, BP4_K_BLAS1, 2);
-    CU(bp4::launch_diag(c->degree, c->n_cells, c->d_entity, c->d_coef, c->d_gll, tmp->p(), n_nodes,
-                        c->stream));
+    Timed t(c, BP4_K_BLAS1, 3);
+    CU(bp4::launch_diag_assemble(c->degree, c->n_cells, c->d_entity, c->d_coef, c->d_gll, tmp->p(), 3,
+                                 c->stream));
   }
-  CU(cudaMemcpyAsync(out->p(), tmp->p(), sizeof(double) * (c->n_owned / 3), cudaMemcpyDeviceToDevice,
-                     c->stream));
+  if (!c->peer.empty())
+    if (int e = bp4_compress_add(c, tmp))
+      return e;
+  CU(bp4::launch_stride3(c->n_owned / 3, tmp->p(), out->p(), c->stream));
+  CU(bp4::launch_diag_invert(c->n_owned / 3, out->p(), c->stream));
   return bp4_vec_free(c, tmp);
 }
 
@@ -709,24 +709,62 @@ int bp4_comm_init(bp4_ctx *c, int rank, int n_ranks, const unsigned char id[BP4_
   return 0;
 }
 
+// owners -> ghost copies (LA::distributed::Vector::update_ghost_values): pack the exported owned
+// entries, one ncclSend/ncclRecv pair per peer inside a group, receive straight into the
+// (contiguous, per-owner) ghost blocks
 int bp4_update_ghost_values(bp4_ctx *c, bp4_vec *v)
 {
-  (void)v;
-  if (!c)
-    return fail(BP4_ERR_ARG, "null ctx");
+  if (!c || !v)
+    return fail(BP4_ERR_ARG, "null argument");
   if (c->peer.empty())
     return 0;
-  return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
+  if (!c->comm)
+    return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
+  const uint64_t ne = c->export_off.back();
+  {
+    Timed t(c, BP4_K_BLAS1);
+    CU(bp4::launch_pack(ne, c->d_export, v->p(), c->d_sendbuf, c->stream));
+  }
+  NC(ncclGroupStart());
+  for (size_t k = 0; k < c->peer.size(); ++k)
+    {
+      const uint64_t ns = c->export_off[k + 1] - c->export_off[k], nr = c->import_off[k + 1] - c->import_off[k];
+      if (ns)
+        NC(ncclSend(c->d_sendbuf + c->export_off[k], ns, ncclDouble, c->peer[k], c->comm, c->stream));
+      if (nr)
+        NC(ncclRecv(v->p() + c->n_owned + c->import_off[k], nr, ncclDouble, c->peer[k], c->comm, c->stream));
+    }
+  NC(ncclGroupEnd());
+  return 0;
 }
 
+// ghost contributions -> owners, added (compress(VectorOperation::add)); ghost slots are zeroed
 int bp4_compress_add(bp4_ctx *c, bp4_vec *v)
 {
-  (void)v;
-  if (!c)
-    return fail(BP4_ERR_ARG, "null ctx");
+  if (!c || !v)
+    return fail(BP4_ERR_ARG, "null argument");
   if (c->peer.empty())
     return 0;
-  return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
+  if (!c->comm)
+    return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
+  NC(ncclGroupStart());
+  for (size_t k = 0; k < c->peer.size(); ++k)
+    {
+      const uint64_t nr = c->export_off[k + 1] - c->export_off[k], ns = c->import_off[k + 1] - c->import_off[k];
+      if (ns)
+        NC(ncclSend(v->p() + c->n_owned + c->import_off[k], ns, ncclDouble, c->peer[k], c->comm, c->stream));
+      if (nr)
+        NC(ncclRecv(c->d_recvbuf + c->export_off[k], nr, ncclDouble, c->peer[k], c->comm, c->stream));
+    }
+  NC(ncclGroupEnd());
+  {
+    Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
+    for (size_t k = 0; k < c->peer.size(); ++k) // per peer: an owned entry may be exported to several
+      CU(bp4::launch_unpack_add(c->export_off[k + 1] - c->export_off[k], c->d_export + c->export_off[k],
+                                c->d_recvbuf + c->export_off[k], v->p(), c->stream));
+  }
+  CU(cudaMemsetAsync(v->p() + c->n_owned, 0, sizeof(double) * c->n_ghost, c->stream));
+  return 0;
 }
 
 // ---- measurement -------------------------------------------------------------------------

@@ -920,6 +920,30 @@ namespace bp4
       atomicOr(flag, 1);
   }
 
+  // ghost exchange helpers: buf[k] = v[idx[k]] and v[idx[k]] += buf[k]
+  __global__ void __launch_bounds__(256) pack_kernel(const uint64_t n, const uint32_t *__restrict__ idx,
+                                                     const double *__restrict__ v, double *__restrict__ buf)
+  {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+      buf[i] = v[idx[i]];
+  }
+  __global__ void __launch_bounds__(256) unpack_add_kernel(const uint64_t n, const uint32_t *__restrict__ idx,
+                                                           const double *__restrict__ buf, double *v)
+  {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+      v[idx[i]] += buf[i]; // export lists of different peers may repeat an index: launched per peer
+  }
+  // out[i] = in[3 i]
+  __global__ void __launch_bounds__(256) stride3_kernel(const uint64_t n, const double *__restrict__ in,
+                                                        double *__restrict__ out)
+  {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+      out[i] = in[3 * i];
+  }
+
   // dst[3i+c] = diag[i]*src[3i+c]   (diagonal_matrix_blocked.h:21-26)
   __global__ void __launch_bounds__(256) jacobi_kernel(const uint64_t n, double *__restrict__ dst,
                                                        const double *__restrict__ src,
@@ -982,7 +1006,8 @@ namespace bp4
   __global__ void __launch_bounds__(128) diag_kernel(const int p, const uint64_t n_cells,
                                                      const uint32_t *__restrict__ entity_index,
                                                      const double *__restrict__ coef,
-                                                     const double *__restrict__ gll, double *diag)
+                                                     const double *__restrict__ gll, double *diag,
+                                                     const int stride)
   {
     const int      N  = p + 1, N3 = N * N * N;
     const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1014,7 +1039,7 @@ namespace bp4
     metric_at(cf, x[i], x[j], x[k], w[i] * w[j] * w[k], g00, g01, g02, g11, g12, g22);
     const double di = Dg[i * N + i], dj = Dg[j * N + j], dk = Dg[k * N + k];
     s += 2. * (di * dj * g01 + di * dk * g02 + dj * dk * g12);
-    atomicAdd(diag + (size_t)base / 3 + pos, s);
+    atomicAdd(diag + ((size_t)base / 3 + pos) * stride, s);
   }
 
   __global__ void __launch_bounds__(256) invert_diag_kernel(const uint64_t n, double *d)
@@ -1272,19 +1297,44 @@ namespace bp4
     return cudaGetLastError();
   }
 
-  cudaError_t launch_diag(int degree, uint64_t n_cells, const uint32_t *entity_index, const double *coef,
-                          const double *gll, double *diag, uint64_t n_nodes, cudaStream_t st)
+  // assemble the scalar GLL diagonal: entry of node i goes to diag[i * stride]
+  cudaError_t launch_diag_assemble(int degree, uint64_t n_cells, const uint32_t *entity_index,
+                                   const double *coef, const double *gll, double *diag, int stride,
+                                   cudaStream_t st)
   {
     const int      N3 = (degree + 1) * (degree + 1) * (degree + 1);
     const uint64_t n  = n_cells * N3;
     if (n > 0)
       diag_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(degree, n_cells, entity_index, coef, gll,
-                                                                diag);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess)
-      return e;
+                                                                diag, stride);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_diag_invert(uint64_t n_nodes, double *diag, cudaStream_t st)
+  {
     if (n_nodes > 0)
       invert_diag_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, st>>>(n_nodes, diag);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_pack(uint64_t n, const uint32_t *idx, const double *v, double *buf, cudaStream_t st)
+  {
+    if (n > 0)
+      pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, idx, v, buf);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_unpack_add(uint64_t n, const uint32_t *idx, const double *buf, double *v, cudaStream_t st)
+  {
+    if (n > 0)
+      unpack_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, idx, buf, v);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_stride3(uint64_t n, const double *in, double *out, cudaStream_t st)
+  {
+    if (n > 0)
+      stride3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in, out);
     return cudaGetLastError();
   }
 

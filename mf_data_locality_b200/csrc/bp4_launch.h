@@ -35,7 +35,12 @@ namespace bp4
                             cudaStream_t st);
   cudaError_t launch_xfinal(uint64_t n, double *x, const double *d, const double *g, const double *prec,
                             double c1, double c2, int sms, cudaStream_t st);
-  cudaError_t launch_diag(int degree, uint64_t n_cells, const uint32_t *entity_index, const double *coef,
-                          const double *gll, double *diag, uint64_t n_nodes, cudaStream_t st);
+  cudaError_t launch_diag_assemble(int degree, uint64_t n_cells, const uint32_t *entity_index,
+                                   const double *coef, const double *gll, double *diag, int stride,
+                                   cudaStream_t st);
+  cudaError_t launch_diag_invert(uint64_t n_nodes, double *diag, cudaStream_t st);
+  cudaError_t launch_pack(uint64_t n, const uint32_t *idx, const double *v, double *buf, cudaStream_t st);
+  cudaError_t launch_unpack_add(uint64_t n, const uint32_t *idx, const double *buf, double *v, cudaStream_t st);
+  cudaError_t launch_stride3(uint64_t n, const double *in, double *out, cudaStream_t st);
   void        gll_table(int degree, std::vector<double> &out);
 } // namespace bp4

@@ -97,6 +97,23 @@ class Problem:
         self._chk(self.l.bp4h_get_diagonal(self.h, _p(out)))
         return out
 
+    def plan(self):
+        """ghost exchange plan of the vector partitioner: peers, import/export offsets (DoFs),
+        exported owned local DoF indices"""
+        cnt = (C.c_uint64 * 2)()
+        self._chk(self.l.bp4h_plan_sizes(self.h, cnt))
+        npeer, nexp = int(cnt[0]), int(cnt[1])
+        peers = np.zeros(npeer, dtype=np.int32)
+        io = np.zeros(npeer + 1, dtype=np.uint64)
+        eo = np.zeros(npeer + 1, dtype=np.uint64)
+        ex = np.zeros(max(nexp, 1), dtype=np.uint32)
+        self._chk(self.l.bp4h_get_plan(self.h, _p(peers), _p(io), _p(eo), _p(ex)))
+        return {"rank": peers, "import_offset": io, "export_offset": eo, "export_index": ex[:nexp]}
+
+    def comm_init(self, rank, n_ranks, unique_id: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._chk(self.l.bp4h_comm_init(self.h, C.c_int(rank), C.c_int(n_ranks), buf))
+
     def set_solver(self, max_steps=100, abs_tol=1e-15, rel_tol=1e-8):
         self.l.bp4h_set_solver(max_steps, abs_tol, rel_tol)
 

@@ -178,6 +178,34 @@ int bp4h_get_node_of_local(void *h, std::uint64_t *out)
   });
 }
 
+// exchange plan: counts = [n_peers, n_export]; then peers[n_peers], import_offset[n_peers+1],
+// export_offset[n_peers+1], export_index[n_export]
+int bp4h_plan_sizes(void *h, std::uint64_t *counts)
+{
+  return guarded([&] {
+    const auto &part = *static_cast<ProblemBase *>(h)->mf().get_dof_info().vector_partitioner;
+    counts[0]        = part.peers.size();
+    counts[1]        = part.export_index.size();
+  });
+}
+int bp4h_get_plan(void *h, int *peers, std::uint64_t *import_offset, std::uint64_t *export_offset,
+                  std::uint32_t *export_index)
+{
+  return guarded([&] {
+    const auto &part = *static_cast<ProblemBase *>(h)->mf().get_dof_info().vector_partitioner;
+    std::copy(part.peers.begin(), part.peers.end(), peers);
+    std::copy(part.import_offset.begin(), part.import_offset.end(), import_offset);
+    std::copy(part.export_offset.begin(), part.export_offset.end(), export_offset);
+    std::copy(part.export_index.begin(), part.export_index.end(), export_index);
+  });
+}
+
+// NCCL communicator of the operator's context (rank 0 creates the id with bp4_comm_unique_id)
+int bp4h_comm_init(void *h, int rank, int n_ranks, const unsigned char *id)
+{
+  return guarded([&] { bp4_check(bp4_comm_init(static_cast<ProblemBase *>(h)->ctx(), rank, n_ranks, id)); });
+}
+
 int bp4h_set_solver(unsigned int max_steps, double abs_tol, double rel_tol)
 {
   solver_settings().max_steps = max_steps;

@@ -99,6 +99,73 @@ namespace dealii
           part->ghost_nodes.erase(std::unique(part->ghost_nodes.begin(), part->ghost_nodes.end()),
                                   part->ghost_nodes.end());
         }
+      // point-to-point plan.  Ghosts are sorted by global number and every rank owns a contiguous
+      // global range, so the ghosts owned by one peer are one contiguous block; a peer ghosts
+      // exactly those of my nodes that one of its cells touches.  Both sides derive the same
+      // sets in the same (global number) order, so send and receive counts match by construction.
+      if (tria.n_ranks > 1)
+        {
+          std::vector<std::vector<std::uint32_t>> exports(tria.n_ranks); // owned local node indices
+          std::vector<std::uint64_t>              imports(tria.n_ranks, 0);
+          for (const std::uint32_t g : part->ghost_nodes)
+            {
+              const unsigned int o = (unsigned int)(std::upper_bound(dh.rank_offset.begin(), dh.rank_offset.end(),
+                                                                     (std::uint64_t)g) - dh.rank_offset.begin()) - 1;
+              ++imports[o];
+            }
+          const unsigned int  p     = dh.get_fe().degree;
+          const std::uint64_t first = dh.rank_offset[rank];
+          // my shared owned nodes sit on cells of the comm partition or on inner cells next to
+          // another rank; walk all local cells' nodes once and look at the up-to-8 touching cells
+          std::vector<unsigned char> seen; // per owned node
+          seen.assign(dh.rank_offset[rank + 1] - first, 0);
+          for (std::uint64_t c = c0; c < c1; ++c)
+            dh.for_each_cell_node(c, [&](std::uint64_t node, int, int, int) {
+              if (dh.owner[node] != rank || !dh.shared[node])
+                return;
+              const std::uint32_t ln = dh.node_number[node] - (std::uint32_t)first;
+              if (seen[ln])
+                return;
+              seen[ln] = 1;
+              const std::uint64_t I = node % dh.nn[0], J = (node / dh.nn[0]) % dh.nn[1],
+                                  K = node / (dh.nn[0] * dh.nn[1]);
+              const std::uint64_t idx[3] = {I, J, K};
+              std::uint32_t       lo[3], hi[3];
+              for (int d = 0; d < 3; ++d)
+                {
+                  const std::uint32_t q = (std::uint32_t)(idx[d] / p);
+                  hi[d]                 = std::min<std::uint32_t>(q, tria.n_cells_dir[d] - 1);
+                  lo[d]                 = (idx[d] % p == 0 && q > 0) ? q - 1 : hi[d];
+                }
+              unsigned int ranks[8], nr = 0;
+              for (std::uint32_t z = lo[2]; z <= hi[2]; ++z)
+                for (std::uint32_t y = lo[1]; y <= hi[1]; ++y)
+                  for (std::uint32_t x = lo[0]; x <= hi[0]; ++x)
+                    {
+                      const unsigned int r = tria.subdomain_id(tria.cell_index({{x, y, z}}));
+                      bool               dup = r == rank;
+                      for (unsigned int k = 0; k < nr; ++k)
+                        dup |= ranks[k] == r;
+                      if (!dup)
+                        ranks[nr++] = r;
+                    }
+              for (unsigned int k = 0; k < nr; ++k)
+                exports[ranks[k]].push_back(ln);
+            });
+          part->import_offset.assign(1, 0);
+          part->export_offset.assign(1, 0);
+          for (unsigned int r = 0; r < tria.n_ranks; ++r)
+            if (imports[r] || !exports[r].empty())
+              {
+                std::sort(exports[r].begin(), exports[r].end());
+                part->peers.push_back((int)r);
+                part->import_offset.push_back(part->import_offset.back() + 3 * imports[r]);
+                for (const std::uint32_t ln : exports[r])
+                  for (unsigned int c = 0; c < 3; ++c)
+                    part->export_index.push_back(3 * ln + c);
+                part->export_offset.push_back(part->export_index.size());
+              }
+        }
       dof_info.vector_partitioner = part;
 
       // owned constrained DoFs, local indices ascending (get_constrained_dofs)

@@ -673,6 +673,92 @@ def solver_cg_merged(A_cells, x, b, diag, control: ReductionControl, reduce=lamb
 
 
 # --------------------------------------------------------------------------- #
+# virtual MPI ranks in one process: ghost exchange emulated with numpy
+# --------------------------------------------------------------------------- #
+
+
+def multi_update_ghosts(rds, vecs):
+    """LA::distributed::Vector::update_ghost_values: owners -> ghost copies"""
+    for rd, v in zip(rds, vecs):
+        for g in range(rd.n_ghost // 3):
+            o, l = int(rd.ghost_owner[g]), int(rd.ghost_remote_local[g])
+            v[rd.n_owned + 3 * g: rd.n_owned + 3 * g + 3] = vecs[o][3 * l: 3 * l + 3]
+
+
+def multi_compress_add(rds, vecs):
+    """compress(VectorOperation::add): ghost contributions added into the owners, ghosts zeroed"""
+    for rd, v in zip(rds, vecs):
+        for g in range(rd.n_ghost // 3):
+            o, l = int(rd.ghost_owner[g]), int(rd.ghost_remote_local[g])
+            vecs[o][3 * l: 3 * l + 3] += v[rd.n_owned + 3 * g: rd.n_owned + 3 * g + 3]
+        v[rd.n_owned:] = 0.0
+
+
+def multi_vmult_cells(rds, t, srcs, cell_op=None):
+    """cell loop of every rank with the two exchanges of MatrixFree::cell_loop around it;
+    srcs/dsts are local vectors [owned | ghost]"""
+    srcs = [s.copy() for s in srcs]
+    multi_update_ghosts(rds, srcs)
+    dsts = [(cell_op(rd, s) if cell_op else vmult_cells(rd, t, s)) for rd, s in zip(rds, srcs)]
+    multi_compress_add(rds, dsts)
+    return dsts
+
+
+def multi_vmult(rds, t, srcs, cell_op=None):
+    dsts = multi_vmult_cells(rds, t, srcs, cell_op)
+    for rd, d, s in zip(rds, dsts, srcs):
+        d[rd.constrained] = s[rd.constrained]
+    return dsts
+
+
+def multi_inverse_diagonal(rds):
+    diags = []
+    for rd in rds:
+        d = np.zeros(rd.n_owned + rd.n_ghost)
+        d[0::3] = inverse_diagonal(rd)
+        diags.append(d)
+    multi_compress_add(rds, diags)
+    return [finish_inverse_diagonal(d[: rd.n_owned: 3]) for rd, d in zip(rds, diags)]
+
+
+def multi_cg_merged(rds, t, bs, diags, control: ReductionControl, cell_op=None):
+    """SolverCGFullMerge over virtual ranks: per-rank pre/post sweeps, exchanged cell loop,
+    sums reduced over the ranks (the MPI_Allreduce at poisson_operator.h:373)"""
+    n = [rd.n_owned for rd in rds]
+    prec3 = [np.repeat(d, 3)[:k] for d, k in zip(diags, n)]
+    xs = [np.zeros(rd.n_owned + rd.n_ghost) for rd in rds]
+    gs = [np.concatenate([-b[:k], np.zeros(rd.n_ghost)]) for b, k, rd in zip(bs, n, rds)]
+    ds = [np.zeros(rd.n_owned + rd.n_ghost) for rd in rds]
+    hs = [np.zeros(rd.n_owned + rd.n_ghost) for rd in rds]
+    res = math.sqrt(sum(float(g[:k] @ g[:k]) for g, k in zip(gs, n)))
+    if control.check(0, res) != "iterate":
+        return xs
+    alpha = beta = alpha_old = beta_old = 0.0
+    it = 0
+    while True:
+        it += 1
+        for r in range(len(rds)):
+            k = n[r]
+            cg_update4b(hs[r][:k], xs[r][:k], gs[r][:k], ds[r][:k], prec3[r], alpha, beta,
+                        alpha_old if it % 2 == 1 else 0.0, beta_old)
+        hs = multi_vmult_cells(rds, t, ds, cell_op)
+        S = sum(cg_update3b(gs[r][:n[r]], ds[r][:n[r]], hs[r][:n[r]], prec3[r]) for r in range(len(rds)))
+        alpha_old, beta_old = alpha, beta
+        alpha = S[6] / S[0]
+        res = math.sqrt(S[3] + 2 * alpha * S[2] + alpha * alpha * S[1])
+        if control.check(it, res) != "iterate":
+            for r in range(len(rds)):
+                k = n[r]
+                if it % 2 == 1:
+                    xs[r][:k] += alpha * ds[r][:k]
+                else:
+                    xs[r][:k] += (alpha + alpha_old / beta_old) * ds[r][:k] + (alpha_old / beta_old) * prec3[r] * gs[r][:k]
+            break
+        beta = alpha * (S[4] + alpha * S[5]) / S[6]
+    return xs
+
+
+# --------------------------------------------------------------------------- #
 # independent pin: dense brute-force assembly (no sum factorisation, no entity
 # compression) of the same bilinear form on a handful of cells
 # --------------------------------------------------------------------------- #
