@@ -184,16 +184,15 @@ def main():
     # weak scaling: the mesh grows with the GPU count (s + log2 N: twice the cells per doubling,
     # SURVEY 8d config 5), partitioned along the renumbered cell order, one partition per GPU
     s_run = args.s + max(0, world.bit_length() - 1)
-    prob = host.Problem(args.degree, s_run, plugin=args.solver, device=local_rank, n_ranks=world, rank=rank)
+    nccl_id = None
+    if world > 1:
+        idt = torch.tensor(list(capi.unique_id() if rank == 0 else bytes(128)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, src=0)
+        nccl_id = bytes(idt.cpu().tolist())
+    prob = host.Problem(args.degree, s_run, plugin=args.solver, device=local_rank, n_ranks=world, rank=rank,
+                        nccl_id=nccl_id)
     ctx = C.c_void_p(prob.ctx_handle())
     L = capi.lib()
-    if world > 1:
-        idbuf = (C.c_ubyte * 128)()
-        if rank == 0:
-            capi._chk(L.bp4_comm_unique_id(idbuf))
-        idt = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, src=0)
-        prob.comm_init(rank, world, bytes(idt.cpu().tolist()))
     stream_ptr = C.c_void_p()
     L.bp4_ctx_stream(ctx, C.byref(stream_ptr))
     stream = torch.cuda.ExternalStream(stream_ptr.value or 0, device=local_rank)
@@ -228,6 +227,15 @@ def main():
     total_ms = float(ms.item())
     kms, kcnt = C.c_double(), C.c_uint64()
     L.bp4_profile_get(ctx, kernel_id, C.byref(kms), C.byref(kcnt))
+    kernel_name = "cell_kernel_merged (fused pre + cells + post)" if kernel_id == capi.K_MERGED else "cell_kernel_plain"
+    if kcnt.value == 0:   # merged solver running its three-kernel variant: the cell kernel dominates
+        kernel_id, kernel_name = capi.K_VMULT, "cell_kernel_plain (merged CG = pre + cell + post kernels)"
+        L.bp4_profile_get(ctx, kernel_id, C.byref(kms), C.byref(kcnt))
+    parts = {}
+    for nm, kid in (("cells", capi.K_VMULT), ("merged", capi.K_MERGED), ("pre", capi.K_PRE), ("post", capi.K_POST), ("blas1", capi.K_BLAS1)):
+        a_, b_ = C.c_double(), C.c_uint64()
+        L.bp4_profile_get(ctx, kid, C.byref(a_), C.byref(b_))
+        parts[nm] = {"ms_total": a_.value, "launches": int(b_.value)}
     launches = C.c_uint64()
     L.bp4_launch_count(ctx, C.byref(launches))
     L.bp4_profile_enable(ctx, 0)
@@ -260,8 +268,13 @@ def main():
     merged = args.solver == "merged"
     # per launch = per GPU: this rank's share of the DoFs and cells
     share = prob.n_owned / n_dofs
-    alg_bytes = (algorithmic_bytes_per_iteration(args.degree, s_run, merged) if merged else
+    fused = kernel_id == capi.K_MERGED
+    alg_bytes = (algorithmic_bytes_per_iteration(args.degree, s_run, True) if fused else
                  16.0 * n_dofs + 300.0 * (1 << s_run)) * share
+    # whole CG iteration against the same roof: SURVEY 8(d) bytes per iteration over the
+    # device time of one iteration (all kernels, exchanges and the host round trip for the sums)
+    it_bytes = algorithmic_bytes_per_iteration(args.degree, s_run, merged) * share
+    it_ms = total_ms / max(iters, 1)
     avg_ms = kms.value / max(kcnt.value, 1)
     achieved = alg_bytes / (avg_ms * 1e-3) * 1e-9 if avg_ms > 0 else 0.0
     traffic = None
@@ -271,10 +284,13 @@ def main():
             traffic = json.load(f).get(f"{args.solver}_q{args.degree}_s{args.s}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "cell_kernel_merged" if merged else "cell_kernel_plain",
+                "kernel": kernel_name, "kernels_in_timed_region": parts,
                 "kernel_ms_avg": avg_ms, "kernel_launches": int(kcnt.value),
                 "kernel_share_of_step": kms.value / total_ms if total_ms else None,
-                "algorithmic_bytes_per_launch": alg_bytes}
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "iteration": {"algorithmic_bytes": it_bytes, "ms": it_ms,
+                              "achieved": it_bytes / (it_ms * 1e-3) * 1e-9,
+                              "frac": it_bytes / (it_ms * 1e-3) * 1e-9 / peak}}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

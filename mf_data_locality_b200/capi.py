@@ -77,6 +77,13 @@ def device_count() -> int:
     return n.value
 
 
+def unique_id() -> bytes:
+    """ncclUniqueId for bp4_comm_init (call on rank 0, distribute to the other ranks)"""
+    buf = (C.c_ubyte * 128)()
+    _chk(lib().bp4_comm_unique_id(buf))
+    return bytes(buf)
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 

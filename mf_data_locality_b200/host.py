@@ -42,12 +42,15 @@ class Problem:
     """BenchmarkProblem of host/benchmark.h.  device < 0 builds the tables only (no GPU)."""
 
     def __init__(self, degree, s, plugin="merged", n_ranks=1, rank=0, device=0, n_lanes=8,
-                 batches_per_range=1, renumber=(0, 1, 2)):
+                 batches_per_range=1, renumber=(0, 1, 2), nccl_id: bytes | None = None):
+        """nccl_id: the 128-byte ncclUniqueId shared by all ranks (needed when n_ranks > 1 and a
+        device is used; see capi.unique_id())"""
         self.l = lib(plugin)
         self.plugin = plugin
         opts = (C.c_int * 8)(n_ranks, rank, device, n_lanes, batches_per_range, *renumber)
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(nccl_id) if nccl_id else None
         self.h = C.c_void_p()
-        self._chk(self.l.bp4h_create(C.c_int(degree), C.c_int(s), opts, C.byref(self.h)))
+        self._chk(self.l.bp4h_create(C.c_int(degree), C.c_int(s), opts, idbuf, C.byref(self.h)))
         sz = (C.c_uint64 * 8)()
         self._chk(self.l.bp4h_sizes(self.h, sz))
         (self.n_cells, self.n_owned, self.n_ghost, self.n_dofs, self.n_cells_global, self.n_constrained,
@@ -109,10 +112,6 @@ class Problem:
         ex = np.zeros(max(nexp, 1), dtype=np.uint32)
         self._chk(self.l.bp4h_get_plan(self.h, _p(peers), _p(io), _p(eo), _p(ex)))
         return {"rank": peers, "import_offset": io, "export_offset": eo, "export_index": ex[:nexp]}
-
-    def comm_init(self, rank, n_ranks, unique_id: bytes):
-        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
-        self._chk(self.l.bp4h_comm_init(self.h, C.c_int(rank), C.c_int(n_ranks), buf))
 
     def set_solver(self, max_steps=100, abs_tol=1e-15, rel_tol=1e-8):
         self.l.bp4h_set_solver(max_steps, abs_tol, rel_tol)

@@ -58,6 +58,9 @@ struct BenchmarkOptions
   int          device  = 0;
   unsigned int n_lanes = 8, batches_per_range = 1; // deal.II batch/range model
   unsigned int renumber_a = 0, renumber_r = 1, renumber_g = 2;
+  // multi-GPU: the 128-byte ncclUniqueId all ranks share (created by rank 0 with
+  // bp4_comm_unique_id and distributed by the launcher); plays the role of MPI_COMM_WORLD
+  const unsigned char *nccl_id = nullptr;
 };
 
 class Timer
@@ -112,6 +115,11 @@ struct BenchmarkProblem
     laplace_operator.initialize(matrix_free, constraints, opt.device);
     if (opt.device < 0)
       return; // tables only
+    if (opt.n_ranks > 1)
+      {
+        AssertThrow(opt.nccl_id != nullptr, "n_ranks > 1 needs BenchmarkOptions::nccl_id");
+        bp4_check(bp4_comm_init(laplace_operator.context(), (int)opt.rank, (int)opt.n_ranks, opt.nccl_id));
+      }
     laplace_operator.compute_inverse_diagonal(diag_mat.diagonal);
 
     // right-hand side i % 8 on unconstrained local entries, start vector 0 (benchmark.h:170-176)

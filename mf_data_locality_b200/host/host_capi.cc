@@ -77,10 +77,11 @@ const char *bp4h_plugin(void)
 }
 
 // options: [n_ranks, rank, device, n_lanes, batches_per_range, renumber_a, renumber_r, renumber_g]
-int bp4h_create(int degree, int s, const int *options, void **out)
+int bp4h_create(int degree, int s, const int *options, const unsigned char *nccl_id, void **out)
 {
   return guarded([&] {
     BenchmarkOptions opt;
+    opt.nccl_id = nccl_id;
     if (options)
       {
         opt.n_ranks = options[0], opt.rank = options[1], opt.device = options[2];
@@ -198,12 +199,6 @@ int bp4h_get_plan(void *h, int *peers, std::uint64_t *import_offset, std::uint64
     std::copy(part.export_offset.begin(), part.export_offset.end(), export_offset);
     std::copy(part.export_index.begin(), part.export_index.end(), export_index);
   });
-}
-
-// NCCL communicator of the operator's context (rank 0 creates the id with bp4_comm_unique_id)
-int bp4h_comm_init(void *h, int rank, int n_ranks, const unsigned char *id)
-{
-  return guarded([&] { bp4_check(bp4_comm_init(static_cast<ProblemBase *>(h)->ctx(), rank, n_ranks, id)); });
 }
 
 int bp4h_set_solver(unsigned int max_steps, double abs_tol, double rel_tol)

@@ -25,13 +25,10 @@ def main():
     for (p, s, plugin) in [(3, 6, "merged"), (4, 7, "merged"), (3, 7, "plain"), (2, 9, "merged")]:
         rds = O.build_problem(p, s, n_ranks=world)
         rd = rds[rank]
-        prob = host.Problem(p, s, plugin=plugin, device=lr, n_ranks=world, rank=rank)
-        idbuf = (C.c_ubyte * 128)()
-        if rank == 0:
-            capi._chk(L.bp4_comm_unique_id(idbuf))
-        idt = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
+        idt = torch.tensor(list(capi.unique_id() if rank == 0 else bytes(128)), dtype=torch.uint8, device="cuda")
         dist.broadcast(idt, src=0)
-        prob.comm_init(rank, world, bytes(idt.cpu().tolist()))
+        prob = host.Problem(p, s, plugin=plugin, device=lr, n_ranks=world, rank=rank,
+                            nccl_id=bytes(idt.cpu().tolist()))
         assert np.array_equal(prob.entity_index(), rd.entity_index)
         assert np.array_equal(prob.node_of_local(), rd.node_of_local.astype(np.uint64))
         t = O.make_tables(p)
@@ -49,12 +46,12 @@ def main():
         if plugin == "merged":
             ctl = O.ReductionControl(100, 1e-15, 1e-8)
             xs = O.multi_cg_merged(rds, t, [r.rhs for r in rds], diag, ctl, cell_op=op)
-            x, it = prob.run_cg_solver()
+            x, it = prob.run_cg_solver(rd.rhs)      # vmult() above overwrote the input vector
             assert abs(it - ctl.last_step) <= 1, (it, ctl.last_step)
             errx = np.linalg.norm(x - xs[rank][: rd.n_owned]) / np.linalg.norm(xs[rank][: rd.n_owned])
             assert errx <= (1e-8 if ctl.last_step < 100 else 1e-6), ("x", errx)
         else:
-            x, it = prob.run_cg_solver()
+            x, it = prob.run_cg_solver(rd.rhs)
             assert 0 < it <= 100
         if rank == 0:
             print(f"mgpu ok: Q{p} s={s} {plugin} world={world} vmult {err:.1e} diag {errd:.1e} it {it}", flush=True)
