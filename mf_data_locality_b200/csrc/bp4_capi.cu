@@ -71,13 +71,14 @@ struct bp4_ctx
   uint64_t     n_cells = 0, n_owned = 0, n_ghost = 0, n_constrained = 0;
   cudaStream_t stream = nullptr;
   uint32_t    *d_entity = nullptr, *d_constrained = nullptr, *d_walk = nullptr;
+  uint16_t    *d_stage_tab = nullptr; // TMA variant: slot[28] + inverse table
   double      *d_coef = nullptr, *d_gll = nullptr;
   double      *d_acc  = nullptr; // [8] reduction scratch
   int         *d_flag = nullptr;
   double      *h_acc  = nullptr; // pinned [8]
   int         *h_flag = nullptr; // pinned
   int          merged_variant = 0; // 0 three kernels, 1 fused, 2 fused + warp-specialised
-  int          cell_variant   = 0; // plain cell kernel: 0 classic, 1 warp-specialised
+  int          cell_variant   = 2; // plain cell kernel: 0 TMA, 1 warp-specialised, 2 classic (default), 3 cp.async prefetch
   uint8_t     *d_meta = nullptr;     // fused kernel: per-cell entity meta bytes [n_cells][28]
   uint32_t    *d_counters = nullptr; // fused kernel: arrival counters [n_nodes]
   // multi-GPU
@@ -153,8 +154,8 @@ namespace
         c->pool.erase(it);
       }
     else
-      CU(cudaMalloc(out, sizeof(double) * (n ? n : 1)));
-    CU(cudaMemsetAsync(*out, 0, sizeof(double) * n, c->stream));
+      CU(cudaMalloc(out, sizeof(double) * (n + 2))); // + 2: pad doubles of the TMA bulk copies
+    CU(cudaMemsetAsync(*out, 0, sizeof(double) * (n + 2), c->stream));
     return 0;
   }
 
@@ -221,6 +222,11 @@ int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
   CU(bp4::launch_init_degree(d->degree, walk));
   CU(cudaMalloc(&c->d_walk, sizeof(uint32_t) * walk.size()));
   CU(cudaMemcpy(c->d_walk, walk.data(), sizeof(uint32_t) * walk.size(), cudaMemcpyHostToDevice));
+
+  std::vector<uint16_t> stab;
+  CU(bp4::launch_stage_tables(d->degree, stab));
+  CU(cudaMalloc(&c->d_stage_tab, sizeof(uint16_t) * stab.size()));
+  CU(cudaMemcpy(c->d_stage_tab, stab.data(), sizeof(uint16_t) * stab.size(), cudaMemcpyHostToDevice));
 
   const size_t nc = d->n_cells ? d->n_cells : 1;
   CU(cudaMalloc(&c->d_entity, sizeof(uint32_t) * 27 * nc));
@@ -294,6 +300,7 @@ int bp4_ctx_destroy(bp4_ctx *c)
   cudaFree(c->d_entity);
   cudaFree(c->d_constrained);
   cudaFree(c->d_walk);
+  cudaFree(c->d_stage_tab);
   cudaFree(c->d_coef);
   cudaFree(c->d_gll);
   cudaFree(c->d_acc);
@@ -431,8 +438,24 @@ static int cell_loop(bp4_ctx *c, double *dst, const double *src, bool zero_dst)
   Timed t(c, BP4_K_VMULT);
   if (c->cell_variant == 1)
     CU(bp4::launch_cell_ws(c->degree, nullptr, &a, c->sms, c->stream));
-  else
+  else if (c->cell_variant == 2)
     CU(bp4::launch_cell_plain(c->degree, a, c->sms, c->stream));
+  else if (c->cell_variant == 3)
+    CU(bp4::launch_cell_pf(c->degree, a, c->sms, c->stream));
+  else if (c->cell_variant == 4)
+    CU(bp4::launch_cell_trio(c->degree, a, c->sms, c->stream));
+  else
+    {
+      bp4::TmaArgs t;
+      t.entity_index = c->d_entity;
+      t.coef         = c->d_coef;
+      t.slot         = c->d_stage_tab;
+      t.itab         = c->d_stage_tab + 28;
+      t.n_cells      = c->n_cells;
+      t.src          = src;
+      t.dst          = dst;
+      CU(bp4::launch_cell_tma(c->degree, t, c->sms, c->stream));
+    }
   return 0;
 }
 
@@ -465,9 +488,11 @@ int bp4_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src)
 
 int bp4_set_merged_variant(bp4_ctx *c, int variant)
 {
-  if (!c || variant < 0 || variant > 5)
+  if (!c || variant < 0 || variant > 14)
     return fail(BP4_ERR_ARG, "bad variant");
-  // 0 three kernels, 1 fused, 2 fused + warp-specialised; +3: plain cell kernel warp-specialised
+  // merged: 0 three kernels, 1 fused, 2 fused + warp-specialised;
+  // plain cell kernel: +0 TMA bulk gather/scatter (default), +3 warp-specialised, +6 classic,
+  // +9 cp.async prefetch, +12 trio (256 threads, three lanes per y-line in phase 2)
   c->merged_variant = variant % 3;
   c->cell_variant   = variant / 3;
   return 0;

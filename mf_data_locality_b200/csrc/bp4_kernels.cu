@@ -16,6 +16,9 @@ namespace bp4
   // ---------------------------------------------------------------------------------------
   // cell kernels
   // ---------------------------------------------------------------------------------------
+#ifndef BP4_TAB_IN_SMEM
+#  define BP4_TAB_IN_SMEM 0
+#endif
   constexpr int kGatherUnroll = 4;
   constexpr int kPlainUnroll  = 9;
 
@@ -29,6 +32,8 @@ namespace bp4
         sm.xq[threadIdx.x] = c_tab<P>.xq[threadIdx.x];
         sm.wq[threadIdx.x] = c_tab<P>.wq[threadIdx.x];
       }
+    for (int i = threadIdx.x; i < (int)(sizeof(Tab<P>) / sizeof(double)); i += kThreads)
+      reinterpret_cast<double *>(&sm.tab)[i] = reinterpret_cast<const double *>(&c_tab<P>)[i];
   }
 
   // phases 1-3 on the nc cells staged in the work rows (in place), with the barriers between them
@@ -37,7 +42,7 @@ namespace bp4
   {
     using G          = Geom<P>;
     constexpr int Q  = G::Q;
-    const Tab<P> &tb = c_tab<P>;
+    const Tab<P> &tb = BP4_TAB_IN_SMEM ? sm.tab : c_tab<P>;
     const int     tid = threadIdx.x;
     for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
       phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
@@ -131,6 +136,407 @@ namespace bp4
           }
         __syncthreads();
       }
+  }
+
+  template <int P, int CPB>
+  __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_pf(const CellArgs a)
+  {
+    using G         = Geom<P>;
+    constexpr int Q = G::Q;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PfSmem<P, CPB> &sm  = *reinterpret_cast<PfSmem<P, CPB> *>(smem_raw);
+    const int       tid = threadIdx.x;
+    const Tab<P>   &tb  = c_tab<P>;
+    for (int i = tid; i < G::DOF; i += kThreads)
+      sm.dtab[i] = a.dtab[i];
+    if (tid < Q)
+      {
+        sm.xq[tid] = tb.xq[tid];
+        sm.wq[tid] = tb.wq[tid];
+      }
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    const int      my_n =
+      n_batches > blockIdx.x ? (int)((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    auto batch_cells = [&](const int i, uint64_t &cell0) {
+      cell0 = ((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x) * CPB;
+      return (int)min((uint64_t)CPB, a.n_cells - cell0);
+    };
+    auto load_meta = [&](const int i) {
+      uint64_t  cell0;
+      const int nc = batch_cells(i, cell0), bf = i & 1;
+      for (int k = tid; k < nc * 27; k += kThreads)
+        sm.eidx[bf][k / 27][k % 27] = a.entity_index[cell0 * 27 + k];
+      for (int k = tid; k < nc * 24; k += kThreads)
+        sm.coef[bf][k / 24][k % 24] = a.coef[cell0 * 24 + k];
+    };
+    // asynchronous gather of batch i into sm.dofs (vector_access_reduced.h:175-258)
+    auto issue_gather = [&](const int i) {
+      uint64_t  cell0;
+      const int nc = batch_cells(i, cell0), bf = i & 1;
+      const int total = nc * G::DOF;
+      for (int m = tid; m < total; m += kThreads)
+        {
+          const int      cell = m / G::DOF;
+          const uint32_t t    = sm.dtab[m - cell * G::DOF];
+          const uint32_t base = sm.eidx[bf][cell][dtab_ent(t)];
+          const bool     ok   = base != 0xFFFFFFFFu;
+          const double  *g    = a.src + (ok ? (size_t)base + dtab_rel(t) : 0);
+          const uint32_t sa =
+            (uint32_t)__cvta_generic_to_shared(sm.dofs + cell * G::DOFS + dtab_off<P>(t));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g), "r"(ok ? 8 : 0)
+                       : "memory");
+        }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (my_n > 0)
+      load_meta(0);
+    __syncthreads();
+    if (my_n > 0)
+      issue_gather(0);
+
+    for (int i = 0; i < my_n; ++i)
+      {
+        uint64_t  cell0;
+        const int nc = batch_cells(i, cell0), bf = i & 1;
+        if (i + 1 < my_n)
+          load_meta(i + 1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+          phase1<P>(tb, sm.dofs + it * G::RD, sm.work + it * G::RW);
+        __syncthreads();
+        if (i + 1 < my_n)
+          issue_gather(i + 1);
+        {
+          // full rounds first; the ragged tail rotates over the warps from batch to batch
+          const int n2 = nc * G::ITEMS2, full = (n2 / kThreads) * kThreads;
+          const int rot = (tid + 32 * (i & 3)) & (kThreads - 1);
+          for (int it = tid; it < full + kThreads; it += kThreads)
+            {
+              const int item = it < full ? it : full + rot;
+              if (item < n2)
+                {
+                  const int cell = item / G::ITEMS2, r = item % G::ITEMS2;
+                  const int qz = r / Q, qx = r % Q;
+                  phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
+                            sm.wq[qx] * sm.wq[qz]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+          phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+        __syncthreads();
+        // scatter-add (vector_access_reduced.h:437-521); interior entity: plain store
+        const int total = nc * G::DOF;
+        for (int m = tid; m < total; m += kThreads)
+          {
+            const int      cell = m / G::DOF;
+            const uint32_t t    = sm.dtab[m - cell * G::DOF];
+            const uint32_t ent  = dtab_ent(t);
+            const uint32_t base = sm.eidx[bf][cell][ent];
+            if (base != 0xFFFFFFFFu)
+              {
+                const double v = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
+                double      *p = a.dst + (size_t)base + dtab_rel(t);
+                if (ent == 13u)
+                  *p = v;
+                else
+                  atomicAdd(p, v);
+              }
+          }
+        __syncthreads();
+      }
+  }
+
+  template <int P, int CPB>
+  __global__ void __launch_bounds__(kTrioThreads, kBlocksPerSM) cell_kernel_trio(const CellArgs a)
+  {
+    using G         = Geom<P>;
+    constexpr int Q = G::Q;
+    constexpr int T = kTrioThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
+    const int         tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Tab<P>     &tb  = c_tab<P>;
+    for (int i = tid; i < G::DOF; i += T)
+      sm.dtab[i] = a.dtab[i];
+    if (tid < Q)
+      {
+        sm.xq[tid] = tb.xq[tid];
+        sm.wq[tid] = tb.wq[tid];
+      }
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    for (uint64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x)
+      {
+        const uint64_t cell0 = batch * CPB;
+        const int      nc    = (int)min((uint64_t)CPB, a.n_cells - cell0);
+        for (int i = tid; i < nc * 27; i += T)
+          sm.eidx[i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
+        for (int i = tid; i < nc * 24; i += T)
+          sm.coef[i / 24][i % 24] = a.coef[cell0 * 24 + i];
+        __syncthreads();
+        constexpr int U     = 6;
+        const int     total = nc * G::DOF;
+        for (int m0 = tid; m0 < total; m0 += T * U)
+          {
+            double   v[U];
+            uint32_t off[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              {
+                const int m = m0 + u * T;
+                v[u]        = 0.;
+                off[u]      = 0;
+                if (m < total)
+                  {
+                    const int      cell = m / G::DOF;
+                    const uint32_t t    = sm.dtab[m - cell * G::DOF];
+                    const uint32_t base = sm.eidx[cell][dtab_ent(t)];
+                    off[u]              = cell * G::WORK + dtab_off_work<P>(t);
+                    if (base != 0xFFFFFFFFu)
+                      v[u] = __ldg(a.src + (size_t)base + dtab_rel(t));
+                  }
+              }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (m0 + u * T < total)
+                sm.work[off[u]] = v[u];
+          }
+        __syncthreads();
+        for (int it = tid; it < nc * G::ITEMS13; it += T)
+          phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+        __syncthreads();
+        {
+          // 10 trios (lines) per warp, lanes 30 and 31 idle; every warp runs the same number of
+          // rounds so that the shuffles are always executed by the full trio mask
+          const int n_lines = nc * G::ITEMS2;
+          const int rounds  = (n_lines + 10 * (T / 32) - 1) / (10 * (T / 32));
+          const int trio = lane / 3, c = lane - 3 * trio;
+          for (int r = 0; r < rounds; ++r)
+            {
+              if (lane < 30)
+                {
+                  const int  line   = (r * (T / 32) + warp) * 10 + trio;
+                  const bool active = line < n_lines;
+                  const int  l      = active ? line : 0;
+                  const int  cell = l / G::ITEMS2, rr = l % G::ITEMS2;
+                  const int  qz = rr / Q, qx = rr % Q;
+                  phase2_trio<P>(tb, sm.coef[cell], sm.work + cell * G::WORK, qx, qz, c, 3 * trio, 0x3FFFFFFFu,
+                                 active, sm.xq[qx], sm.xq[qz], sm.wq[qx] * sm.wq[qz]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int it = tid; it < nc * G::ITEMS13; it += T)
+          phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+        __syncthreads();
+        for (int m = tid; m < total; m += T)
+          {
+            const int      cell = m / G::DOF;
+            const uint32_t t    = sm.dtab[m - cell * G::DOF];
+            const uint32_t ent  = dtab_ent(t);
+            const uint32_t base = sm.eidx[cell][ent];
+            if (base != 0xFFFFFFFFu)
+              {
+                const double v = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
+                double      *p = a.dst + (size_t)base + dtab_rel(t);
+                if (ent == 13u)
+                  *p = v;
+                else
+                  atomicAdd(p, v);
+              }
+          }
+        __syncthreads();
+      }
+  }
+
+  // ---- mbarrier / bulk-copy wrappers (PTX ISA: mbarrier, cp.async.bulk, cp.reduce.async.bulk) ----
+  __device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __device__ __forceinline__ void mbar_arrive(const uint32_t bar)
+  {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  }
+  __device__ __forceinline__ void mbar_arrive_expect_tx(const uint32_t bar, const uint32_t bytes)
+  {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  }
+  __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t parity)
+  {
+    asm volatile("{\n\t.reg .pred p;\n"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n\t}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+  }
+  __device__ __forceinline__ void bulk_load(const uint32_t smem_dst, const void *gmem_src, const uint32_t bytes,
+                                            const uint32_t bar)
+  {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  __device__ __forceinline__ void bulk_reduce_add_f64(void *gmem_dst, const uint32_t smem_src, const uint32_t bytes)
+  {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_src), "r"(bytes)
+                 : "memory");
+  }
+
+  template <int P, int CPB>
+  __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_tma(const TmaArgs a)
+  {
+    using G          = Geom<P>;
+    using St         = Stage<P>;
+    constexpr int Q  = G::Q;
+    constexpr int NN = G::N * G::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TmaSmem<P, CPB> &sm   = *reinterpret_cast<TmaSmem<P, CPB> *>(smem_raw);
+    const int        tid  = threadIdx.x;
+    const Tab<P>    &tb   = c_tab<P>;
+    const uint32_t   mbar = (uint32_t)__cvta_generic_to_shared(&sm.mbar);
+    for (int i = tid; i < NN * G::ROWS; i += kThreads)
+      sm.itab[i] = a.itab[i];
+    if (tid < 27)
+      sm.slot[tid] = a.slot[tid];
+    if (tid < Q)
+      {
+        sm.xq[tid] = tb.xq[tid];
+        sm.wq[tid] = tb.wq[tid];
+      }
+    if (tid == 0)
+      mbar_init(mbar, CPB * 27); // every (cell, entity) item arrives once per batch
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    const int      my_n =
+      n_batches > blockIdx.x ? (int)((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    auto batch_cells = [&](const int i, uint64_t &cell0) {
+      cell0 = ((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x) * CPB;
+      return (int)min((uint64_t)CPB, a.n_cells - cell0);
+    };
+    auto load_meta = [&](const int i) {
+      uint64_t  cell0;
+      const int nc = batch_cells(i, cell0), bf = i & 1;
+      for (int k = tid; k < nc * 27; k += kThreads)
+        sm.eidx[bf][k / 27][k % 27] = a.entity_index[cell0 * 27 + k];
+      for (int k = tid; k < nc * 24; k += kThreads)
+        sm.coef[bf][k / 24][k % 24] = a.coef[cell0 * 24 + k];
+    };
+    // gather of batch i: one bulk copy per valid entity, zero-fill for Dirichlet entities
+    auto issue_loads = [&](const int i) {
+      uint64_t  cell0;
+      const int nc = batch_cells(i, cell0), bf = i & 1;
+      for (int k = tid; k < CPB * 27; k += kThreads)
+        {
+          const int cell = k / 27, e = k % 27;
+          if (cell >= nc)
+            {
+              mbar_arrive(mbar);
+              continue;
+            }
+          const uint32_t b    = sm.eidx[bf][cell][e];
+          const uint32_t slot = sm.slot[e];
+          const int      n    = St::n_dofs(e);
+          double        *dst  = sm.stage_in + cell * St::SIZE + slot;
+          if (b == 0xFFFFFFFFu)
+            {
+              sm.off[bf][cell][e] = (uint16_t)slot;
+              for (int q = 0; q < n; ++q)
+                dst[q] = 0.;
+              mbar_arrive(mbar);
+            }
+          else
+            {
+              const uint32_t par  = b & 1u;
+              sm.off[bf][cell][e] = (uint16_t)(slot + par);
+              const uint32_t bytes = (uint32_t)St::r2(n + (int)par) * 8u;
+              mbar_arrive_expect_tx(mbar, bytes);
+              bulk_load((uint32_t)__cvta_generic_to_shared(dst), a.src + (b - par), bytes, mbar);
+            }
+        }
+    };
+
+    if (my_n > 0)
+      load_meta(0);
+    __syncthreads();
+    if (my_n > 0)
+      issue_loads(0);
+
+    for (int i = 0; i < my_n; ++i)
+      {
+        uint64_t  cell0;
+        const int nc = batch_cells(i, cell0), bf = i & 1;
+        mbar_wait(mbar, (uint32_t)(i & 1));                               // stage_in(i) has landed
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // reduces of batch i-1 left stage_out
+        __syncthreads();
+        if (i + 1 < my_n)
+          load_meta(i + 1);
+        // pads of the output stage must add 0.0
+        for (int k = tid; k < nc * 27; k += kThreads)
+          {
+            const int cell = k / 27, e = k % 27;
+            double   *o    = sm.stage_out + cell * St::SIZE + sm.slot[e];
+            const int n    = St::n_dofs(e);
+            o[0]           = 0.;
+            o[n]           = 0.;
+            o[n + 1]       = 0.;
+          }
+        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+          {
+            const int cell = it / G::ROWS, row = it % G::ROWS;
+            phase1_io<P>(tb, StageIn{sm.stage_in + cell * St::SIZE, sm.itab, sm.off[bf][cell], row, G::ROWS},
+                         sm.work + it * G::RW);
+          }
+        __syncthreads();
+        if (i + 1 < my_n)
+          issue_loads(i + 1);
+        {
+          const int n2 = nc * G::ITEMS2, full = (n2 / kThreads) * kThreads;
+          const int rot = (tid + 32 * (i & 3)) & (kThreads - 1);
+          for (int it = tid; it < full + kThreads; it += kThreads)
+            {
+              const int item = it < full ? it : full + rot;
+              if (item < n2)
+                {
+                  const int cell = item / G::ITEMS2, r = item % G::ITEMS2;
+                  const int qz = r / Q, qx = r % Q;
+                  phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
+                            sm.wq[qx] * sm.wq[qz]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+          {
+            const int cell = it / G::ROWS, row = it % G::ROWS;
+            phase3_io<P>(tb, sm.work + it * G::RW,
+                         StageOut{sm.stage_out + cell * St::SIZE, sm.itab, sm.off[bf][cell], row, G::ROWS});
+          }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes -> async proxy reads
+        __syncthreads();
+        // scatter-add: one bulk reduction per valid entity
+        for (int k = tid; k < nc * 27; k += kThreads)
+          {
+            const int      cell = k / 27, e = k % 27;
+            const uint32_t b    = sm.eidx[bf][cell][e];
+            if (b == 0xFFFFFFFFu)
+              continue;
+            const uint32_t par   = b & 1u;
+            const uint32_t bytes = (uint32_t)St::r2(St::n_dofs(e) + (int)par) * 8u;
+            bulk_reduce_add_f64(a.dst + (b - par),
+                                (uint32_t)__cvta_generic_to_shared(sm.stage_out + cell * St::SIZE + sm.slot[e]),
+                                bytes);
+          }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   __device__ __forceinline__ double warp_sum(double v)
@@ -1077,6 +1483,18 @@ namespace bp4
                              (int)sizeof(CellSmem<P, CPB>));
     if (e != cudaSuccess)
       return e;
+    e = cudaFuncSetAttribute(cell_kernel_trio<P, TrioCfg<P>::CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CellSmem<P, TrioCfg<P>::CPB>));
+    if (e != cudaSuccess)
+      return e;
+    e = cudaFuncSetAttribute(cell_kernel_pf<P, PfCfg<P>::CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(PfSmem<P, PfCfg<P>::CPB>));
+    if (e != cudaSuccess)
+      return e;
+    e = cudaFuncSetAttribute(cell_kernel_tma<P, TmaCfg<P>::CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(TmaSmem<P, TmaCfg<P>::CPB>));
+    if (e != cudaSuccess)
+      return e;
     constexpr int WCPB = WsCfg<P>::CPB;
     e = cudaFuncSetAttribute(cell_kernel_ws<P, WCPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(WsSmem<P, WCPB>));
@@ -1114,6 +1532,49 @@ namespace bp4
   }
 
   template <int P>
+  static cudaError_t run_cell_trio(const CellArgs &a, int sms, cudaStream_t st)
+  {
+    constexpr int  CPB       = TrioCfg<P>::CPB;
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
+    if (grid == 0)
+      return cudaSuccess;
+    cell_kernel_trio<P, CPB><<<grid, kTrioThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
+    return cudaGetLastError();
+  }
+
+  template <int P>
+  static cudaError_t run_cell_pf(const CellArgs &a, int sms, cudaStream_t st)
+  {
+    constexpr int  CPB       = PfCfg<P>::CPB;
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
+    if (grid == 0)
+      return cudaSuccess;
+    cell_kernel_pf<P, CPB><<<grid, kThreads, sizeof(PfSmem<P, CPB>), st>>>(a);
+    return cudaGetLastError();
+  }
+
+  template <int P>
+  static cudaError_t run_cell_tma(const TmaArgs &a, int sms, cudaStream_t st)
+  {
+    constexpr int  CPB       = TmaCfg<P>::CPB;
+    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
+    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
+    if (grid == 0)
+      return cudaSuccess;
+    cell_kernel_tma<P, CPB><<<grid, kThreads, sizeof(TmaSmem<P, CPB>), st>>>(a);
+    return cudaGetLastError();
+  }
+
+  template <int P>
+  static void stage_tables(std::vector<uint16_t> &out)
+  {
+    out.assign(28 + Geom<P>::N * Geom<P>::N * Geom<P>::ROWS, 0);
+    build_stage_tables<P>(out.data(), out.data() + 28);
+  }
+
+  template <int P>
   static cudaError_t run_cell_merged(const MergedArgs &a, int sms, cudaStream_t st)
   {
     constexpr int  CPB       = Cfg<P>::CPB;
@@ -1147,6 +1608,31 @@ namespace bp4
   cudaError_t launch_cell_plain(int degree, const CellArgs &a, int sms, cudaStream_t st)
   {
     BP4_DISPATCH(degree, return run_cell_plain<P>(a, sms, st));
+    return cudaSuccess;
+  }
+
+  cudaError_t launch_cell_tma(int degree, const TmaArgs &a, int sms, cudaStream_t st)
+  {
+    BP4_DISPATCH(degree, return run_cell_tma<P>(a, sms, st));
+    return cudaSuccess;
+  }
+
+  // [0,28): slot table, [28, ...): inverse table of the TMA variant
+  cudaError_t launch_stage_tables(int degree, std::vector<uint16_t> &out)
+  {
+    BP4_DISPATCH(degree, stage_tables<P>(out));
+    return cudaSuccess;
+  }
+
+  cudaError_t launch_cell_trio(int degree, const CellArgs &a, int sms, cudaStream_t st)
+  {
+    BP4_DISPATCH(degree, return run_cell_trio<P>(a, sms, st));
+    return cudaSuccess;
+  }
+
+  cudaError_t launch_cell_pf(int degree, const CellArgs &a, int sms, cudaStream_t st)
+  {
+    BP4_DISPATCH(degree, return run_cell_pf<P>(a, sms, st));
     return cudaSuccess;
   }
 

@@ -23,7 +23,7 @@ namespace bp4
   {
     using G = Geom<P>;
     static constexpr int per_cell = (G::WORK + 24) * 8 + 28 * 4 + 28 + 64 * 5 + 16;
-    static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 256) / per_cell;
+    static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 256 - (int)sizeof(Tab<P>)) / per_cell;
     // phase 2 carries ~2/3 of the FP64 work: prefer Q^2*CPB close to a multiple of the block
     static constexpr int want = (2 * kThreads) / (G::Q * G::Q) > 0 ? (2 * kThreads) / (G::Q * G::Q) : 1;
     static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
@@ -39,6 +39,7 @@ namespace bp4
     double   coef[CPB][24];
     double   xq[G::Q];
     double   wq[G::Q];
+    Tab<P>   tab; // shared-memory copy of the 1-D tables (read with broadcast LDS)
     uint32_t eidx[CPB][28];
     uint32_t dtab[G::DOF];
     // merged kernel only
@@ -77,6 +78,95 @@ namespace bp4
     double          alpha, beta, c1, c2; // c1 = alpha + alpha_old/beta_old, c2 = alpha_old/beta_old
     int             update_x;            // alpha_old != 0
     double         *acc;                 // [7]
+  };
+
+  // ---- trio variant: 256 threads, <= 128 registers, phase 2 split over three lanes per y-line --
+  constexpr int kTrioThreads = 256;
+  template <int P>
+  struct TrioCfg
+  {
+    using G = Geom<P>;
+    static constexpr int per_cell = (G::WORK + 24) * 8 + 28 * 4 + 16;
+    static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 256) / per_cell;
+    // lines per round = 10 per warp; prefer a batch that fills whole rounds
+    static constexpr int lines_per_round = 10 * (kTrioThreads / 32);
+    static constexpr int want = (3 * lines_per_round) / (G::Q * G::Q) > 0 ? (3 * lines_per_round) / (G::Q * G::Q) : 1;
+    static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
+  };
+
+  // ---- prefetching variant of the plain cell kernel -------------------------------------------
+  // gather of batch i+1 is issued with cp.async (LDGSTS, zero-filled for Dirichlet entities)
+  // right after phase 1 of batch i has consumed the input staging, so its latency hides behind
+  // phases 2 and 3; the scatter is fire-and-forget (RED).
+  template <int P>
+  struct PfCfg
+  {
+    using G = Geom<P>;
+    static constexpr int per_cell = (G::WORK + G::DOFS + 2 * 24) * 8 + 2 * 28 * 4 + 16;
+    static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 512) / per_cell;
+    static constexpr int want = (2 * kThreads) / (G::Q * G::Q) > 0 ? (2 * kThreads) / (G::Q * G::Q) : 1;
+    static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
+  };
+
+  template <int P, int CPB>
+  struct alignas(16) PfSmem
+  {
+    using G = Geom<P>;
+    double   work[CPB * G::WORK];
+    double   dofs[CPB * G::DOFS];
+    double   coef[2][CPB][24];
+    double   xq[G::Q];
+    double   wq[G::Q];
+    uint32_t eidx[2][CPB][28];
+    uint32_t dtab[G::DOF];
+  };
+
+  // ---- TMA variant of the plain cell kernel ---------------------------------------------------
+  // The 27 entity segments of a cell are contiguous in the vector, so they move as BULK copies:
+  //   gather : cp.async.bulk.shared.global (UBLKCP) per entity, completion on an mbarrier,
+  //            issued one batch ahead (double-buffered stage) so the latency hides behind
+  //            phases 2 and 3;
+  //   scatter: cp.reduce.async.bulk.global.shared .add.f64 (UBLKRED) per entity: the FP64
+  //            scatter-add is done by the TMA unit at L2, not by 375 per-lane REDs per cell.
+  // Segments start at multiples of 24 B; a segment whose first DoF index is odd is moved from
+  // its 16-byte-aligned predecessor with one or two pad doubles (gathered pads are never read,
+  // scattered pads are 0.0 and add nothing).  Vectors carry two doubles of slack for that.
+  template <int P>
+  struct TmaCfg
+  {
+    using G = Geom<P>;
+    static constexpr int per_cell = (G::WORK + 2 * Stage<P>::SIZE + 2 * 24) * 8 + 2 * 28 * 4 + 2 * 28 * 2 + 16;
+    static constexpr int fit      = (kSmemBudget - 2 * G::DOF - 16 * G::Q - 512) / per_cell;
+    static constexpr int want = (2 * kThreads) / (G::Q * G::Q) > 0 ? (2 * kThreads) / (G::Q * G::Q) : 1;
+    static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
+  };
+
+  template <int P, int CPB>
+  struct alignas(16) TmaSmem
+  {
+    using G = Geom<P>;
+    double             work[CPB * G::WORK];
+    alignas(16) double stage_in[CPB * Stage<P>::SIZE]; // bulk copies need 16-byte aligned smem
+    alignas(16) double stage_out[CPB * Stage<P>::SIZE];
+    double             coef[2][CPB][24];
+    double             xq[G::Q];
+    double             wq[G::Q];
+    unsigned long long mbar;
+    uint32_t           eidx[2][CPB][28];
+    uint16_t           off[2][CPB][28]; // slot + (first DoF & 1) of every entity
+    uint16_t           slot[28];
+    uint16_t           itab[G::N * G::N * G::ROWS];
+  };
+
+  struct TmaArgs
+  {
+    const uint32_t *entity_index;
+    const double   *coef;
+    const uint16_t *slot; // [27]
+    const uint16_t *itab; // [N*N][ROWS]
+    uint64_t        n_cells;
+    const double   *src;
+    double         *dst;
   };
 
   // ---- warp-specialised variant ------------------------------------------------------------

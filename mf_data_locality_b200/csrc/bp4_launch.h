@@ -12,6 +12,10 @@ namespace bp4
   cudaError_t launch_init_degree(int degree, std::vector<uint32_t> &walk);
   int         cells_per_block(int degree);
   cudaError_t launch_cell_plain(int degree, const CellArgs &a, int sms, cudaStream_t st);
+  cudaError_t launch_cell_trio(int degree, const CellArgs &a, int sms, cudaStream_t st);
+  cudaError_t launch_cell_pf(int degree, const CellArgs &a, int sms, cudaStream_t st);
+  cudaError_t launch_cell_tma(int degree, const TmaArgs &a, int sms, cudaStream_t st);
+  cudaError_t launch_stage_tables(int degree, std::vector<uint16_t> &out);
   // warp-specialised kernel: pass exactly one of m (merged) / p (plain)
   cudaError_t launch_cell_ws(int degree, const MergedArgs *m, const CellArgs *p, int sms, cudaStream_t st);
   cudaError_t launch_cell_merged(int degree, const MergedArgs &a, int sms, cudaStream_t st);

@@ -14,12 +14,12 @@ VMULT_CASES = [(2, 3), (2, 7), (3, 3), (3, 6), (3, 10), (4, 4), (4, 9), (4, 11),
                (6, 8), (7, 4), (7, 6), (8, 3), (8, 7)]
 
 
-@pytest.mark.parametrize("ws", [0, 1])
+@pytest.mark.parametrize("ws", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("p,s", VMULT_CASES)
 def test_vmult_matches_oracle(p, s, ws, bp4_lib, c_oracle_lib):
     rd, co = single(p, s)
     ctx = make_ctx(rd)
-    ctx.set_merged_variant(3 * ws)          # plain cell kernel: classic / warp-specialised
+    ctx.set_merged_variant(3 * ws)          # plain cell kernel: TMA / warp-specialised / classic / cp.async prefetch
     rng = np.random.default_rng(100 * p + s)
     v = rng.standard_normal(rd.n_owned)
     src, dst = ctx.vector(data=v), ctx.vector()
