@@ -37,7 +37,8 @@ def build_cuda(force=False, verbose=False):
     procs = []
     for s in srcs:
         o = os.path.join(CSRC, os.path.basename(s) + ".o")
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        extra = os.environ.get("BP4_NVCC_EXTRA", "").split()
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(o)
     for cmd, p in procs:

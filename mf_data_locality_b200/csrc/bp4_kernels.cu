@@ -16,9 +16,6 @@ namespace bp4
   // ---------------------------------------------------------------------------------------
   // cell kernels
   // ---------------------------------------------------------------------------------------
-#ifndef BP4_TAB_IN_SMEM
-#  define BP4_TAB_IN_SMEM 0
-#endif
   constexpr int kGatherUnroll = 4;
   constexpr int kPlainUnroll  = 9;
 
@@ -32,8 +29,6 @@ namespace bp4
         sm.xq[threadIdx.x] = c_tab<P>.xq[threadIdx.x];
         sm.wq[threadIdx.x] = c_tab<P>.wq[threadIdx.x];
       }
-    for (int i = threadIdx.x; i < (int)(sizeof(Tab<P>) / sizeof(double)); i += kThreads)
-      reinterpret_cast<double *>(&sm.tab)[i] = reinterpret_cast<const double *>(&c_tab<P>)[i];
   }
 
   // phases 1-3 on the nc cells staged in the work rows (in place), with the barriers between them
@@ -42,7 +37,7 @@ namespace bp4
   {
     using G          = Geom<P>;
     constexpr int Q  = G::Q;
-    const Tab<P> &tb = BP4_TAB_IN_SMEM ? sm.tab : c_tab<P>;
+    const Tab<P> &tb = c_tab<P>;
     const int     tid = threadIdx.x;
     for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
       phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
@@ -51,7 +46,7 @@ namespace bp4
       {
         const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
         const int qz = r / Q, qx = r % Q;
-        phase2<P>(tb, sm.coef[cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
+        phase2<P>(tb, sm.coef[0][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
                   sm.wq[qx] * sm.wq[qz]);
       }
     __syncthreads();
@@ -60,35 +55,102 @@ namespace bp4
     __syncthreads();
   }
 
+  // optional per-phase clock accounting (compile with -DBP4_PHASE_TIMING, run with
+  // BP4_PHASE_TIMING=1): how a warp's time splits over metadata / gather / phases / scatter
+#ifdef BP4_PHASE_TIMING
+  __device__ unsigned long long g_phase_clk[8];
+#  define BP4_TICK_INIT unsigned long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long t0 = clock64();
+#  define BP4_TICK(k) { const long long t1 = clock64(); tc[k] += t1 - t0; t0 = t1; }
+#  define BP4_TICK_FLUSH if ((threadIdx.x & 31) == 0) for (int k = 0; k < 8; ++k) atomicAdd(&g_phase_clk[k], tc[k]);
+#else
+#  define BP4_TICK_INIT
+#  define BP4_TICK(k)
+#  define BP4_TICK_FLUSH
+#endif
+
+  // Classic cell kernel: every warp does every phase; two blocks per SM overlap one block's
+  // memory phases with the other's FP64 phases.  The memory phases are kept short:
+  //  * the next batch's metadata (27 indices + 24 coefficients per cell) is loaded into
+  //    registers before phase 1 and parked in the other half of a double buffer after phase 3;
+  //  * the gather issues all loads of the batch before the first use (one latency, not many);
+  //  * the scatter reads its table/index/value operands for several DoFs before the REDs go out.
   template <int P, int CPB>
   __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_plain(const CellArgs a)
   {
-    using G = Geom<P>;
+    using G         = Geom<P>;
+    constexpr int Q = G::Q;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
     const int         tid = threadIdx.x;
+    const Tab<P>     &tb  = c_tab<P>;
     load_tables<P, CPB>(sm, a.dtab);
+    BP4_TICK_INIT
 
     const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    for (uint64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x)
-      {
-        const uint64_t cell0 = batch * CPB;
-        const int      nc    = (int)min((uint64_t)CPB, a.n_cells - cell0);
-        for (int i = tid; i < nc * 27; i += kThreads)
-          sm.eidx[i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
-        for (int i = tid; i < nc * 24; i += kThreads)
-          sm.coef[i / 24][i % 24] = a.coef[cell0 * 24 + i];
-        __syncthreads();
-
-        // gather (vector_access_reduced.h:175-258): consecutive threads walk an entity's
-        // contiguous DoF segment; kPlainUnroll independent loads in flight per thread
-        const int total = nc * G::DOF;
-        for (int m0 = tid; m0 < total; m0 += kThreads * kPlainUnroll)
-          {
-            double   v[kPlainUnroll];
-            uint32_t off[kPlainUnroll];
+    const int      my_n =
+      n_batches > blockIdx.x ? (int)((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    auto batch_cells = [&](const int i, uint64_t &cell0) {
+      cell0 = ((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x) * CPB;
+      return (int)min((uint64_t)CPB, a.n_cells - cell0);
+    };
+    // metadata items of a batch handled by this thread: at most ME indices and MC coefficients
+    constexpr int ME = (CPB * 27 + kThreads - 1) / kThreads, MC = (CPB * 24 + kThreads - 1) / kThreads;
+    uint32_t      me[ME];
+    double        mc[MC];
+    auto          fetch_meta = [&](const int i) {
+      uint64_t  cell0;
+      const int nc = batch_cells(i, cell0);
 #pragma unroll
-            for (int u = 0; u < kPlainUnroll; ++u)
+      for (int u = 0; u < ME; ++u)
+        {
+          const int k = tid + u * kThreads;
+          me[u]       = k < nc * 27 ? __ldg(a.entity_index + cell0 * 27 + k) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+      for (int u = 0; u < MC; ++u)
+        {
+          const int k = tid + u * kThreads;
+          mc[u]       = k < nc * 24 ? __ldg(a.coef + cell0 * 24 + k) : 0.;
+        }
+    };
+    auto park_meta = [&](const int bf) {
+#pragma unroll
+      for (int u = 0; u < ME; ++u)
+        {
+          const int k = tid + u * kThreads;
+          if (k < CPB * 27)
+            sm.eidx[bf][k / 27][k % 27] = me[u];
+        }
+#pragma unroll
+      for (int u = 0; u < MC; ++u)
+        {
+          const int k = tid + u * kThreads;
+          if (k < CPB * 24)
+            sm.coef[bf][k / 24][k % 24] = mc[u];
+        }
+    };
+    if (my_n > 0)
+      {
+        fetch_meta(0);
+        park_meta(0);
+      }
+    __syncthreads();
+
+    for (int i = 0; i < my_n; ++i)
+      {
+        uint64_t  cell0;
+        const int nc = batch_cells(i, cell0), bf = i & 1;
+        BP4_TICK(0)
+        // gather (vector_access_reduced.h:175-258): consecutive threads walk an entity's
+        // contiguous DoF segment; all loads of the batch are issued before the first use
+        constexpr int GU    = 16;
+        const int     total = nc * G::DOF;
+        for (int m0 = tid; m0 < total; m0 += kThreads * GU)
+          {
+            double   v[GU];
+            uint32_t off[GU];
+#pragma unroll
+            for (int u = 0; u < GU; ++u)
               {
                 const int m = m0 + u * kThreads;
                 v[u]        = 0.;
@@ -97,45 +159,88 @@ namespace bp4
                   {
                     const int      cell = m / G::DOF;
                     const uint32_t t    = sm.dtab[m - cell * G::DOF];
-                    const uint32_t base = sm.eidx[cell][dtab_ent(t)];
+                    const uint32_t base = sm.eidx[bf][cell][dtab_ent(t)];
                     off[u]              = cell * G::WORK + dtab_off_work<P>(t);
                     if (base != 0xFFFFFFFFu)
                       v[u] = __ldg(a.src + (size_t)base + dtab_rel(t));
                   }
               }
 #pragma unroll
-            for (int u = 0; u < kPlainUnroll; ++u)
+            for (int u = 0; u < GU; ++u)
               if (m0 + u * kThreads < total)
                 sm.work[off[u]] = v[u];
           }
+        BP4_TICK(1)
         __syncthreads();
-
-        apply_staged<P, CPB>(sm, nc);
-
+        BP4_TICK(2)
+        if (i + 1 < my_n)
+          fetch_meta(i + 1); // lands during the phases
+        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+          phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+        BP4_TICK(3)
+        __syncthreads();
+        BP4_TICK(2)
+        for (int it = tid; it < nc * G::ITEMS2; it += kThreads)
+          {
+            const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
+            const int qz = r / Q, qx = r % Q;
+            phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
+                      sm.wq[qx] * sm.wq[qz]);
+          }
+        BP4_TICK(4)
+        __syncthreads();
+        BP4_TICK(2)
+        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+          phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+        if (i + 1 < my_n)
+          park_meta(bf ^ 1);
+        BP4_TICK(5)
+        __syncthreads();
+        BP4_TICK(2)
         // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13) is
         // touched by this cell only -> plain store
-        for (int cell = 0; cell < nc; ++cell)
+        constexpr int SU = 6;
+        for (int m0 = tid; m0 < total; m0 += kThreads * SU)
           {
-            const uint32_t *eidx = sm.eidx[cell];
-            const double   *dofs = sm.work + cell * G::WORK;
-            for (int r = tid; r < G::DOF; r += kThreads)
+            double   v[SU];
+            uint32_t adr[SU];
+            bool     inner[SU];
+#pragma unroll
+            for (int u = 0; u < SU; ++u)
               {
-                const uint32_t t    = sm.dtab[r];
-                const uint32_t ent  = dtab_ent(t);
-                const uint32_t base = eidx[ent];
-                if (base != 0xFFFFFFFFu)
+                const int m = m0 + u * kThreads;
+                adr[u]      = 0xFFFFFFFFu;
+                inner[u]    = false;
+                v[u]        = 0.;
+                if (m < total)
                   {
-                    const double v = dofs[dtab_off_work<P>(t)];
-                    double      *p = a.dst + (size_t)base + dtab_rel(t);
-                    if (ent == 13u)
-                      *p = v;
-                    else
-                      atomicAdd(p, v);
+                    const int      cell = m / G::DOF;
+                    const uint32_t t    = sm.dtab[m - cell * G::DOF];
+                    const uint32_t ent  = dtab_ent(t);
+                    const uint32_t base = sm.eidx[bf][cell][ent];
+                    if (base != 0xFFFFFFFFu)
+                      {
+                        adr[u]   = base + dtab_rel(t);
+                        inner[u] = ent == 13u;
+                        v[u]     = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
+                      }
                   }
               }
+#pragma unroll
+            for (int u = 0; u < SU; ++u)
+              if (adr[u] != 0xFFFFFFFFu)
+                {
+                  if (inner[u])
+                    a.dst[adr[u]] = v[u];
+                  else
+                    atomicAdd(a.dst + adr[u], v[u]);
+                }
           }
+        BP4_TICK(6)
         __syncthreads();
+        BP4_TICK(2)
       }
+    BP4_TICK_FLUSH
   }
 
   template <int P, int CPB>
@@ -273,9 +378,9 @@ namespace bp4
         const uint64_t cell0 = batch * CPB;
         const int      nc    = (int)min((uint64_t)CPB, a.n_cells - cell0);
         for (int i = tid; i < nc * 27; i += T)
-          sm.eidx[i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
+          sm.eidx[0][i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
         for (int i = tid; i < nc * 24; i += T)
-          sm.coef[i / 24][i % 24] = a.coef[cell0 * 24 + i];
+          sm.coef[0][i / 24][i % 24] = a.coef[cell0 * 24 + i];
         __syncthreads();
         constexpr int U     = 6;
         const int     total = nc * G::DOF;
@@ -293,7 +398,7 @@ namespace bp4
                   {
                     const int      cell = m / G::DOF;
                     const uint32_t t    = sm.dtab[m - cell * G::DOF];
-                    const uint32_t base = sm.eidx[cell][dtab_ent(t)];
+                    const uint32_t base = sm.eidx[0][cell][dtab_ent(t)];
                     off[u]              = cell * G::WORK + dtab_off_work<P>(t);
                     if (base != 0xFFFFFFFFu)
                       v[u] = __ldg(a.src + (size_t)base + dtab_rel(t));
@@ -323,7 +428,7 @@ namespace bp4
                   const int  l      = active ? line : 0;
                   const int  cell = l / G::ITEMS2, rr = l % G::ITEMS2;
                   const int  qz = rr / Q, qx = rr % Q;
-                  phase2_trio<P>(tb, sm.coef[cell], sm.work + cell * G::WORK, qx, qz, c, 3 * trio, 0x3FFFFFFFu,
+                  phase2_trio<P>(tb, sm.coef[0][cell], sm.work + cell * G::WORK, qx, qz, c, 3 * trio, 0x3FFFFFFFu,
                                  active, sm.xq[qx], sm.xq[qz], sm.wq[qx] * sm.wq[qz]);
                 }
             }
@@ -337,7 +442,7 @@ namespace bp4
             const int      cell = m / G::DOF;
             const uint32_t t    = sm.dtab[m - cell * G::DOF];
             const uint32_t ent  = dtab_ent(t);
-            const uint32_t base = sm.eidx[cell][ent];
+            const uint32_t base = sm.eidx[0][cell][ent];
             if (base != 0xFFFFFFFFu)
               {
                 const double v = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
@@ -619,11 +724,11 @@ namespace bp4
         const int      nc    = (int)min((uint64_t)CPB, a.n_cells - cell0);
         for (int i = tid; i < nc * 27; i += kThreads)
           {
-            sm.eidx[i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
+            sm.eidx[0][i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
             sm.meta[i / 27][i % 27] = a.meta[cell0 * 28 + (i / 27) * 28 + i % 27];
           }
         for (int i = tid; i < nc * 24; i += kThreads)
-          sm.coef[i / 24][i % 24] = a.coef[cell0 * 24 + i];
+          sm.coef[0][i / 24][i % 24] = a.coef[cell0 * 24 + i];
         if (tid == 0)
           sm.n_chunks = 0;
         __syncthreads();
@@ -631,7 +736,7 @@ namespace bp4
         // gather + do_cg_update4b (solver_cg_optimized.h:65-161)
         for (int cell = 0; cell < nc; ++cell)
           {
-            const uint32_t *eidx = sm.eidx[cell];
+            const uint32_t *eidx = sm.eidx[0][cell];
             const uint8_t  *meta = sm.meta[cell];
             double         *dofs = sm.work + cell * G::WORK;
             for (int r0 = tid; r0 < G::DOF; r0 += kThreads * kGatherUnroll)
@@ -701,7 +806,7 @@ namespace bp4
         // with its do_cg_update3b terms taken on the spot
         for (int cell = 0; cell < nc; ++cell)
           {
-            const uint32_t *eidx = sm.eidx[cell];
+            const uint32_t *eidx = sm.eidx[0][cell];
             const double   *dofs = sm.work + cell * G::WORK;
             for (int r0 = tid; r0 < G::DOF; r0 += kThreads * kGatherUnroll)
               {
@@ -748,7 +853,7 @@ namespace bp4
         for (int i = tid; i < nc * 27; i += kThreads)
           {
             const int      cell = i / 27, ent = i % 27;
-            const uint32_t base = sm.eidx[cell][ent];
+            const uint32_t base = sm.eidx[0][cell][ent];
             if (ent == 13 || base == 0xFFFFFFFFu)
               continue;
             const uint32_t nt   = (sm.meta[cell][ent] & 15u); // touching cells - 1
@@ -1528,6 +1633,19 @@ namespace bp4
     if (grid == 0)
       return cudaSuccess;
     cell_kernel_plain<P, CPB><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
+#ifdef BP4_PHASE_TIMING
+    if (getenv("BP4_PHASE_TIMING"))
+      {
+        cudaStreamSynchronize(st);
+        unsigned long long h[8], z[8] = {0};
+        cudaMemcpyFromSymbol(h, g_phase_clk, sizeof(h));
+        cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
+        const double tot = double(h[0] + h[1] + h[2] + h[3] + h[4] + h[5] + h[6]);
+        fprintf(stderr, "phase clk share: meta %.1f%% gather %.1f%% barrier %.1f%% P1 %.1f%% P2 %.1f%% P3 %.1f%% scatter %.1f%% | per-warp total %.0f clk\n",
+                100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot,
+                100 * h[5] / tot, 100 * h[6] / tot, tot / (grid * (kThreads / 32)));
+      }
+#endif
     return cudaGetLastError();
   }
 

@@ -22,8 +22,8 @@ namespace bp4
   struct Cfg
   {
     using G = Geom<P>;
-    static constexpr int per_cell = (G::WORK + 24) * 8 + 28 * 4 + 28 + 64 * 5 + 16;
-    static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 256 - (int)sizeof(Tab<P>)) / per_cell;
+    static constexpr int per_cell = (G::WORK + 2 * 24) * 8 + 2 * 28 * 4 + 28 + 64 * 5 + 16;
+    static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 256) / per_cell;
     // phase 2 carries ~2/3 of the FP64 work: prefer Q^2*CPB close to a multiple of the block
     static constexpr int want = (2 * kThreads) / (G::Q * G::Q) > 0 ? (2 * kThreads) / (G::Q * G::Q) : 1;
     static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
@@ -36,11 +36,10 @@ namespace bp4
     // the gathered DoFs, the three phases and the result all live in the work rows: gather
     // fills the first N*N slots of each row, phases 1 and 3 run in place
     double   work[CPB * G::WORK];
-    double   coef[CPB][24];
+    double   coef[2][CPB][24]; // double-buffered: the next batch's metadata is prefetched
     double   xq[G::Q];
     double   wq[G::Q];
-    Tab<P>   tab; // shared-memory copy of the 1-D tables (read with broadcast LDS)
-    uint32_t eidx[CPB][28];
+    uint32_t eidx[2][CPB][28];
     uint32_t dtab[G::DOF];
     // merged kernel only
     uint8_t  meta[CPB][28];
