@@ -17,6 +17,23 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--threads", "0"]
 
 
+def _nccl_dir():
+    """site-packages/nvidia/nccl of the interpreter's environment (the NCCL torch loads)"""
+    for p in sys.path:
+        d = os.path.join(p, "nvidia", "nccl")
+        if os.path.isdir(os.path.join(d, "lib")):
+            return d
+    return None
+
+
+def _nccl_include():
+    d = _nccl_dir()
+    return ["-I", os.path.join(d, "include")] if d and os.path.exists(os.path.join(d, "include", "nccl.h")) else []
+
+
+NCCL_INC = _nccl_include()
+
+
 def _newer(target, sources):
     if not os.path.exists(target):
         return True
@@ -38,13 +55,21 @@ def build_cuda(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(CSRC, os.path.basename(s) + ".o")
         extra = os.environ.get("BP4_NVCC_EXTRA", "").split()
-        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = ["nvcc"] + NVCC_FLAGS + NCCL_INC + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(o)
     for cmd, p in procs:
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lnccl", "-lcudart"]
+    # link the NCCL that torch bundles (torch.distributed loads it too: one NCCL per process);
+    # fall back to the system library
+    nccl = []
+    d = _nccl_dir()
+    if d and os.path.exists(os.path.join(d, "lib", "libnccl.so.2")):
+        nccl = ["-L", os.path.join(d, "lib"), "-l:libnccl.so.2", "-Xlinker", "-rpath", "-Xlinker",
+                os.path.join(d, "lib")]
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + \
+          (nccl or ["-lnccl"]) + ["-lcudart"]
     subprocess.check_call(cmd)
     return LIB
 
