@@ -175,7 +175,10 @@ namespace bp4
         BP4_TICK(2)
         if (i + 1 < my_n)
           fetch_meta(i + 1); // lands during the phases
-        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+        // phase 1/3 items are handed out from the LAST thread downwards: the ragged final round
+        // of phase 2 lands on the first warps, so the two kinds of partial rounds end up on
+        // different warps (= different SM sub-partitions) instead of piling up on warp 0
+        for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
           phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
         BP4_TICK(3)
         __syncthreads();
@@ -190,7 +193,7 @@ namespace bp4
         BP4_TICK(4)
         __syncthreads();
         BP4_TICK(2)
-        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
+        for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
           phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
         if (i + 1 < my_n)
           park_meta(bf ^ 1);
