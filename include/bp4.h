@@ -73,6 +73,11 @@ typedef struct bp4_desc
   const uint64_t *import_offset;  /* [n_peers + 1] */
   const uint64_t *export_offset;  /* [n_peers + 1] */
   const uint32_t *export_index;   /* [export_offset[n_peers]] */
+  /* cell partitions of MatrixFree::cell_loop: cells [0, n_cells_before_comm)
+   * and [n_cells_before_comm + n_cells_comm, n_cells) touch no ghost DoF; the exchange of
+   * ghost values / ghost contributions is overlapped with them.  0/0 = no overlap.           */
+  uint64_t n_cells_before_comm;
+  uint64_t n_cells_comm;
 } bp4_desc;
 
 const char *bp4_last_error(void);

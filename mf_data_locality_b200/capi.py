@@ -28,7 +28,8 @@ class _Desc(C.Structure):
                 ("entity_index", C.c_void_p), ("vertices", C.c_void_p),
                 ("n_constrained", C.c_uint64), ("constrained", C.c_void_p),
                 ("n_peers", C.c_int), ("peer_rank", C.c_void_p), ("import_offset", C.c_void_p),
-                ("export_offset", C.c_void_p), ("export_index", C.c_void_p)]
+                ("export_offset", C.c_void_p), ("export_index", C.c_void_p),
+                ("n_cells_before_comm", C.c_uint64), ("n_cells_comm", C.c_uint64)]
 
 
 _lib = None

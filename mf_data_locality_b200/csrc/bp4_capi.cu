@@ -69,6 +69,10 @@ struct bp4_ctx
 {
   int          degree = 0, device = 0, sms = 0;
   uint64_t     n_cells = 0, n_owned = 0, n_ghost = 0, n_constrained = 0;
+  uint64_t     n_before = 0, n_comm = 0; // cell partitions for the overlapped exchange
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t  ev_a = nullptr, ev_b = nullptr;
+  int          overlap = 1;
   cudaStream_t stream = nullptr;
   uint32_t    *d_entity = nullptr, *d_constrained = nullptr, *d_walk = nullptr;
   uint16_t    *d_stage_tab = nullptr; // TMA variant: slot[28] + inverse table
@@ -215,8 +219,18 @@ int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
   c->n_owned = d->n_owned;
   c->n_ghost = d->n_ghost;
   c->n_constrained = d->n_constrained;
+  c->n_before      = d->n_cells_before_comm;
+  c->n_comm        = d->n_cells_comm;
+  if (c->n_before + c->n_comm > c->n_cells)
+    {
+      delete c;
+      return fail(BP4_ERR_ARG, "cell partitions exceed n_cells");
+    }
   CU(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, d->device));
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
 
   std::vector<uint32_t> walk;
   CU(bp4::launch_init_degree(d->degree, walk));
@@ -312,6 +326,9 @@ int bp4_ctx_destroy(bp4_ctx *c)
   cudaFree(c->d_recvbuf);
   cudaFreeHost(c->h_acc);
   cudaFreeHost(c->h_flag);
+  cudaEventDestroy(c->ev_a);
+  cudaEventDestroy(c->ev_b);
+  cudaStreamDestroy(c->comm_stream);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -422,17 +439,16 @@ static int check_len(const bp4_ctx *c, const bp4_vec *v, const char *name)
   return 0;
 }
 
-// cell loop: dst = sum_cells A_cell src on the local vector (owned + ghost slots)
-static int cell_loop(bp4_ctx *c, double *dst, const double *src, bool zero_dst)
+// cell loop over the cells [begin, end): dst += sum_cells A_cell src on the local vector
+static int cell_range(bp4_ctx *c, double *dst, const double *src, uint64_t begin, uint64_t end)
 {
-  const uint64_t n = c->n_owned + c->n_ghost;
-  if (zero_dst)
-    CU(cudaMemsetAsync(dst, 0, sizeof(double) * n, c->stream));
+  if (end <= begin)
+    return 0;
   bp4::CellArgs a;
-  a.entity_index = c->d_entity;
-  a.coef         = c->d_coef;
+  a.entity_index = c->d_entity + 27 * begin;
+  a.coef         = c->d_coef + 24 * begin;
   a.dtab         = c->d_walk;
-  a.n_cells      = c->n_cells;
+  a.n_cells      = end - begin;
   a.src          = src;
   a.dst          = dst;
   Timed t(c, BP4_K_VMULT);
@@ -447,15 +463,65 @@ static int cell_loop(bp4_ctx *c, double *dst, const double *src, bool zero_dst)
   else
     {
       bp4::TmaArgs t;
-      t.entity_index = c->d_entity;
-      t.coef         = c->d_coef;
+      t.entity_index = a.entity_index;
+      t.coef         = a.coef;
       t.slot         = c->d_stage_tab;
       t.itab         = c->d_stage_tab + 28;
-      t.n_cells      = c->n_cells;
+      t.n_cells      = a.n_cells;
       t.src          = src;
       t.dst          = dst;
       CU(bp4::launch_cell_tma(c->degree, t, c->sms, c->stream));
     }
+  return 0;
+}
+
+static int exchange_ghosts_on(bp4_ctx *c, double *v, cudaStream_t st);
+static int exchange_compress_on(bp4_ctx *c, double *v, cudaStream_t st);
+
+// MatrixFree::cell_loop (poisson_operator.h:310, :339) on one rank: update_ghost_values(src),
+// cells, compress(add)(dst).  With a partitioned mesh the two exchanges run on a second stream
+// while the cells that touch no ghost DoF are processed:
+//   pack | interior part 1 || send/recv ghosts | ghost-touching cells | interior part 2 ||
+//   send/recv contributions | unpack-add.
+// dst must already be zero where the cells accumulate (owned and ghost slots).
+static int cell_loop(bp4_ctx *c, double *dst, const double *src)
+{
+  if (c->peer.empty())
+    return cell_range(c, dst, src, 0, c->n_cells);
+  if (!c->comm)
+    return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
+  const uint64_t ne      = c->export_off.back();
+  const bool     overlap = c->overlap && c->n_comm > 0;
+  const uint64_t n1 = overlap ? c->n_before : 0, n2 = overlap ? c->n_before + c->n_comm : c->n_cells;
+  {
+    Timed t(c, BP4_K_BLAS1);
+    CU(bp4::launch_pack(ne, c->d_export, src, c->d_sendbuf, c->stream));
+  }
+  CU(cudaEventRecord(c->ev_a, c->stream));
+  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+  if (int e = exchange_ghosts_on(c, const_cast<double *>(src), c->comm_stream))
+    return e;
+  CU(cudaEventRecord(c->ev_b, c->comm_stream));
+  if (int e = cell_range(c, dst, src, 0, n1))
+    return e;
+  CU(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+  if (int e = cell_range(c, dst, src, n1, n2))
+    return e;
+  CU(cudaEventRecord(c->ev_a, c->stream));
+  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+  if (int e = exchange_compress_on(c, dst, c->comm_stream))
+    return e;
+  CU(cudaEventRecord(c->ev_b, c->comm_stream));
+  if (int e = cell_range(c, dst, src, n2, c->n_cells))
+    return e;
+  CU(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+  {
+    Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
+    for (size_t k = 0; k < c->peer.size(); ++k) // per peer: an owned entry may be exported to several
+      CU(bp4::launch_unpack_add(c->export_off[k + 1] - c->export_off[k], c->d_export + c->export_off[k],
+                                c->d_recvbuf + c->export_off[k], dst, c->stream));
+  }
+  CU(cudaMemsetAsync(dst + c->n_owned, 0, sizeof(double) * c->n_ghost, c->stream));
   return 0;
 }
 
@@ -469,16 +535,9 @@ int bp4_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src)
     return e;
   if (dst == src)
     return fail(BP4_ERR_ARG, "vmult: dst aliases src");
-  // update_ghost_values / compress(add) around the cell loop (MatrixFree::cell_loop,
-  // poisson_operator.h:310); no-ops on a single rank
-  if (!c->peer.empty())
-    if (int e = bp4_update_ghost_values(c, const_cast<bp4_vec *>(src)))
-      return e;
-  if (int e = cell_loop(c, dst->p(), src->p(), true))
+  CU(cudaMemsetAsync(dst->p(), 0, sizeof(double) * (c->n_owned + c->n_ghost), c->stream));
+  if (int e = cell_loop(c, dst->p(), src->p()))
     return e;
-  if (!c->peer.empty())
-    if (int e = bp4_compress_add(c, dst))
-      return e;
   {
     Timed t(c, BP4_K_BLAS1);
     CU(bp4::launch_fixup(c->n_constrained, c->d_constrained, dst->p(), src->p(), c->stream));
@@ -569,17 +628,10 @@ int bp4_vmult_merged(bp4_ctx *c, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h,
     CU(bp4::launch_pre(n, h->p(), x->p(), g->p(), d->p(), prec->p(), alpha, beta, alpha_old, beta_old,
                        c->sms, c->stream));
   }
-  if (!c->peer.empty())
-    {
-      if (int e = bp4_update_ghost_values(c, d))
-        return e;
-      CU(cudaMemsetAsync(h->p() + n, 0, sizeof(double) * c->n_ghost, c->stream));
-    }
-  if (int e = cell_loop(c, h->p(), d->p(), false))
+  if (c->n_ghost)
+    CU(cudaMemsetAsync(h->p() + n, 0, sizeof(double) * c->n_ghost, c->stream));
+  if (int e = cell_loop(c, h->p(), d->p()))
     return e;
-  if (!c->peer.empty())
-    if (int e = bp4_compress_add(c, h))
-      return e;
   CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 7, c->stream));
   {
     Timed t(c, BP4_K_POST);
@@ -734,9 +786,40 @@ int bp4_comm_init(bp4_ctx *c, int rank, int n_ranks, const unsigned char id[BP4_
   return 0;
 }
 
-// owners -> ghost copies (LA::distributed::Vector::update_ghost_values): pack the exported owned
-// entries, one ncclSend/ncclRecv pair per peer inside a group, receive straight into the
-// (contiguous, per-owner) ghost blocks
+// NCCL part of update_ghost_values: the packed exports go out, ghosts come straight into the
+// (contiguous, per-owner) ghost blocks of v
+static int exchange_ghosts_on(bp4_ctx *c, double *v, cudaStream_t st)
+{
+  NC(ncclGroupStart());
+  for (size_t k = 0; k < c->peer.size(); ++k)
+    {
+      const uint64_t ns = c->export_off[k + 1] - c->export_off[k], nr = c->import_off[k + 1] - c->import_off[k];
+      if (ns)
+        NC(ncclSend(c->d_sendbuf + c->export_off[k], ns, ncclDouble, c->peer[k], c->comm, st));
+      if (nr)
+        NC(ncclRecv(v + c->n_owned + c->import_off[k], nr, ncclDouble, c->peer[k], c->comm, st));
+    }
+  NC(ncclGroupEnd());
+  return 0;
+}
+
+// NCCL part of compress(add): ghost contributions go to their owners' receive buffer
+static int exchange_compress_on(bp4_ctx *c, double *v, cudaStream_t st)
+{
+  NC(ncclGroupStart());
+  for (size_t k = 0; k < c->peer.size(); ++k)
+    {
+      const uint64_t nr = c->export_off[k + 1] - c->export_off[k], ns = c->import_off[k + 1] - c->import_off[k];
+      if (ns)
+        NC(ncclSend(v + c->n_owned + c->import_off[k], ns, ncclDouble, c->peer[k], c->comm, st));
+      if (nr)
+        NC(ncclRecv(c->d_recvbuf + c->export_off[k], nr, ncclDouble, c->peer[k], c->comm, st));
+    }
+  NC(ncclGroupEnd());
+  return 0;
+}
+
+// owners -> ghost copies (LA::distributed::Vector::update_ghost_values)
 int bp4_update_ghost_values(bp4_ctx *c, bp4_vec *v)
 {
   if (!c || !v)
@@ -745,22 +828,11 @@ int bp4_update_ghost_values(bp4_ctx *c, bp4_vec *v)
     return 0;
   if (!c->comm)
     return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
-  const uint64_t ne = c->export_off.back();
   {
     Timed t(c, BP4_K_BLAS1);
-    CU(bp4::launch_pack(ne, c->d_export, v->p(), c->d_sendbuf, c->stream));
+    CU(bp4::launch_pack(c->export_off.back(), c->d_export, v->p(), c->d_sendbuf, c->stream));
   }
-  NC(ncclGroupStart());
-  for (size_t k = 0; k < c->peer.size(); ++k)
-    {
-      const uint64_t ns = c->export_off[k + 1] - c->export_off[k], nr = c->import_off[k + 1] - c->import_off[k];
-      if (ns)
-        NC(ncclSend(c->d_sendbuf + c->export_off[k], ns, ncclDouble, c->peer[k], c->comm, c->stream));
-      if (nr)
-        NC(ncclRecv(v->p() + c->n_owned + c->import_off[k], nr, ncclDouble, c->peer[k], c->comm, c->stream));
-    }
-  NC(ncclGroupEnd());
-  return 0;
+  return exchange_ghosts_on(c, v->p(), c->stream);
 }
 
 // ghost contributions -> owners, added (compress(VectorOperation::add)); ghost slots are zeroed
@@ -772,16 +844,8 @@ int bp4_compress_add(bp4_ctx *c, bp4_vec *v)
     return 0;
   if (!c->comm)
     return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
-  NC(ncclGroupStart());
-  for (size_t k = 0; k < c->peer.size(); ++k)
-    {
-      const uint64_t nr = c->export_off[k + 1] - c->export_off[k], ns = c->import_off[k + 1] - c->import_off[k];
-      if (ns)
-        NC(ncclSend(v->p() + c->n_owned + c->import_off[k], ns, ncclDouble, c->peer[k], c->comm, c->stream));
-      if (nr)
-        NC(ncclRecv(c->d_recvbuf + c->export_off[k], nr, ncclDouble, c->peer[k], c->comm, c->stream));
-    }
-  NC(ncclGroupEnd());
+  if (int e = exchange_compress_on(c, v->p(), c->stream))
+    return e;
   {
     Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
     for (size_t k = 0; k < c->peer.size(); ++k) // per peer: an owned entry may be exported to several

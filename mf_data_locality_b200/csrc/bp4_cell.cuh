@@ -290,6 +290,93 @@ namespace bp4
   }
 
   // ---------------------------------------------------------------------------------------
+  // split phases 1 and 3 for the high degrees: two items per row (c, j), item g owns the qx
+  // columns [g*QH, min(Q, (g+1)*QH)).  d/dxi is taken directly from the nodal values with Dn
+  // (no exchange between the two halves), which costs ~18 % more FMAs in these phases but doubles
+  // their parallelism and halves their register footprint (t[N][Q] no longer fits at Q6+).
+  //   phase1_split : in[N*N] (registers, read before any thread overwrites the row) -> row
+  //   phase3_split : row -> acc[N*N] partial result over the item's qx columns (registers);
+  //                  the caller stores item g's partial at row[g*N*N + kk] after a barrier and
+  //                  the scatter adds the two partials
+  // ---------------------------------------------------------------------------------------
+  template <int P, int GH>
+  BP4_HD void phase1_split(const Tab<P> &tb, const double (&in)[(P + 1) * (P + 1)], double *out)
+  {
+    using G          = Geom<P>;
+    constexpr int N  = G::N, Q = G::Q;
+    constexpr int QH = (Q + 1) / 2, q0 = GH * QH, q1 = (GH + 1) * QH < Q ? (GH + 1) * QH : Q;
+    BP4_UNROLL
+    for (int qx = q0; qx < q1; ++qx)
+      {
+        double t[N], t2[N];
+        BP4_UNROLL
+        for (int k = 0; k < N; ++k)
+          {
+            double s = tb.S[0][qx] * in[k * N], s2 = tb.Dn[0][qx] * in[k * N];
+            BP4_UNROLL
+            for (int i = 1; i < N; ++i)
+              {
+                s += tb.S[i][qx] * in[k * N + i];
+                s2 += tb.Dn[i][qx] * in[k * N + i];
+              }
+            t[k]  = s;
+            t2[k] = s2;
+          }
+        BP4_UNROLL
+        for (int qz = 0; qz < Q; ++qz)
+          {
+            double u = tb.S[0][qz] * t[0], wz = tb.Dn[0][qz] * t[0], wx = tb.S[0][qz] * t2[0];
+            BP4_UNROLL
+            for (int k = 1; k < N; ++k)
+              {
+                u += tb.S[k][qz] * t[k];
+                wz += tb.Dn[k][qz] * t[k];
+                wx += tb.S[k][qz] * t2[k];
+              }
+            out[0 * Q * Q + qz * Q + qx] = u;
+            out[1 * Q * Q + qz * Q + qx] = wx;
+            out[2 * Q * Q + qz * Q + qx] = wz;
+          }
+      }
+  }
+
+  template <int P, int GH>
+  BP4_HD void phase3_split(const Tab<P> &tb, const double *in, double (&acc)[(P + 1) * (P + 1)])
+  {
+    using G          = Geom<P>;
+    constexpr int N  = G::N, Q = G::Q;
+    constexpr int QH = (Q + 1) / 2, q0 = GH * QH, q1 = (GH + 1) * QH < Q ? (GH + 1) * QH : Q;
+    BP4_UNROLL
+    for (int kk = 0; kk < N * N; ++kk)
+      acc[kk] = 0.;
+    BP4_UNROLL
+    for (int qx = q0; qx < q1; ++qx)
+      {
+        double av[N], bv[N];
+        BP4_UNROLL
+        for (int k = 0; k < N; ++k)
+          av[k] = bv[k] = 0.;
+        BP4_UNROLL
+        for (int qz = 0; qz < Q; ++qz)
+          {
+            const double v = in[0 * Q * Q + qz * Q + qx], fx = in[1 * Q * Q + qz * Q + qx],
+                         fz = in[2 * Q * Q + qz * Q + qx];
+            BP4_UNROLL
+            for (int k = 0; k < N; ++k)
+              {
+                av[k] += tb.S[k][qz] * v + tb.Dn[k][qz] * fz;
+                bv[k] += tb.S[k][qz] * fx;
+              }
+          }
+        BP4_UNROLL
+        for (int k = 0; k < N; ++k)
+          BP4_UNROLL
+        for (int i = 0; i < N; ++i)
+          acc[k * N + i] += tb.S[i][qx] * av[k] + tb.Dn[i][qx] * bv[k];
+      }
+  }
+
+  // ---------------------------------------------------------------------------------------
   // phase 2: item = (qx, qz), all three components, one y-line of quadrature points.
   // cf = tri-linear coefficients [8][3] in the order v0,v1,v3,v4,v9,v10,v12,v13
   // (poisson_operator.h:165-177); x = xq[qx], z = xq[qz], wxz = wq[qx]*wq[qz].

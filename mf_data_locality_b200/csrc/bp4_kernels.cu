@@ -78,7 +78,10 @@ namespace bp4
   __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_plain(const CellArgs a)
   {
     using G         = Geom<P>;
-    constexpr int Q = G::Q;
+    constexpr int Q = G::Q, NN = G::N * G::N;
+    // optional: two items per row in phases 1 and 3 (see phase1_split)
+    constexpr bool kSplit = false; // measured slower (spills in the split phase 3), kept for reference
+    static_assert(!kSplit || 2 * CPB * G::ITEMS13 <= kThreads, "split phases need a single round");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
     const int         tid = threadIdx.x;
@@ -178,8 +181,33 @@ namespace bp4
         // phase 1/3 items are handed out from the LAST thread downwards: the ragged final round
         // of phase 2 lands on the first warps, so the two kinds of partial rounds end up on
         // different warps (= different SM sub-partitions) instead of piling up on warp 0
-        for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
-          phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+        if (!kSplit)
+          {
+            for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
+              phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+          }
+        else
+          {
+            // two items per row: read the row into registers, barrier, then overwrite it
+            const int  n13 = nc * G::ITEMS13, it = kThreads - 1 - tid;
+            const bool on  = it < 2 * n13;
+            const int  row = on ? it % n13 : 0;
+            double     in[NN];
+            if (on)
+              {
+#pragma unroll
+                for (int kk = 0; kk < NN; ++kk)
+                  in[kk] = sm.work[row * G::RW + kk];
+              }
+            __syncthreads();
+            if (on)
+              {
+                if (it < n13)
+                  phase1_split<P, 0>(tb, in, sm.work + row * G::RW);
+                else
+                  phase1_split<P, 1>(tb, in, sm.work + row * G::RW);
+              }
+          }
         BP4_TICK(3)
         __syncthreads();
         BP4_TICK(2)
@@ -193,8 +221,35 @@ namespace bp4
         BP4_TICK(4)
         __syncthreads();
         BP4_TICK(2)
-        for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
-          phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+        if (!kSplit)
+          {
+            for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
+              phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+          }
+        else
+          {
+            // partial results of the two qx halves go to row[0..NN) and row[NN..2NN); the
+            // scatter adds them
+            const int  n13 = nc * G::ITEMS13, it = kThreads - 1 - tid;
+            const bool on  = it < 2 * n13;
+            const int  row = on ? it % n13 : 0;
+            double     acc[NN];
+            if (on)
+              {
+                if (it < n13)
+                  phase3_split<P, 0>(tb, sm.work + row * G::RW, acc);
+                else
+                  phase3_split<P, 1>(tb, sm.work + row * G::RW, acc);
+              }
+            __syncthreads();
+            if (on)
+              {
+                double *o = sm.work + row * G::RW + (it < n13 ? 0 : NN);
+#pragma unroll
+                for (int kk = 0; kk < NN; ++kk)
+                  o[kk] = acc[kk];
+              }
+          }
         if (i + 1 < my_n)
           park_meta(bf ^ 1);
         BP4_TICK(5)
@@ -226,6 +281,8 @@ namespace bp4
                         adr[u]   = base + dtab_rel(t);
                         inner[u] = ent == 13u;
                         v[u]     = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
+                        if (kSplit)
+                          v[u] += sm.work[cell * G::WORK + dtab_off_work<P>(t) + NN];
                       }
                   }
               }

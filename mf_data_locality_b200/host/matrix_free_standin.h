@@ -79,6 +79,8 @@ namespace dealii
           add_partition(inner.data(), inner.data() + n_before);
           add_partition(comm.data(), comm.data() + comm.size());
           add_partition(inner.data() + n_before, inner.data() + inner.size());
+          n_cells_before_comm = n_before;
+          n_cells_comm        = comm.size();
         }
       else
         add_partition(inner.data(), inner.data() + inner.size());
@@ -205,6 +207,7 @@ namespace dealii
     std::vector<std::uint64_t> cell_order;  // active-cell index per physical cell, loop order
     std::vector<unsigned int>  batch_start; // first physical cell of every batch (+ sentinel)
     unsigned int               n_q_points_1d = 0;
+    std::uint64_t              n_cells_before_comm = 0, n_cells_comm = 0; // physical cells per partition
 
   private:
     const DoFHandler         *dof_handler = nullptr;

@@ -94,6 +94,8 @@ namespace Poisson
       desc.import_offset = part.import_offset.data();
       desc.export_offset = part.export_offset.data();
       desc.export_index  = part.export_index.data();
+      desc.n_cells_before_comm = data->n_cells_before_comm;
+      desc.n_cells_comm        = data->n_cells_comm;
       if (ctx)
         bp4_ctx_destroy(ctx);
       ctx = nullptr;

@@ -4,6 +4,7 @@
 // the oracle without a GPU.  Never linked into the product library.
 #include <cstdint>
 #include <cstring>
+#include <array>
 #include <vector>
 
 #include "../../mf_data_locality_b200/csrc/bp4_tables.h"
@@ -55,6 +56,98 @@ static void run(long n_cells, const uint32_t *eidx, const double *verts, const d
             dst[(size_t)base + bp4::dtab_rel(t)] += dofs[bp4::dtab_off<P>(t)];
         }
     }
+}
+
+// same, with phases 1 and 3 split in two qx halves per row (the high-degree path of the kernel)
+template <int P>
+static void run_split(long n_cells, const uint32_t *eidx, const double *verts, const double *src, double *dst)
+{
+  using G = bp4::Geom<P>;
+  constexpr int NN = G::N * G::N;
+  bp4::Tab<P> tb;
+  bp4::fill_tab<P>(tb);
+  std::vector<uint32_t> dtab(G::DOF);
+  bp4::build_dof_table<P>(dtab.data());
+  std::vector<double> work(G::WORK);
+  for (long cell = 0; cell < n_cells; ++cell)
+    {
+      const uint32_t *e = eidx + 27 * cell;
+      const double   *v = verts + 24 * cell;
+      double          cf[24];
+      for (int k = 0; k < 3; ++k)
+        {
+          cf[0 + k]  = v[0 + k];
+          cf[3 + k]  = v[3 + k] - v[0 + k];
+          cf[6 + k]  = v[6 + k] - v[0 + k];
+          cf[9 + k]  = v[9 + k] - v[6 + k] - (v[3 + k] - v[0 + k]);
+          cf[12 + k] = v[12 + k] - v[0 + k];
+          cf[15 + k] = v[15 + k] - v[12 + k] - (v[3 + k] - v[0 + k]);
+          cf[18 + k] = v[18 + k] - v[12 + k] - (v[6 + k] - v[0 + k]);
+          cf[21 + k] = (v[21 + k] - v[18 + k] - (v[15 + k] - v[12 + k]) -
+                        (v[9 + k] - v[6 + k] - (v[3 + k] - v[0 + k])));
+        }
+      for (int m = 0; m < G::DOF; ++m)
+        {
+          const uint32_t t = dtab[m], base = e[bp4::dtab_ent(t)];
+          work[bp4::dtab_off_work<P>(t)] = base != 0xFFFFFFFFu ? src[(size_t)base + bp4::dtab_rel(t)] : 0.;
+        }
+      // phase 1: every item reads its row before any item writes (barrier in the kernel)
+      std::vector<std::array<double, NN>> regs(2 * G::ROWS);
+      for (int it = 0; it < 2 * G::ROWS; ++it)
+        for (int kk = 0; kk < NN; ++kk)
+          regs[it][kk] = work[(it % G::ROWS) * G::RW + kk];
+      for (int it = 0; it < 2 * G::ROWS; ++it)
+        {
+          double in[NN];
+          for (int kk = 0; kk < NN; ++kk)
+            in[kk] = regs[it][kk];
+          if (it < G::ROWS)
+            bp4::phase1_split<P, 0>(tb, in, work.data() + (it % G::ROWS) * G::RW);
+          else
+            bp4::phase1_split<P, 1>(tb, in, work.data() + (it % G::ROWS) * G::RW);
+        }
+      for (int it = 0; it < G::ITEMS2; ++it)
+        {
+          const int qz = it / G::Q, qx = it % G::Q;
+          bp4::phase2<P>(tb, cf, work.data(), qx, qz, tb.xq[qx], tb.xq[qz], tb.wq[qx] * tb.wq[qz]);
+        }
+      for (int it = 0; it < 2 * G::ROWS; ++it)
+        {
+          double acc[NN];
+          if (it < G::ROWS)
+            bp4::phase3_split<P, 0>(tb, work.data() + (it % G::ROWS) * G::RW, acc);
+          else
+            bp4::phase3_split<P, 1>(tb, work.data() + (it % G::ROWS) * G::RW, acc);
+          for (int kk = 0; kk < NN; ++kk)
+            regs[it][kk] = acc[kk];
+        }
+      for (int it = 0; it < 2 * G::ROWS; ++it) // after the barrier: park the partials in the row
+        for (int kk = 0; kk < NN; ++kk)
+          work[(it % G::ROWS) * G::RW + (it / G::ROWS) * NN + kk] = regs[it][kk];
+      for (int m = 0; m < G::DOF; ++m)
+        {
+          const uint32_t t = dtab[m], base = e[bp4::dtab_ent(t)];
+          if (base != 0xFFFFFFFFu)
+            dst[(size_t)base + bp4::dtab_rel(t)] +=
+              work[bp4::dtab_off_work<P>(t)] + work[bp4::dtab_off_work<P>(t) + NN];
+        }
+    }
+}
+
+extern "C" int emu_vmult_cells_split(int p, long n_cells, const uint32_t *eidx, const double *verts,
+                                     const double *src, double *dst)
+{
+  switch (p)
+    {
+      case 2: run_split<2>(n_cells, eidx, verts, src, dst); return 0;
+      case 3: run_split<3>(n_cells, eidx, verts, src, dst); return 0;
+      case 4: run_split<4>(n_cells, eidx, verts, src, dst); return 0;
+      case 5: run_split<5>(n_cells, eidx, verts, src, dst); return 0;
+      case 6: run_split<6>(n_cells, eidx, verts, src, dst); return 0;
+      case 7: run_split<7>(n_cells, eidx, verts, src, dst); return 0;
+      case 8: run_split<8>(n_cells, eidx, verts, src, dst); return 0;
+    }
+  return -1;
 }
 
 extern "C" int emu_vmult_cells(int p, long n_cells, const uint32_t *eidx, const double *verts,
