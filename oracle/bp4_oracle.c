@@ -25,7 +25,15 @@ typedef struct
   const double *wq;  /* [Q] */
   const int    *ent; /* [N^3] entity of every cell node (lexicographic) */
   const int    *pos; /* [N^3] lexicographic position inside its entity */
+  /* optional colouring: cells of one colour share no DoF, so they can be scattered without
+   * atomics (plays the role of the rank-private data of the reference's MPI run) */
+  int         n_colors;
+  const long *color_start; /* [n_colors + 1] */
+  const long *color_cells; /* cell indices grouped by colour */
 } oracle_tables;
+
+#define VL 8
+typedef double vd __attribute__((vector_size(8 * VL)));
 
 #define P 2
 #include "bp4_oracle_kernel.inc"
@@ -49,8 +57,8 @@ typedef struct
 #include "bp4_oracle_kernel.inc"
 #undef P
 
-typedef void (*cell_fn)(const oracle_tables *, const uint32_t *, const double *, const double *,
-                        double *);
+typedef void (*cell_fn)(const oracle_tables *, const long *, int, const uint32_t *, const double *,
+                        const double *, double *, int);
 static cell_fn pick(int p)
 {
   switch (p)
@@ -85,9 +93,25 @@ int oracle_vmult_cells(const oracle_tables *t, long n_cells, long n_local, const
 #pragma omp parallel for schedule(static)
   for (long i = 0; i < n_local; ++i)
     dst[i] = 0.;
-#pragma omp parallel for schedule(dynamic, 16)
-  for (long c = 0; c < n_cells; ++c)
-    f(t, eidx + 27 * c, coef + 24 * c, src, dst);
+  if (t->n_colors > 0)
+    {
+      for (int col = 0; col < t->n_colors; ++col)
+        {
+          const long k0 = t->color_start[col], k1 = t->color_start[col + 1];
+#pragma omp parallel for schedule(static)
+          for (long k = k0; k < k1; k += VL)
+            f(t, t->color_cells + k, (int)(k1 - k < VL ? k1 - k : VL), eidx, coef, src, dst, 0);
+        }
+      return 0;
+    }
+#pragma omp parallel for schedule(dynamic, 4)
+  for (long c = 0; c < n_cells; c += VL)
+    {
+      long cells[VL];
+      for (int v = 0; v < VL; ++v)
+        cells[v] = c + v < n_cells ? c + v : c;
+      f(t, cells, (int)(n_cells - c < VL ? n_cells - c : VL), eidx, coef, src, dst, 1);
+    }
   return 0;
 }
 

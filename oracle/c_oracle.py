@@ -16,7 +16,8 @@ _LIB = None
 
 class _Tables(C.Structure):
     _fields_ = [("degree", C.c_int), ("S", C.c_void_p), ("D", C.c_void_p), ("xq", C.c_void_p),
-                ("wq", C.c_void_p), ("ent", C.c_void_p), ("pos", C.c_void_p)]
+                ("wq", C.c_void_p), ("ent", C.c_void_p), ("pos", C.c_void_p),
+                ("n_colors", C.c_int), ("color_start", C.c_void_p), ("color_cells", C.c_void_p)]
 
 
 def build():
@@ -66,7 +67,12 @@ class COracle:
                     pos[l] = off(i) + size(ex) * (off(j) + size(ey) * off(k))
                     l += 1
         self._keep = [np.ascontiguousarray(a) for a in (t.S, t.D, t.xq, t.wq, ent, pos)]
-        self.tab = _Tables(p, *[_p(a) for a in self._keep])
+        # 8-colouring of the structured mesh by lattice parity: cells of one colour share no DoF
+        col = (rd.cells[:, 0] % 2) + 2 * (rd.cells[:, 1] % 2) + 4 * (rd.cells[:, 2] % 2)
+        order = np.argsort(col, kind="stable").astype(np.int64)
+        start = np.concatenate(([0], np.cumsum(np.bincount(col, minlength=8)))).astype(np.int64)
+        self._keep += [np.ascontiguousarray(start), np.ascontiguousarray(order)]
+        self.tab = _Tables(p, *[_p(a) for a in self._keep[:6]], 8, _p(self._keep[6]), _p(self._keep[7]))
         self.eidx = np.ascontiguousarray(rd.entity_index, dtype=np.uint32)
         self.coef = np.ascontiguousarray(O.trilinear_coefficients(rd.vertices))
         self.con = np.ascontiguousarray(rd.constrained, dtype=np.uint32)
