@@ -149,3 +149,46 @@ def test_cg_plain_parity(p, s, bp4_lib, c_oracle_lib):
     assert abs(ctl.last_step - ito) <= 1
     assert rel_l2(x, xo) <= (1e-8 if ito < 100 else 1e-6)
     ctx.close()
+
+
+def test_error_behaviour(bp4_lib):
+    """argument errors are reported through negative codes + bp4_last_error, with the
+    reference's wording where it has one (diagonal_matrix_blocked.h:17-20)"""
+    from mf_data_locality_b200 import capi
+    rd, _ = single(3, 5)
+    ctx = make_ctx(rd)
+    short, full = ctx.vector(10), ctx.vector()
+    with pytest.raises(capi.Bp4Error, match="n_owned"):
+        ctx.vmult(full, short)
+    with pytest.raises(capi.Bp4Error, match="aliases"):
+        ctx.vmult(full, full)
+    with pytest.raises(capi.Bp4Error, match="Dimension mismatch"):
+        ctx.jacobi_vmult(full, full, ctx.vector(3))
+    with pytest.raises(capi.Bp4Error, match="degree"):
+        capi.Context(9, rd.entity_index, rd.vertices, rd.n_owned)
+    with pytest.raises(capi.Bp4Error, match="multiples of 3"):
+        capi.Context(3, rd.entity_index, rd.vertices, rd.n_owned + 1)
+    ctx.close()
+
+
+def test_empty_and_ragged_inputs(bp4_lib, c_oracle_lib):
+    """a context without cells applies the identity on constrained rows and zero elsewhere; a cell
+    count that is not a multiple of the block's batch size is handled (ragged last batch)"""
+    from mf_data_locality_b200 import capi
+    ctx = capi.Context(4, np.zeros((0, 27), np.uint32), np.zeros((0, 8, 3)), 30, 0, np.arange(6, dtype=np.uint32))
+    v = np.arange(30, dtype=np.float64) + 1
+    src, dst = ctx.vector(data=v), ctx.vector()
+    ctx.vmult(dst, src)
+    got = dst.download()
+    assert np.array_equal(got[:6], v[:6]) and not got[6:].any()
+    ctx.close()
+    for p, s in [(4, 3), (3, 4), (5, 3)]:          # 8, 16, 8 cells: never a multiple of 7 / 10 / 5
+        rd, co = single(p, s)
+        ctx = make_ctx(rd)
+        for variant in (0, 3, 6, 9, 12):
+            ctx.set_merged_variant(variant)
+            w = np.random.default_rng(variant).standard_normal(rd.n_owned)
+            a, b = ctx.vector(data=w), ctx.vector()
+            ctx.vmult(b, a)
+            assert rel_l2(b.download(), co.vmult(w)) <= 1e-12
+        ctx.close()
