@@ -52,6 +52,24 @@ inline SolverSettings &solver_settings()
   return s;
 }
 
+// shared body of the two plugins: build the solver on the benchmark's stopping rule, solve, and
+// report the iteration count -- hitting the iteration cap is a normal outcome here, not an error
+// (the reference swallows NoConvergence the same way, bench.cc:19-24)
+template <typename SolverType, typename Operator, typename VectorType, typename Preconditioner>
+unsigned int solve_and_count(const Operator &A, VectorType &x, const VectorType &b, const Preconditioner &P)
+{
+  const SolverSettings &st = solver_settings();
+  ReductionControl      control(st.max_steps, st.abs_tol, st.rel_tol);
+  SolverType            solver(control);
+  try
+    {
+      solver.solve(A, x, b, P);
+    }
+  catch (const SolverControl::NoConvergence &)
+    {}
+  return control.last_step();
+}
+
 struct BenchmarkOptions
 {
   unsigned int n_ranks = 1, rank = 0; // partition held by this process
