@@ -290,89 +290,138 @@ namespace bp4
   }
 
   // ---------------------------------------------------------------------------------------
-  // split phases 1 and 3 for the high degrees: two items per row (c, j), item g owns the qx
-  // columns [g*QH, min(Q, (g+1)*QH)).  d/dxi is taken directly from the nodal values with Dn
-  // (no exchange between the two halves), which costs ~18 % more FMAs in these phases but doubles
-  // their parallelism and halves their register footprint (t[N][Q] no longer fits at Q6+).
-  //   phase1_split : in[N*N] (registers, read before any thread overwrites the row) -> row
-  //   phase3_split : row -> acc[N*N] partial result over the item's qx columns (registers);
-  //                  the caller stores item g's partial at row[g*N*N + kk] after a barrier and
-  //                  the scatter adds the two partials
+  // fine-grained phases 1 and 3 for the high degrees.  With few cells per block the 3N rows
+  // (c, j) of a cell are too few items for 128 threads (Q8: 27), and one row's t[N][Q] no longer
+  // fits the register file.  Here every 1-D contraction is its own sweep with a block barrier
+  // in between, one line per item, in place in the row:
+  //   1a (row, k ): dofs[k][:]            -> t[k][:]      kept in the d/dzeta slots
+  //   1b (row, qx): t[:][qx]              -> u[:][qx], d/dzeta[:][qx]   (own column, in place)
+  //   1c (row, qz): u[qz][:]              -> d/dxi[qz][:]
+  //   3a (row, qz): v[qz][:], fx[qz][:]   -> v[qz][:] += D fx
+  //   3b (row, qx): v[:][qx], fz[:][qx]   -> t[:][qx]     (own column of the d/dzeta slots)
+  //   3c (row, k ): t[k][:]               -> result[k][:]
+  // Same FMAs as phase1/phase3, (N + Q) registers of data per item, Q or N independent chains.
+  // The matrix entries stay compile-time constant-bank operands: the line index only selects data.
   // ---------------------------------------------------------------------------------------
-  template <int P, int GH>
-  BP4_HD void phase1_split(const Tab<P> &tb, const double (&in)[(P + 1) * (P + 1)], double *out)
+  template <int P>
+  BP4_HD void phase1a(const Tab<P> &tb, double *row, const int k)
   {
-    using G          = Geom<P>;
-    constexpr int N  = G::N, Q = G::Q;
-    constexpr int QH = (Q + 1) / 2, q0 = GH * QH, q1 = (GH + 1) * QH < Q ? (GH + 1) * QH : Q;
+    constexpr int N = Geom<P>::N, Q = Geom<P>::Q;
+    double        r[N];
     BP4_UNROLL
-    for (int qx = q0; qx < q1; ++qx)
+    for (int i = 0; i < N; ++i)
+      r[i] = row[k * N + i];
+    BP4_UNROLL
+    for (int q = 0; q < Q; ++q)
       {
-        double t[N], t2[N];
+        double s = tb.S[0][q] * r[0];
         BP4_UNROLL
-        for (int k = 0; k < N; ++k)
-          {
-            double s = tb.S[0][qx] * in[k * N], s2 = tb.Dn[0][qx] * in[k * N];
-            BP4_UNROLL
-            for (int i = 1; i < N; ++i)
-              {
-                s += tb.S[i][qx] * in[k * N + i];
-                s2 += tb.Dn[i][qx] * in[k * N + i];
-              }
-            t[k]  = s;
-            t2[k] = s2;
-          }
-        BP4_UNROLL
-        for (int qz = 0; qz < Q; ++qz)
-          {
-            double u = tb.S[0][qz] * t[0], wz = tb.Dn[0][qz] * t[0], wx = tb.S[0][qz] * t2[0];
-            BP4_UNROLL
-            for (int k = 1; k < N; ++k)
-              {
-                u += tb.S[k][qz] * t[k];
-                wz += tb.Dn[k][qz] * t[k];
-                wx += tb.S[k][qz] * t2[k];
-              }
-            out[0 * Q * Q + qz * Q + qx] = u;
-            out[1 * Q * Q + qz * Q + qx] = wx;
-            out[2 * Q * Q + qz * Q + qx] = wz;
-          }
+        for (int i = 1; i < N; ++i)
+          s += tb.S[i][q] * r[i];
+        row[2 * Q * Q + k * Q + q] = s;
       }
   }
 
-  template <int P, int GH>
-  BP4_HD void phase3_split(const Tab<P> &tb, const double *in, double (&acc)[(P + 1) * (P + 1)])
+  template <int P>
+  BP4_HD void phase1b(const Tab<P> &tb, double *row, const int qx)
   {
-    using G          = Geom<P>;
-    constexpr int N  = G::N, Q = G::Q;
-    constexpr int QH = (Q + 1) / 2, q0 = GH * QH, q1 = (GH + 1) * QH < Q ? (GH + 1) * QH : Q;
+    constexpr int N = Geom<P>::N, Q = Geom<P>::Q;
+    double        t[N];
     BP4_UNROLL
-    for (int kk = 0; kk < N * N; ++kk)
-      acc[kk] = 0.;
+    for (int k = 0; k < N; ++k)
+      t[k] = row[2 * Q * Q + k * Q + qx];
     BP4_UNROLL
-    for (int qx = q0; qx < q1; ++qx)
+    for (int qz = 0; qz < Q; ++qz)
       {
-        double av[N], bv[N];
+        double su = tb.S[0][qz] * t[0];
+        double sz = tb.Dn[0][qz] * t[0];
         BP4_UNROLL
-        for (int k = 0; k < N; ++k)
-          av[k] = bv[k] = 0.;
-        BP4_UNROLL
-        for (int qz = 0; qz < Q; ++qz)
+        for (int k = 1; k < N; ++k)
           {
-            const double v = in[0 * Q * Q + qz * Q + qx], fx = in[1 * Q * Q + qz * Q + qx],
-                         fz = in[2 * Q * Q + qz * Q + qx];
-            BP4_UNROLL
-            for (int k = 0; k < N; ++k)
-              {
-                av[k] += tb.S[k][qz] * v + tb.Dn[k][qz] * fz;
-                bv[k] += tb.S[k][qz] * fx;
-              }
+            su += tb.S[k][qz] * t[k];
+            sz += tb.Dn[k][qz] * t[k];
           }
+        row[0 * Q * Q + qz * Q + qx] = su;
+        row[2 * Q * Q + qz * Q + qx] = sz;
+      }
+  }
+
+  template <int P>
+  BP4_HD void phase1c(const Tab<P> &tb, double *row, const int qz)
+  {
+    constexpr int Q = Geom<P>::Q;
+    double        u[Q];
+    BP4_UNROLL
+    for (int i = 0; i < Q; ++i)
+      u[i] = row[qz * Q + i];
+    BP4_UNROLL
+    for (int q = 0; q < Q; ++q)
+      {
+        double sx = tb.D[0][q] * u[0];
         BP4_UNROLL
-        for (int k = 0; k < N; ++k)
-          BP4_UNROLL
-        for (int i = 0; i < N; ++i)
-          acc[k * N + i] += tb.S[i][qx] * av[k] + tb.Dn[i][qx] * bv[k];
+        for (int i = 1; i < Q; ++i)
+          sx += tb.D[i][q] * u[i];
+        row[1 * Q * Q + qz * Q + q] = sx;
+      }
+  }
+
+  template <int P>
+  BP4_HD void phase3a(const Tab<P> &tb, double *row, const int qz)
+  {
+    constexpr int Q = Geom<P>::Q;
+    double        fx[Q];
+    BP4_UNROLL
+    for (int q = 0; q < Q; ++q)
+      fx[q] = row[1 * Q * Q + qz * Q + q];
+    BP4_UNROLL
+    for (int i = 0; i < Q; ++i)
+      {
+        double s = row[qz * Q + i];
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          s += tb.D[i][q] * fx[q];
+        row[qz * Q + i] = s;
+      }
+  }
+
+  template <int P>
+  BP4_HD void phase3b(const Tab<P> &tb, double *row, const int qx)
+  {
+    constexpr int N = Geom<P>::N, Q = Geom<P>::Q;
+    double        v[Q], fz[Q];
+    BP4_UNROLL
+    for (int qz = 0; qz < Q; ++qz)
+      {
+        v[qz]  = row[0 * Q * Q + qz * Q + qx];
+        fz[qz] = row[2 * Q * Q + qz * Q + qx];
+      }
+    BP4_UNROLL
+    for (int k = 0; k < N; ++k)
+      {
+        double s = tb.S[k][0] * v[0] + tb.Dn[k][0] * fz[0];
+        BP4_UNROLL
+        for (int qz = 1; qz < Q; ++qz)
+          s += tb.S[k][qz] * v[qz] + tb.Dn[k][qz] * fz[qz];
+        row[2 * Q * Q + k * Q + qx] = s;
+      }
+  }
+
+  template <int P>
+  BP4_HD void phase3c(const Tab<P> &tb, double *row, const int k)
+  {
+    constexpr int N = Geom<P>::N, Q = Geom<P>::Q;
+    double        t[Q];
+    BP4_UNROLL
+    for (int q = 0; q < Q; ++q)
+      t[q] = row[2 * Q * Q + k * Q + q];
+    BP4_UNROLL
+    for (int i = 0; i < N; ++i)
+      {
+        double s = tb.S[i][0] * t[0];
+        BP4_UNROLL
+        for (int q = 1; q < Q; ++q)
+          s += tb.S[i][q] * t[q];
+        row[k * N + i] = s;
       }
   }
 

@@ -6,6 +6,11 @@
 #include "bp4_launch.h"
 #include "bp4_tables.h"
 
+// degrees >= BP4_FINE_FROM run phases 1 and 3 as fine-grained sweeps (phase1a..c, phase3a..c)
+#ifndef BP4_FINE_FROM
+#  define BP4_FINE_FROM 6
+#endif
+
 namespace bp4
 {
   // one table per degree in the constant bank: with fully unrolled contractions every
@@ -79,9 +84,8 @@ namespace bp4
   {
     using G         = Geom<P>;
     constexpr int Q = G::Q, NN = G::N * G::N;
-    // optional: two items per row in phases 1 and 3 (see phase1_split)
-    constexpr bool kSplit = false; // measured slower (spills in the split phase 3), kept for reference
-    static_assert(!kSplit || 2 * CPB * G::ITEMS13 <= kThreads, "split phases need a single round");
+    // high degrees: phases 1 and 3 as one sweep per 1-D contraction (see phase1a)
+    constexpr bool kFine = P >= BP4_FINE_FROM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
     const int         tid = threadIdx.x;
@@ -150,27 +154,28 @@ namespace bp4
         const int     total = nc * G::DOF;
         for (int m0 = tid; m0 < total; m0 += kThreads * GU)
           {
+            // three straight-line passes (addresses, loads, stores) without branches: the
+            // loads of all GU slots are in flight together
             double   v[GU];
-            uint32_t off[GU];
+            uint32_t off[GU], idx[GU];
 #pragma unroll
             for (int u = 0; u < GU; ++u)
               {
-                const int m = m0 + u * kThreads;
-                v[u]        = 0.;
-                off[u]      = 0;
-                if (m < total)
-                  {
-                    const int      cell = m / G::DOF;
-                    const uint32_t t    = sm.dtab[m - cell * G::DOF];
-                    const uint32_t base = sm.eidx[bf][cell][dtab_ent(t)];
-                    off[u]              = cell * G::WORK + dtab_off_work<P>(t);
-                    if (base != 0xFFFFFFFFu)
-                      v[u] = __ldg(a.src + (size_t)base + dtab_rel(t));
-                  }
+                const int      m    = m0 + u * kThreads;
+                const bool     on   = m < total;
+                const int      mm   = on ? m : 0;
+                const int      cell = mm / G::DOF;
+                const uint32_t t    = sm.dtab[mm - cell * G::DOF];
+                const uint32_t base = sm.eidx[bf][cell][dtab_ent(t)];
+                off[u]              = on ? cell * G::WORK + dtab_off_work<P>(t) : 0xFFFFFFFFu;
+                idx[u]              = on && base != 0xFFFFFFFFu ? base + dtab_rel(t) : 0xFFFFFFFFu;
               }
 #pragma unroll
             for (int u = 0; u < GU; ++u)
-              if (m0 + u * kThreads < total)
+              v[u] = idx[u] != 0xFFFFFFFFu ? __ldg(a.src + idx[u]) : 0.;
+#pragma unroll
+            for (int u = 0; u < GU; ++u)
+              if (off[u] != 0xFFFFFFFFu)
                 sm.work[off[u]] = v[u];
           }
         BP4_TICK(1)
@@ -181,32 +186,24 @@ namespace bp4
         // phase 1/3 items are handed out from the LAST thread downwards: the ragged final round
         // of phase 2 lands on the first warps, so the two kinds of partial rounds end up on
         // different warps (= different SM sub-partitions) instead of piling up on warp 0
-        if (!kSplit)
+        if (!kFine)
           {
             for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
               phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
           }
         else
           {
-            // two items per row: read the row into registers, barrier, then overwrite it
-            const int  n13 = nc * G::ITEMS13, it = kThreads - 1 - tid;
-            const bool on  = it < 2 * n13;
-            const int  row = on ? it % n13 : 0;
-            double     in[NN];
-            if (on)
-              {
-#pragma unroll
-                for (int kk = 0; kk < NN; ++kk)
-                  in[kk] = sm.work[row * G::RW + kk];
-              }
+            // one 1-D line per item, consecutive lanes on consecutive rows (odd row stride:
+            // no bank conflicts); see phase1a
+            const int n_rows = nc * G::ITEMS13;
+            for (int it = tid; it < n_rows * G::N; it += kThreads)
+              phase1a<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
             __syncthreads();
-            if (on)
-              {
-                if (it < n13)
-                  phase1_split<P, 0>(tb, in, sm.work + row * G::RW);
-                else
-                  phase1_split<P, 1>(tb, in, sm.work + row * G::RW);
-              }
+            for (int it = tid; it < n_rows * Q; it += kThreads)
+              phase1b<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
+            __syncthreads();
+            for (int it = tid; it < n_rows * Q; it += kThreads)
+              phase1c<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
           }
         BP4_TICK(3)
         __syncthreads();
@@ -221,34 +218,22 @@ namespace bp4
         BP4_TICK(4)
         __syncthreads();
         BP4_TICK(2)
-        if (!kSplit)
+        if (!kFine)
           {
             for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
               phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
           }
         else
           {
-            // partial results of the two qx halves go to row[0..NN) and row[NN..2NN); the
-            // scatter adds them
-            const int  n13 = nc * G::ITEMS13, it = kThreads - 1 - tid;
-            const bool on  = it < 2 * n13;
-            const int  row = on ? it % n13 : 0;
-            double     acc[NN];
-            if (on)
-              {
-                if (it < n13)
-                  phase3_split<P, 0>(tb, sm.work + row * G::RW, acc);
-                else
-                  phase3_split<P, 1>(tb, sm.work + row * G::RW, acc);
-              }
+            const int n_rows = nc * G::ITEMS13;
+            for (int it = tid; it < n_rows * Q; it += kThreads)
+              phase3a<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
             __syncthreads();
-            if (on)
-              {
-                double *o = sm.work + row * G::RW + (it < n13 ? 0 : NN);
-#pragma unroll
-                for (int kk = 0; kk < NN; ++kk)
-                  o[kk] = acc[kk];
-              }
+            for (int it = tid; it < n_rows * Q; it += kThreads)
+              phase3b<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
+            __syncthreads();
+            for (int it = tid; it < n_rows * G::N; it += kThreads)
+              phase3c<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
           }
         if (i + 1 < my_n)
           park_meta(bf ^ 1);
@@ -281,8 +266,6 @@ namespace bp4
                         adr[u]   = base + dtab_rel(t);
                         inner[u] = ent == 13u;
                         v[u]     = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
-                        if (kSplit)
-                          v[u] += sm.work[cell * G::WORK + dtab_off_work<P>(t) + NN];
                       }
                   }
               }

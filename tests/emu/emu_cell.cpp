@@ -58,12 +58,12 @@ static void run(long n_cells, const uint32_t *eidx, const double *verts, const d
     }
 }
 
-// same, with phases 1 and 3 split in two qx halves per row (the high-degree path of the kernel)
+// same, with phases 1 and 3 as fine-grained sweeps, in place in the work rows (the high-degree
+// path of the kernel); each inner loop is what the threads of a block do between two barriers
 template <int P>
-static void run_split(long n_cells, const uint32_t *eidx, const double *verts, const double *src, double *dst)
+static void run_fine(long n_cells, const uint32_t *eidx, const double *verts, const double *src, double *dst)
 {
   using G = bp4::Geom<P>;
-  constexpr int NN = G::N * G::N;
   bp4::Tab<P> tb;
   bp4::fill_tab<P>(tb);
   std::vector<uint32_t> dtab(G::DOF);
@@ -91,61 +91,45 @@ static void run_split(long n_cells, const uint32_t *eidx, const double *verts, c
           const uint32_t t = dtab[m], base = e[bp4::dtab_ent(t)];
           work[bp4::dtab_off_work<P>(t)] = base != 0xFFFFFFFFu ? src[(size_t)base + bp4::dtab_rel(t)] : 0.;
         }
-      // phase 1: every item reads its row before any item writes (barrier in the kernel)
-      std::vector<std::array<double, NN>> regs(2 * G::ROWS);
-      for (int it = 0; it < 2 * G::ROWS; ++it)
-        for (int kk = 0; kk < NN; ++kk)
-          regs[it][kk] = work[(it % G::ROWS) * G::RW + kk];
-      for (int it = 0; it < 2 * G::ROWS; ++it)
-        {
-          double in[NN];
-          for (int kk = 0; kk < NN; ++kk)
-            in[kk] = regs[it][kk];
-          if (it < G::ROWS)
-            bp4::phase1_split<P, 0>(tb, in, work.data() + (it % G::ROWS) * G::RW);
-          else
-            bp4::phase1_split<P, 1>(tb, in, work.data() + (it % G::ROWS) * G::RW);
-        }
+      // items in reverse order on purpose: a hazard between items of one sweep would show
+      for (int it = G::ROWS * G::N - 1; it >= 0; --it)
+        bp4::phase1a<P>(tb, work.data() + (it % G::ROWS) * G::RW, it / G::ROWS);
+      for (int it = G::ROWS * G::Q - 1; it >= 0; --it)
+        bp4::phase1b<P>(tb, work.data() + (it % G::ROWS) * G::RW, it / G::ROWS);
+      for (int it = G::ROWS * G::Q - 1; it >= 0; --it)
+        bp4::phase1c<P>(tb, work.data() + (it % G::ROWS) * G::RW, it / G::ROWS);
       for (int it = 0; it < G::ITEMS2; ++it)
         {
           const int qz = it / G::Q, qx = it % G::Q;
           bp4::phase2<P>(tb, cf, work.data(), qx, qz, tb.xq[qx], tb.xq[qz], tb.wq[qx] * tb.wq[qz]);
         }
-      for (int it = 0; it < 2 * G::ROWS; ++it)
-        {
-          double acc[NN];
-          if (it < G::ROWS)
-            bp4::phase3_split<P, 0>(tb, work.data() + (it % G::ROWS) * G::RW, acc);
-          else
-            bp4::phase3_split<P, 1>(tb, work.data() + (it % G::ROWS) * G::RW, acc);
-          for (int kk = 0; kk < NN; ++kk)
-            regs[it][kk] = acc[kk];
-        }
-      for (int it = 0; it < 2 * G::ROWS; ++it) // after the barrier: park the partials in the row
-        for (int kk = 0; kk < NN; ++kk)
-          work[(it % G::ROWS) * G::RW + (it / G::ROWS) * NN + kk] = regs[it][kk];
+      for (int it = G::ROWS * G::Q - 1; it >= 0; --it)
+        bp4::phase3a<P>(tb, work.data() + (it % G::ROWS) * G::RW, it / G::ROWS);
+      for (int it = G::ROWS * G::Q - 1; it >= 0; --it)
+        bp4::phase3b<P>(tb, work.data() + (it % G::ROWS) * G::RW, it / G::ROWS);
+      for (int it = G::ROWS * G::N - 1; it >= 0; --it)
+        bp4::phase3c<P>(tb, work.data() + (it % G::ROWS) * G::RW, it / G::ROWS);
       for (int m = 0; m < G::DOF; ++m)
         {
           const uint32_t t = dtab[m], base = e[bp4::dtab_ent(t)];
           if (base != 0xFFFFFFFFu)
-            dst[(size_t)base + bp4::dtab_rel(t)] +=
-              work[bp4::dtab_off_work<P>(t)] + work[bp4::dtab_off_work<P>(t) + NN];
+            dst[(size_t)base + bp4::dtab_rel(t)] += work[bp4::dtab_off_work<P>(t)];
         }
     }
 }
 
-extern "C" int emu_vmult_cells_split(int p, long n_cells, const uint32_t *eidx, const double *verts,
+extern "C" int emu_vmult_cells_fine(int p, long n_cells, const uint32_t *eidx, const double *verts,
                                      const double *src, double *dst)
 {
   switch (p)
     {
-      case 2: run_split<2>(n_cells, eidx, verts, src, dst); return 0;
-      case 3: run_split<3>(n_cells, eidx, verts, src, dst); return 0;
-      case 4: run_split<4>(n_cells, eidx, verts, src, dst); return 0;
-      case 5: run_split<5>(n_cells, eidx, verts, src, dst); return 0;
-      case 6: run_split<6>(n_cells, eidx, verts, src, dst); return 0;
-      case 7: run_split<7>(n_cells, eidx, verts, src, dst); return 0;
-      case 8: run_split<8>(n_cells, eidx, verts, src, dst); return 0;
+      case 2: run_fine<2>(n_cells, eidx, verts, src, dst); return 0;
+      case 3: run_fine<3>(n_cells, eidx, verts, src, dst); return 0;
+      case 4: run_fine<4>(n_cells, eidx, verts, src, dst); return 0;
+      case 5: run_fine<5>(n_cells, eidx, verts, src, dst); return 0;
+      case 6: run_fine<6>(n_cells, eidx, verts, src, dst); return 0;
+      case 7: run_fine<7>(n_cells, eidx, verts, src, dst); return 0;
+      case 8: run_fine<8>(n_cells, eidx, verts, src, dst); return 0;
     }
   return -1;
 }

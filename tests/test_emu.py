@@ -43,7 +43,7 @@ def test_device_phases_match_oracle(emu, p, s):
     e, vt = np.ascontiguousarray(rd.entity_index), np.ascontiguousarray(rd.vertices)
     assert emu.emu_vmult_cells(p, C.c_long(rd.n_cells), _p(e), _p(vt), _p(v), _p(got)) == 0
     assert rel_l2(got, want) <= 1e-13
-    # the split form of phases 1 and 3 used for the high degrees
+    # the fine-grained sweeps of phases 1 and 3 used for the high degrees
     got2 = np.zeros(rd.n_owned)
-    assert emu.emu_vmult_cells_split(p, C.c_long(rd.n_cells), _p(e), _p(vt), _p(v), _p(got2)) == 0
+    assert emu.emu_vmult_cells_fine(p, C.c_long(rd.n_cells), _p(e), _p(vt), _p(v), _p(got2)) == 0
     assert rel_l2(got2, want) <= 1e-13
