@@ -221,7 +221,7 @@ int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
   c->n_constrained = d->n_constrained;
   // fastest measured plain cell kernel per degree (B200, ~50-100 M DoFs, profiles/README.md):
   // warp-specialised for p <= 3, cp.async prefetch for p = 6 and 8, classic otherwise
-  c->cell_variant = d->degree <= 3 ? 1 : ((d->degree == 6 || d->degree == 8) ? 3 : 2);
+  c->cell_variant = d->degree <= 3 ? 1 : 2;
   c->n_before      = d->n_cells_before_comm;
   c->n_comm        = d->n_cells_comm;
   if (c->n_before + c->n_comm > c->n_cells)

@@ -7,6 +7,9 @@
 #include "bp4_tables.h"
 
 // degrees >= BP4_FINE_FROM run phases 1 and 3 as fine-grained sweeps (phase1a..c, phase3a..c)
+#ifndef BP4_SU
+#  define BP4_SU 6 // scatter unroll
+#endif
 #ifndef BP4_FINE_FROM
 #  define BP4_FINE_FROM 6
 #endif
@@ -242,32 +245,26 @@ namespace bp4
         BP4_TICK(2)
         // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13) is
         // touched by this cell only -> plain store
-        constexpr int SU = 6;
+        constexpr int SU = BP4_SU;
         for (int m0 = tid; m0 < total; m0 += kThreads * SU)
           {
             double   v[SU];
             uint32_t adr[SU];
             bool     inner[SU];
+            // branch-free operand pass (clamped index), then the stores / REDs
 #pragma unroll
             for (int u = 0; u < SU; ++u)
               {
-                const int m = m0 + u * kThreads;
-                adr[u]      = 0xFFFFFFFFu;
-                inner[u]    = false;
-                v[u]        = 0.;
-                if (m < total)
-                  {
-                    const int      cell = m / G::DOF;
-                    const uint32_t t    = sm.dtab[m - cell * G::DOF];
-                    const uint32_t ent  = dtab_ent(t);
-                    const uint32_t base = sm.eidx[bf][cell][ent];
-                    if (base != 0xFFFFFFFFu)
-                      {
-                        adr[u]   = base + dtab_rel(t);
-                        inner[u] = ent == 13u;
-                        v[u]     = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
-                      }
-                  }
+                const int      m    = m0 + u * kThreads;
+                const bool     on   = m < total;
+                const int      mm   = on ? m : 0;
+                const int      cell = mm / G::DOF;
+                const uint32_t t    = sm.dtab[mm - cell * G::DOF];
+                const uint32_t ent  = dtab_ent(t);
+                const uint32_t base = sm.eidx[bf][cell][ent];
+                adr[u]              = on && base != 0xFFFFFFFFu ? base + dtab_rel(t) : 0xFFFFFFFFu;
+                inner[u]            = ent == 13u;
+                v[u]                = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
               }
 #pragma unroll
             for (int u = 0; u < SU; ++u)
