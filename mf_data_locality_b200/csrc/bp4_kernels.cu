@@ -7,6 +7,12 @@
 #include "bp4_tables.h"
 
 // degrees >= BP4_FINE_FROM run phases 1 and 3 as fine-grained sweeps (phase1a..c, phase3a..c)
+#ifndef BP4_P2_CALL_FROM
+#  define BP4_P2_CALL_FROM 6 // degrees >= this call phase 2 out of line
+#endif
+#ifndef BP4_GU
+#  define BP4_GU 32 // gather slots in flight per group (>= slots per batch: one latency)
+#endif
 #ifndef BP4_SU
 #  define BP4_SU 6 // scatter unroll
 #endif
@@ -75,6 +81,18 @@ namespace bp4
 #  define BP4_TICK(k)
 #  define BP4_TICK_FLUSH
 #endif
+
+  // Phase 2 as a real call for the high degrees: its ~100 live doubles get a register allocation
+  // of their own instead of competing with whatever the gather/scatter code around it keeps
+  // alive (the inlined form spilled 2.6x more after an unrelated change to the gather).
+  template <int P>
+  __device__ __noinline__ void phase2_call(const uint32_t cf_off, const uint32_t work_off, const int qx,
+                                           const int qz, const double x, const double z, const double wxz)
+  {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    phase2<P>(c_tab<P>, reinterpret_cast<const double *>(smem_raw + cf_off),
+              reinterpret_cast<double *>(smem_raw + work_off), qx, qz, x, z, wxz);
+  }
 
   // Classic cell kernel: every warp does every phase; two blocks per SM overlap one block's
   // memory phases with the other's FP64 phases.  The memory phases are kept short:
@@ -152,34 +170,44 @@ namespace bp4
         const int nc = batch_cells(i, cell0), bf = i & 1;
         BP4_TICK(0)
         // gather (vector_access_reduced.h:175-258): consecutive threads walk an entity's
-        // contiguous DoF segment; all loads of the batch are issued before the first use
-        constexpr int GU    = 16;
-        const int     total = nc * G::DOF;
-        for (int m0 = tid; m0 < total; m0 += kThreads * GU)
+        // contiguous DoF segment.  Thread tid owns elements tid + r * kThreads of EVERY cell of
+        // the batch, so the table entry is decoded once per r and the (cell, r) slots unroll with
+        // compile-time cell offsets: ~7 instructions per element, all loads of a group of GU
+        // slots in flight together.  Cells missing from a ragged last batch carry invalid entity
+        // indices (fetch_meta) and gather zeros.
+        constexpr int GU = BP4_GU, R = (G::DOF + kThreads - 1) / kThreads, S = CPB * R;
+        // only the last r can run past the end of the cell
+        const bool last_on = tid < G::DOF - (R - 1) * kThreads;
+        auto       on      = [&](const int r) { return r < R - 1 || last_on; };
+        uint32_t   tt[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
+#pragma unroll
+        for (int s0 = 0; s0 < S; s0 += GU)
           {
-            // three straight-line passes (addresses, loads, stores) without branches: the
-            // loads of all GU slots are in flight together
             double   v[GU];
-            uint32_t off[GU], idx[GU];
+            uint32_t idx[GU];
 #pragma unroll
             for (int u = 0; u < GU; ++u)
-              {
-                const int      m    = m0 + u * kThreads;
-                const bool     on   = m < total;
-                const int      mm   = on ? m : 0;
-                const int      cell = mm / G::DOF;
-                const uint32_t t    = sm.dtab[mm - cell * G::DOF];
-                const uint32_t base = sm.eidx[bf][cell][dtab_ent(t)];
-                off[u]              = on ? cell * G::WORK + dtab_off_work<P>(t) : 0xFFFFFFFFu;
-                idx[u]              = on && base != 0xFFFFFFFFu ? base + dtab_rel(t) : 0xFFFFFFFFu;
-              }
+              if (s0 + u < S)
+                {
+                  const int      cell = (s0 + u) / R, r = (s0 + u) % R;
+                  const uint32_t base = sm.eidx[bf][cell][dtab_ent(tt[r])];
+                  idx[u] = on(r) && base != 0xFFFFFFFFu ? base + dtab_rel(tt[r]) : 0xFFFFFFFFu;
+                }
 #pragma unroll
             for (int u = 0; u < GU; ++u)
-              v[u] = idx[u] != 0xFFFFFFFFu ? __ldg(a.src + idx[u]) : 0.;
+              if (s0 + u < S)
+                v[u] = idx[u] != 0xFFFFFFFFu ? __ldg(a.src + idx[u]) : 0.;
 #pragma unroll
             for (int u = 0; u < GU; ++u)
-              if (off[u] != 0xFFFFFFFFu)
-                sm.work[off[u]] = v[u];
+              if (s0 + u < S)
+                {
+                  const int cell = (s0 + u) / R, r = (s0 + u) % R;
+                  if (on(r))
+                    sm.work[cell * G::WORK + dtab_off_work<P>(tt[r])] = v[u];
+                }
           }
         BP4_TICK(1)
         __syncthreads();
@@ -215,8 +243,13 @@ namespace bp4
           {
             const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
             const int qz = r / Q, qx = r % Q;
-            phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
-                      sm.wq[qx] * sm.wq[qz]);
+            if constexpr (P >= BP4_P2_CALL_FROM)
+              phase2_call<P>((uint32_t)((const unsigned char *)sm.coef[bf][cell] - smem_raw),
+                             (uint32_t)((const unsigned char *)(sm.work + cell * G::WORK) - smem_raw), qx, qz,
+                             sm.xq[qx], sm.xq[qz], sm.wq[qx] * sm.wq[qz]);
+            else
+              phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
+                        sm.wq[qx] * sm.wq[qz]);
           }
         BP4_TICK(4)
         __syncthreads();
@@ -246,31 +279,28 @@ namespace bp4
         // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13) is
         // touched by this cell only -> plain store
         constexpr int SU = BP4_SU;
-        for (int m0 = tid; m0 < total; m0 += kThreads * SU)
+#pragma unroll
+        for (int r = 0; r < R; ++r) // read again: nothing is kept in registers across phase 2
+          tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
+#pragma unroll
+        for (int s0 = 0; s0 < S; s0 += SU)
           {
             double   v[SU];
             uint32_t adr[SU];
-            bool     inner[SU];
-            // branch-free operand pass (clamped index), then the stores / REDs
 #pragma unroll
             for (int u = 0; u < SU; ++u)
-              {
-                const int      m    = m0 + u * kThreads;
-                const bool     on   = m < total;
-                const int      mm   = on ? m : 0;
-                const int      cell = mm / G::DOF;
-                const uint32_t t    = sm.dtab[mm - cell * G::DOF];
-                const uint32_t ent  = dtab_ent(t);
-                const uint32_t base = sm.eidx[bf][cell][ent];
-                adr[u]              = on && base != 0xFFFFFFFFu ? base + dtab_rel(t) : 0xFFFFFFFFu;
-                inner[u]            = ent == 13u;
-                v[u]                = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
-              }
-#pragma unroll
-            for (int u = 0; u < SU; ++u)
-              if (adr[u] != 0xFFFFFFFFu)
+              if (s0 + u < S)
                 {
-                  if (inner[u])
+                  const int      cell = (s0 + u) / R, r = (s0 + u) % R;
+                  const uint32_t base = sm.eidx[bf][cell][dtab_ent(tt[r])];
+                  adr[u] = on(r) && base != 0xFFFFFFFFu ? base + dtab_rel(tt[r]) : 0xFFFFFFFFu;
+                  v[u]   = sm.work[cell * G::WORK + dtab_off_work<P>(tt[r])];
+                }
+#pragma unroll
+            for (int u = 0; u < SU; ++u)
+              if (s0 + u < S && adr[u] != 0xFFFFFFFFu)
+                {
+                  if (dtab_ent(tt[(s0 + u) % R]) == 13u)
                     a.dst[adr[u]] = v[u];
                   else
                     atomicAdd(a.dst + adr[u], v[u]);
