@@ -219,9 +219,9 @@ int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
   c->n_owned = d->n_owned;
   c->n_ghost = d->n_ghost;
   c->n_constrained = d->n_constrained;
-  // fastest measured plain cell kernel per degree (B200, ~50-100 M DoFs, profiles/README.md):
-  // warp-specialised for p <= 3, cp.async prefetch for p = 6 and 8, classic otherwise
-  c->cell_variant = d->degree <= 3 ? 1 : 2;
+  // the classic kernel is the fastest (or tied) plain cell kernel at every degree on B200
+  // (profiles/README.md); the other variants stay selectable with bp4_set_merged_variant
+  c->cell_variant = 2;
   c->n_before      = d->n_cells_before_comm;
   c->n_comm        = d->n_cells_comm;
   if (c->n_before + c->n_comm > c->n_cells)

@@ -11,12 +11,13 @@ from oracle import bp4_oracle as O
 from mf_data_locality_b200 import capi
 
 p, s = int(sys.argv[1]), int(sys.argv[2])
-variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+variant = int(sys.argv[3]) if len(sys.argv) > 3 else None  # None: the library's per-degree default
 t0 = time.time()
 rd = O.build_problem(p, s)[0]
 print(f"setup {time.time()-t0:.1f}s cells={rd.n_cells} dofs={rd.n_owned}", flush=True)
 ctx = capi.Context(p, rd.entity_index, rd.vertices, rd.n_owned, 0, rd.constrained)
-ctx.set_merged_variant(variant)
+if variant is not None:
+    ctx.set_merged_variant(variant)
 n = rd.n_owned
 src, dst = ctx.vector(data=rd.rhs), ctx.vector()
 for _ in range(3):
