@@ -34,6 +34,11 @@
 #  define BP4_UNROLL
 #endif
 
+// BP4_EO = 1: even-odd 1-D contractions (eo_first / eo_second); 0: plain dense form
+#ifndef BP4_EO
+#  define BP4_EO 1
+#endif
+
 namespace bp4
 {
   // 1 / x without control flow: MUFU.RCP64H seed (~20 bits) + two Newton steps (-> < 1 ulp for
@@ -64,7 +69,123 @@ namespace bp4
     double D[Q][Q];                 // D[i][q]  = d/dx l_i^Gauss(x_q)     (collocation gradient)
     double xq[Q];                   // Gauss points on [0,1]
     double wq[Q];                   // Gauss weights
+    // even-odd halves (the role of deal.II's shape_values_eo / shape_gradients_collocation_eo,
+    // poisson_operator.h:461-463): S[i][q] = S[N-1-i][Q-1-q], D and Dn change sign under the
+    // same reflection.  Xf* pair the FIRST index (used when it is contracted), Xs* the SECOND:
+    //   Xfp[i][q] = (X[i][q] + X[n-1-i][q]) / 2,  Xfm[i][q] = (X[i][q] - X[n-1-i][q]) / 2
+    //   Xsp[i][q] = (X[i][q] + X[i][m-1-q]) / 2,  Xsm[i][q] = (X[i][q] - X[i][m-1-q]) / 2
+    double Sfp[N][Q], Sfm[N][Q], Ssp[N][Q], Ssm[N][Q];
+    double Dnfp[N][Q], Dnfm[N][Q], Dnsp[N][Q], Dnsm[N][Q];
+    double Dfp[Q][Q], Dfm[Q][Q], Dsp[Q][Q], Dsm[Q][Q];
   };
+
+  // ---------------------------------------------------------------------------------------
+  // even-odd 1-D contractions on register arrays.  SG = +1: M[i][q] = M[NI-1-i][NO-1-q] (values),
+  // SG = -1: M[i][q] = -M[NI-1-i][NO-1-q] (derivatives).  About half the multiplications of the
+  // plain form: sums/differences of mirrored inputs meet the even/odd halves of the matrix, and
+  // mirrored outputs are E + O and SG (E - O).
+  // ---------------------------------------------------------------------------------------
+  // out[q] = sum_i M[i][q] in[i]   (first index contracted; Mp/Mm = M's "f" halves)
+  template <int NI, int NO, int SG>
+  BP4_HD void eo_first(const double (&Mp)[NI][NO], const double (&Mm)[NI][NO], const double (&M)[NI][NO],
+                       const double (&in)[NI], double (&out)[NO])
+  {
+    constexpr int HI = NI / 2, HO = NO / 2;
+    double        e[HI > 0 ? HI : 1], o[HI > 0 ? HI : 1];
+    BP4_UNROLL
+    for (int i = 0; i < HI; ++i)
+      {
+        e[i] = in[i] + in[NI - 1 - i];
+        o[i] = in[i] - in[NI - 1 - i];
+      }
+    BP4_UNROLL
+    for (int q = 0; q < HO; ++q)
+      {
+        double E = Mp[0][q] * e[0], O = Mm[0][q] * o[0];
+        BP4_UNROLL
+        for (int i = 1; i < HI; ++i)
+          {
+            E += Mp[i][q] * e[i];
+            O += Mm[i][q] * o[i];
+          }
+        if (NI % 2)
+          E += M[HI][q] * in[HI];
+        out[q]          = E + O;
+        out[NO - 1 - q] = SG > 0 ? E - O : O - E;
+      }
+    if (NO % 2) // the middle output is its own mirror image: only one half contributes
+      {
+        double s;
+        if (SG > 0)
+          {
+            s = Mp[0][HO] * e[0];
+            BP4_UNROLL
+            for (int i = 1; i < HI; ++i)
+              s += Mp[i][HO] * e[i];
+            if (NI % 2)
+              s += M[HI][HO] * in[HI];
+          }
+        else
+          {
+            s = Mm[0][HO] * o[0];
+            BP4_UNROLL
+            for (int i = 1; i < HI; ++i)
+              s += Mm[i][HO] * o[i];
+          }
+        out[HO] = s;
+      }
+  }
+
+  // out[i] = sum_q M[i][q] in[q]   (second index contracted; Mp/Mm = M's "s" halves)
+  template <int NI, int NO, int SG>
+  BP4_HD void eo_second(const double (&Mp)[NI][NO], const double (&Mm)[NI][NO], const double (&M)[NI][NO],
+                        const double (&in)[NO], double (&out)[NI])
+  {
+    constexpr int HI = NI / 2, HO = NO / 2;
+    double        e[HO > 0 ? HO : 1], o[HO > 0 ? HO : 1];
+    BP4_UNROLL
+    for (int q = 0; q < HO; ++q)
+      {
+        e[q] = in[q] + in[NO - 1 - q];
+        o[q] = in[q] - in[NO - 1 - q];
+      }
+    BP4_UNROLL
+    for (int i = 0; i < HI; ++i)
+      {
+        double E = Mp[i][0] * e[0], O = Mm[i][0] * o[0];
+        BP4_UNROLL
+        for (int q = 1; q < HO; ++q)
+          {
+            E += Mp[i][q] * e[q];
+            O += Mm[i][q] * o[q];
+          }
+        if (NO % 2)
+          E += M[i][HO] * in[HO];
+        out[i]          = E + O;
+        out[NI - 1 - i] = SG > 0 ? E - O : O - E;
+      }
+    if (NI % 2)
+      {
+        double s;
+        if (SG > 0)
+          {
+            s = Mp[HI][0] * e[0];
+            BP4_UNROLL
+            for (int q = 1; q < HO; ++q)
+              s += Mp[HI][q] * e[q];
+            if (NO % 2)
+              s += M[HI][HO] * in[HO];
+          }
+        else
+          {
+            s = Mm[HI][0] * o[0];
+            BP4_UNROLL
+            for (int q = 1; q < HO; ++q)
+              s += Mm[HI][q] * o[q];
+          }
+        out[HI] = s;
+      }
+  }
 
   template <int P>
   struct Geom // sizes and shared-memory strides of one cell slot
@@ -237,6 +358,87 @@ namespace bp4
   template <int P, typename In>
   BP4_HD void phase1_io(const Tab<P> &tb, const In in, double *out)
   {
+#if BP4_EO
+    using G         = Geom<P>;
+    constexpr int N = G::N, Q = G::Q, HN = N / 2, HQ = Q / 2;
+    double        t[N][Q];
+    BP4_UNROLL
+    for (int k = 0; k < N; ++k)
+      {
+        double r[N];
+        BP4_UNROLL
+        for (int i = 0; i < N; ++i)
+          r[i] = in(k * N + i);
+        eo_first<N, Q, 1>(tb.Sfp, tb.Sfm, tb.S, r, t[k]);
+      }
+    // z direction: rows k and N-1-k of t become their sum and difference, then every pair of
+    // output layers (qz, Q-1-qz) shares the even and odd partial sums
+    BP4_UNROLL
+    for (int k = 0; k < HN; ++k)
+      BP4_UNROLL
+    for (int q = 0; q < Q; ++q)
+      {
+        const double e = t[k][q] + t[N - 1 - k][q], o = t[k][q] - t[N - 1 - k][q];
+        t[k][q]         = e;
+        t[N - 1 - k][q] = o;
+      }
+    BP4_UNROLL
+    for (int qz = 0; qz < (Q + 1) / 2; ++qz)
+      {
+        const bool mid = (Q % 2) && qz == HQ; // the middle layer is its own mirror image
+        double     uA[Q], uB[Q], zA[Q], zB[Q], sA[Q], sB[Q];
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            double Eu = tb.Sfp[0][qz] * t[0][q], Ou = tb.Sfm[0][qz] * t[N - 1][q];
+            double Ez = tb.Dnfp[0][qz] * t[0][q], Oz = tb.Dnfm[0][qz] * t[N - 1][q];
+            BP4_UNROLL
+            for (int k = 1; k < HN; ++k)
+              {
+                Eu += tb.Sfp[k][qz] * t[k][q];
+                Ou += tb.Sfm[k][qz] * t[N - 1 - k][q];
+                Ez += tb.Dnfp[k][qz] * t[k][q];
+                Oz += tb.Dnfm[k][qz] * t[N - 1 - k][q];
+              }
+            if (N % 2)
+              {
+                Eu += tb.S[HN][qz] * t[HN][q];
+                Ez += tb.Dn[HN][qz] * t[HN][q];
+              }
+            if (mid)
+              {
+                uA[q] = Eu;
+                zA[q] = Oz;
+              }
+            else
+              {
+                uA[q] = Eu + Ou;
+                uB[q] = Eu - Ou;
+                zA[q] = Ez + Oz;
+                zB[q] = Oz - Ez;
+              }
+          }
+        eo_first<Q, Q, -1>(tb.Dfp, tb.Dfm, tb.D, uA, sA);
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            out[0 * Q * Q + qz * Q + q] = uA[q];
+            out[1 * Q * Q + qz * Q + q] = sA[q];
+            out[2 * Q * Q + qz * Q + q] = zA[q];
+          }
+        if (!mid)
+          {
+            eo_first<Q, Q, -1>(tb.Dfp, tb.Dfm, tb.D, uB, sB);
+            BP4_UNROLL
+            for (int q = 0; q < Q; ++q)
+              {
+                out[0 * Q * Q + (Q - 1 - qz) * Q + q] = uB[q];
+                out[1 * Q * Q + (Q - 1 - qz) * Q + q] = sB[q];
+                out[2 * Q * Q + (Q - 1 - qz) * Q + q] = zB[q];
+              }
+          }
+      }
+#else
     using G         = Geom<P>;
     constexpr int N = G::N, Q = G::Q;
     double        t[N][Q];
@@ -287,6 +489,7 @@ namespace bp4
             out[2 * Q * Q + qz * Q + q] = wz[q];
           }
       }
+#endif
   }
 
   // ---------------------------------------------------------------------------------------
@@ -311,6 +514,13 @@ namespace bp4
     BP4_UNROLL
     for (int i = 0; i < N; ++i)
       r[i] = row[k * N + i];
+#if BP4_EO
+    double o[Q];
+    eo_first<N, Q, 1>(tb.Sfp, tb.Sfm, tb.S, r, o);
+    BP4_UNROLL
+    for (int q = 0; q < Q; ++q)
+      row[2 * Q * Q + k * Q + q] = o[q];
+#else
     BP4_UNROLL
     for (int q = 0; q < Q; ++q)
       {
@@ -320,6 +530,7 @@ namespace bp4
           s += tb.S[i][q] * r[i];
         row[2 * Q * Q + k * Q + q] = s;
       }
+#endif
   }
 
   template <int P>
@@ -330,6 +541,17 @@ namespace bp4
     BP4_UNROLL
     for (int k = 0; k < N; ++k)
       t[k] = row[2 * Q * Q + k * Q + qx];
+#if BP4_EO
+    double su[Q], sz[Q];
+    eo_first<N, Q, 1>(tb.Sfp, tb.Sfm, tb.S, t, su);
+    eo_first<N, Q, -1>(tb.Dnfp, tb.Dnfm, tb.Dn, t, sz);
+    BP4_UNROLL
+    for (int qz = 0; qz < Q; ++qz)
+      {
+        row[0 * Q * Q + qz * Q + qx] = su[qz];
+        row[2 * Q * Q + qz * Q + qx] = sz[qz];
+      }
+#else
     BP4_UNROLL
     for (int qz = 0; qz < Q; ++qz)
       {
@@ -344,6 +566,7 @@ namespace bp4
         row[0 * Q * Q + qz * Q + qx] = su;
         row[2 * Q * Q + qz * Q + qx] = sz;
       }
+#endif
   }
 
   template <int P>
@@ -354,6 +577,13 @@ namespace bp4
     BP4_UNROLL
     for (int i = 0; i < Q; ++i)
       u[i] = row[qz * Q + i];
+#if BP4_EO
+    double sx[Q];
+    eo_first<Q, Q, -1>(tb.Dfp, tb.Dfm, tb.D, u, sx);
+    BP4_UNROLL
+    for (int q = 0; q < Q; ++q)
+      row[1 * Q * Q + qz * Q + q] = sx[q];
+#else
     BP4_UNROLL
     for (int q = 0; q < Q; ++q)
       {
@@ -363,6 +593,7 @@ namespace bp4
           sx += tb.D[i][q] * u[i];
         row[1 * Q * Q + qz * Q + q] = sx;
       }
+#endif
   }
 
   template <int P>
@@ -373,6 +604,13 @@ namespace bp4
     BP4_UNROLL
     for (int q = 0; q < Q; ++q)
       fx[q] = row[1 * Q * Q + qz * Q + q];
+#if BP4_EO
+    double d[Q];
+    eo_second<Q, Q, -1>(tb.Dsp, tb.Dsm, tb.D, fx, d);
+    BP4_UNROLL
+    for (int i = 0; i < Q; ++i)
+      row[qz * Q + i] += d[i];
+#else
     BP4_UNROLL
     for (int i = 0; i < Q; ++i)
       {
@@ -382,6 +620,7 @@ namespace bp4
           s += tb.D[i][q] * fx[q];
         row[qz * Q + i] = s;
       }
+#endif
   }
 
   template <int P>
@@ -395,6 +634,14 @@ namespace bp4
         v[qz]  = row[0 * Q * Q + qz * Q + qx];
         fz[qz] = row[2 * Q * Q + qz * Q + qx];
       }
+#if BP4_EO
+    double sv[N], sf[N];
+    eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, v, sv);
+    eo_second<N, Q, -1>(tb.Dnsp, tb.Dnsm, tb.Dn, fz, sf);
+    BP4_UNROLL
+    for (int k = 0; k < N; ++k)
+      row[2 * Q * Q + k * Q + qx] = sv[k] + sf[k];
+#else
     BP4_UNROLL
     for (int k = 0; k < N; ++k)
       {
@@ -404,6 +651,7 @@ namespace bp4
           s += tb.S[k][qz] * v[qz] + tb.Dn[k][qz] * fz[qz];
         row[2 * Q * Q + k * Q + qx] = s;
       }
+#endif
   }
 
   template <int P>
@@ -414,6 +662,13 @@ namespace bp4
     BP4_UNROLL
     for (int q = 0; q < Q; ++q)
       t[q] = row[2 * Q * Q + k * Q + q];
+#if BP4_EO
+    double o[N];
+    eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, t, o);
+    BP4_UNROLL
+    for (int i = 0; i < N; ++i)
+      row[k * N + i] = o[i];
+#else
     BP4_UNROLL
     for (int i = 0; i < N; ++i)
       {
@@ -423,6 +678,7 @@ namespace bp4
           s += tb.S[i][q] * t[q];
         row[k * N + i] = s;
       }
+#endif
   }
 
   // ---------------------------------------------------------------------------------------
@@ -497,6 +753,43 @@ namespace bp4
 #endif
     for (int c = 0; c < 3; ++c)
       {
+#if BP4_EO
+        double *base = work + (c * N) * G::RW + qz * Q + qx; // rows (c, j), j = 0..N-1
+        double  gx[Q], gy[Q], gz[Q], v[Q], a0[N], a1[N], a2[N];
+        BP4_UNROLL
+        for (int j = 0; j < N; ++j)
+          {
+            a0[j] = base[j * G::RW];
+            a1[j] = base[j * G::RW + Q * Q];
+            a2[j] = base[j * G::RW + 2 * Q * Q];
+          }
+        // y-interpolation of value, xi-derivative and zeta-derivative lines, then d/deta
+        eo_first<N, Q, 1>(tb.Sfp, tb.Sfm, tb.S, a0, v);
+        eo_first<N, Q, 1>(tb.Sfp, tb.Sfm, tb.S, a1, gx);
+        eo_first<N, Q, 1>(tb.Sfp, tb.Sfm, tb.S, a2, gz);
+        eo_first<Q, Q, -1>(tb.Dfp, tb.Dfm, tb.D, v, gy);
+        // flux = G grad
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            const double a = gx[q], b = gy[q], e = gz[q];
+            gx[q] = g00[q] * a + g01[q] * b + g02[q] * e;
+            gy[q] = g01[q] * a + g11[q] * b + g12[q] * e;
+            gz[q] = g02[q] * a + g12[q] * b + g22[q] * e;
+          }
+        // d/deta^T on the eta-flux -> value-like line, then y-back-interpolation of the three lines
+        eo_second<Q, Q, -1>(tb.Dsp, tb.Dsm, tb.D, gy, v);
+        eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, v, a0);
+        eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, gx, a1);
+        eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, gz, a2);
+        BP4_UNROLL
+        for (int j = 0; j < N; ++j)
+          {
+            base[j * G::RW]             = a0[j];
+            base[j * G::RW + Q * Q]     = a1[j];
+            base[j * G::RW + 2 * Q * Q] = a2[j];
+          }
+#else
         double *base = work + (c * N) * G::RW + qz * Q + qx; // rows (c, j), j = 0..N-1
         double  gx[Q], gy[Q], gz[Q], v[Q];
         // y-interpolation of value, xi-derivative and zeta-derivative lines
@@ -551,6 +844,7 @@ namespace bp4
             base[j * G::RW + Q * Q]     = o1;
             base[j * G::RW + 2 * Q * Q] = o2;
           }
+#endif
       }
   }
 
@@ -698,6 +992,94 @@ namespace bp4
   template <int P, typename Out>
   BP4_HD void phase3_io(const Tab<P> &tb, const double *in, const Out out)
   {
+#if BP4_EO
+    using G         = Geom<P>;
+    constexpr int N = G::N, Q = G::Q, HN = N / 2, HQ = Q / 2;
+    // X = (even part of S^T v) + (odd part of Dn^T fz), Y = (odd of S^T v) + (even of Dn^T fz):
+    // t[k] = X[k] + Y[k], t[N-1-k] = X[k] - Y[k]
+    double X[(N + 1) / 2][Q], Y[HN > 0 ? HN : 1][Q];
+    BP4_UNROLL
+    for (int qz = 0; qz < (Q + 1) / 2; ++qz)
+      {
+        const bool mid = (Q % 2) && qz == HQ;
+        double     vA[Q], fA[Q], zA[Q], vB[Q], fB[Q], zB[Q], d[Q];
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            vA[q] = in[0 * Q * Q + qz * Q + q];
+            fA[q] = in[1 * Q * Q + qz * Q + q];
+            zA[q] = in[2 * Q * Q + qz * Q + q];
+          }
+        eo_second<Q, Q, -1>(tb.Dsp, tb.Dsm, tb.D, fA, d);
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          vA[q] += d[q];
+        if (!mid)
+          {
+            BP4_UNROLL
+            for (int q = 0; q < Q; ++q)
+              {
+                vB[q] = in[0 * Q * Q + (Q - 1 - qz) * Q + q];
+                fB[q] = in[1 * Q * Q + (Q - 1 - qz) * Q + q];
+                zB[q] = in[2 * Q * Q + (Q - 1 - qz) * Q + q];
+              }
+            eo_second<Q, Q, -1>(tb.Dsp, tb.Dsm, tb.D, fB, d);
+            BP4_UNROLL
+            for (int q = 0; q < Q; ++q)
+              {
+                const double vb = vB[q] + d[q];
+                const double ev = vA[q] + vb, ov = vA[q] - vb, ef = zA[q] + zB[q], of = zA[q] - zB[q];
+                BP4_UNROLL
+                for (int k = 0; k < (N + 1) / 2; ++k)
+                  {
+                    const double x = tb.Ssp[k][qz] * ev + tb.Dnsm[k][qz] * of;
+                    X[k][q]        = qz == 0 ? x : X[k][q] + x;
+                  }
+                BP4_UNROLL
+                for (int k = 0; k < HN; ++k)
+                  {
+                    const double y = tb.Ssm[k][qz] * ov + tb.Dnsp[k][qz] * ef;
+                    Y[k][q]        = qz == 0 ? y : Y[k][q] + y;
+                  }
+              }
+          }
+        else
+          {
+            BP4_UNROLL
+            for (int q = 0; q < Q; ++q)
+              {
+                BP4_UNROLL
+                for (int k = 0; k < (N + 1) / 2; ++k)
+                  X[k][q] += tb.S[k][qz] * vA[q];
+                BP4_UNROLL
+                for (int k = 0; k < HN; ++k)
+                  Y[k][q] += tb.Dn[k][qz] * zA[q];
+              }
+          }
+      }
+    BP4_UNROLL
+    for (int k = 0; k < (N + 1) / 2; ++k)
+      {
+        double tA[Q], tB[Q], o[N];
+        BP4_UNROLL
+        for (int q = 0; q < Q; ++q)
+          {
+            tA[q] = k < HN ? X[k][q] + Y[k < HN ? k : 0][q] : X[k][q];
+            tB[q] = k < HN ? X[k][q] - Y[k < HN ? k : 0][q] : 0.;
+          }
+        eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, tA, o);
+        BP4_UNROLL
+        for (int i = 0; i < N; ++i)
+          out(k * N + i, o[i]);
+        if (k < HN)
+          {
+            eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, tB, o);
+            BP4_UNROLL
+            for (int i = 0; i < N; ++i)
+              out((N - 1 - k) * N + i, o[i]);
+          }
+      }
+#else
     using G         = Geom<P>;
     constexpr int N = G::N, Q = G::Q;
     double        t[N][Q];
@@ -743,6 +1125,7 @@ namespace bp4
           s += tb.S[i][q] * t[k][q];
         out(k * N + i, s);
       }
+#endif
   }
 
   template <int P>

@@ -158,5 +158,19 @@ namespace bp4
         for (int i = 0; i < Q; ++i)
           tb.D[i][q] = lagrange_deriv(xq, i, xq[q]);
       }
+    // even-odd halves, formed from the rounded entries
+    auto halves = [](auto &M, auto &fp, auto &fm, auto &sp, auto &sm, const int ni, const int no) {
+      for (int i = 0; i < ni; ++i)
+        for (int q = 0; q < no; ++q)
+          {
+            fp[i][q] = 0.5 * (M[i][q] + M[ni - 1 - i][q]);
+            fm[i][q] = 0.5 * (M[i][q] - M[ni - 1 - i][q]);
+            sp[i][q] = 0.5 * (M[i][q] + M[i][no - 1 - q]);
+            sm[i][q] = 0.5 * (M[i][q] - M[i][no - 1 - q]);
+          }
+    };
+    halves(tb.S, tb.Sfp, tb.Sfm, tb.Ssp, tb.Ssm, N, Q);
+    halves(tb.Dn, tb.Dnfp, tb.Dnfm, tb.Dnsp, tb.Dnsm, N, Q);
+    halves(tb.D, tb.Dfp, tb.Dfm, tb.Dsp, tb.Dsm, Q, Q);
   }
 } // namespace bp4
