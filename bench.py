@@ -288,12 +288,12 @@ def main():
                 "kernel_ms_avg": avg_ms, "kernel_launches": int(kcnt.value),
                 "kernel_share_of_step": kms.value / total_ms if total_ms else None,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                # second roof: the cell kernel is FP64-pipe bound.  395 FP64
-                # warp-lane instructions per DoF were counted by ncu at Q4 (627.7 M FP64 warp instructions per apply,
-                # profiles/r01_final2_cell_kernel_q4_s18.txt + its source page); the peak is
+                # second roof: the cell kernel is FP64-pipe bound.  336 FP64
+                # warp-lane instructions per DoF were counted by ncu at Q4 (533.9 M FP64 warp instructions per apply,
+                # profiles/r01_final3_cell_kernel_q4_s18.txt + its source page); the peak is
                 # 148 SMs x 64 lanes x sm_max_mhz
-                "fp64_pipe": ({"instr_per_dof": 395, "peak_lane_instr_per_s": 148 * 64 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6,
-                               "frac": 395.0 * prob.n_owned / (avg_ms * 1e-3) /
+                "fp64_pipe": ({"instr_per_dof": 336, "peak_lane_instr_per_s": 148 * 64 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6,
+                               "frac": 336.0 * prob.n_owned / (avg_ms * 1e-3) /
                                        (148 * 64 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6)}
                               if args.degree == 4 and avg_ms > 0 and not fused else None),
                 "iteration": {"algorithmic_bytes": it_bytes, "ms": it_ms,
