@@ -101,7 +101,7 @@ namespace bp4
   //  * the gather issues all loads of the batch before the first use (one latency, not many);
   //  * the scatter reads its table/index/value operands for several DoFs before the REDs go out.
   template <int P, int CPB>
-  __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_plain(const CellArgs a)
+  __global__ void __launch_bounds__(kThreads, Cfg<P>::BLOCKS) cell_kernel_plain(const CellArgs a)
   {
     using G         = Geom<P>;
     constexpr int Q = G::Q, NN = G::N * G::N;
@@ -1699,7 +1699,7 @@ namespace bp4
   {
     constexpr int  CPB       = Cfg<P>::CPB;
     const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
+    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * Cfg<P>::BLOCKS);
     if (grid == 0)
       return cudaSuccess;
     cell_kernel_plain<P, CPB><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);

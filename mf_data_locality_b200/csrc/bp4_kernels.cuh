@@ -15,15 +15,22 @@ namespace bp4
   // may use up to 255 registers per thread (phase 2 keeps 9*Q doubles live), and while one
   // block waits on its gather or a barrier the other keeps the FP64 pipe busy.
   constexpr int kThreads     = 128;
-  constexpr int kBlocksPerSM = 2;
-  constexpr int kSmemBudget  = 113 * 1024; // per block, two blocks per SM
+#ifndef BP4_BLOCKS_PER_SM
+#  define BP4_BLOCKS_PER_SM 2
+#endif
+  constexpr int kBlocksPerSM = BP4_BLOCKS_PER_SM;
+  constexpr int kSmemBudget  = (227 * 1024) / kBlocksPerSM - 512; // per block
 
   template <int P>
   struct Cfg
   {
     using G = Geom<P>;
+    // resident blocks per SM of the classic cell kernel: three (<= 168 registers, smaller batches)
+    // measured faster at Q2 (+12 %) and Q6 (+13 %), slower or equal elsewhere
+    static constexpr int BLOCKS   = (P == 2 || P == 6) ? 3 : kBlocksPerSM;
+    static constexpr int budget   = (227 * 1024) / BLOCKS - 512;
     static constexpr int per_cell = (G::WORK + 2 * 24) * 8 + 2 * 28 * 4 + 28 + 64 * 5 + 16;
-    static constexpr int fit      = (kSmemBudget - 4 * G::DOF - 16 * G::Q - 256) / per_cell;
+    static constexpr int fit      = (budget - 4 * G::DOF - 16 * G::Q - 256) / per_cell;
     // phase 2 carries ~2/3 of the FP64 work: prefer Q^2*CPB close to a multiple of the block
     static constexpr int want = (2 * kThreads) / (G::Q * G::Q) > 0 ? (2 * kThreads) / (G::Q * G::Q) : 1;
     static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
