@@ -34,11 +34,6 @@
 #  define BP4_UNROLL
 #endif
 
-// BP4_EO = 1: even-odd 1-D contractions (eo_first / eo_second); 0: plain dense form
-#ifndef BP4_EO
-#  define BP4_EO 1
-#endif
-
 namespace bp4
 {
   // 1 / x without control flow: MUFU.RCP64H seed (~20 bits) + two Newton steps (-> < 1 ulp for
@@ -358,7 +353,6 @@ namespace bp4
   template <int P, typename In>
   BP4_HD void phase1_io(const Tab<P> &tb, const In in, double *out)
   {
-#if BP4_EO
     using G         = Geom<P>;
     constexpr int N = G::N, Q = G::Q, HN = N / 2, HQ = Q / 2;
     double        t[N][Q];
@@ -438,58 +432,6 @@ namespace bp4
               }
           }
       }
-#else
-    using G         = Geom<P>;
-    constexpr int N = G::N, Q = G::Q;
-    double        t[N][Q];
-    BP4_UNROLL
-    for (int k = 0; k < N; ++k)
-      {
-        double r[N];
-        BP4_UNROLL
-        for (int i = 0; i < N; ++i)
-          r[i] = in(k * N + i);
-        BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          {
-            double s = tb.S[0][q] * r[0];
-            BP4_UNROLL
-            for (int i = 1; i < N; ++i)
-              s += tb.S[i][q] * r[i];
-            t[k][q] = s;
-          }
-      }
-    BP4_UNROLL
-    for (int qz = 0; qz < Q; ++qz)
-      {
-        double u[Q], wz[Q];
-        BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          {
-            double su = tb.S[0][qz] * t[0][q];
-            double sz = tb.Dn[0][qz] * t[0][q];
-            BP4_UNROLL
-            for (int k = 1; k < N; ++k)
-              {
-                su += tb.S[k][qz] * t[k][q];
-                sz += tb.Dn[k][qz] * t[k][q];
-              }
-            u[q]  = su;
-            wz[q] = sz;
-          }
-        BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          {
-            double sx = tb.D[0][q] * u[0];
-            BP4_UNROLL
-            for (int i = 1; i < Q; ++i)
-              sx += tb.D[i][q] * u[i];
-            out[0 * Q * Q + qz * Q + q] = u[q];
-            out[1 * Q * Q + qz * Q + q] = sx;
-            out[2 * Q * Q + qz * Q + q] = wz[q];
-          }
-      }
-#endif
   }
 
   // ---------------------------------------------------------------------------------------
@@ -514,23 +456,11 @@ namespace bp4
     BP4_UNROLL
     for (int i = 0; i < N; ++i)
       r[i] = row[k * N + i];
-#if BP4_EO
     double o[Q];
     eo_first<N, Q, 1>(tb.Sfp, tb.Sfm, tb.S, r, o);
     BP4_UNROLL
     for (int q = 0; q < Q; ++q)
       row[2 * Q * Q + k * Q + q] = o[q];
-#else
-    BP4_UNROLL
-    for (int q = 0; q < Q; ++q)
-      {
-        double s = tb.S[0][q] * r[0];
-        BP4_UNROLL
-        for (int i = 1; i < N; ++i)
-          s += tb.S[i][q] * r[i];
-        row[2 * Q * Q + k * Q + q] = s;
-      }
-#endif
   }
 
   template <int P>
@@ -541,7 +471,6 @@ namespace bp4
     BP4_UNROLL
     for (int k = 0; k < N; ++k)
       t[k] = row[2 * Q * Q + k * Q + qx];
-#if BP4_EO
     double su[Q], sz[Q];
     eo_first<N, Q, 1>(tb.Sfp, tb.Sfm, tb.S, t, su);
     eo_first<N, Q, -1>(tb.Dnfp, tb.Dnfm, tb.Dn, t, sz);
@@ -551,22 +480,6 @@ namespace bp4
         row[0 * Q * Q + qz * Q + qx] = su[qz];
         row[2 * Q * Q + qz * Q + qx] = sz[qz];
       }
-#else
-    BP4_UNROLL
-    for (int qz = 0; qz < Q; ++qz)
-      {
-        double su = tb.S[0][qz] * t[0];
-        double sz = tb.Dn[0][qz] * t[0];
-        BP4_UNROLL
-        for (int k = 1; k < N; ++k)
-          {
-            su += tb.S[k][qz] * t[k];
-            sz += tb.Dn[k][qz] * t[k];
-          }
-        row[0 * Q * Q + qz * Q + qx] = su;
-        row[2 * Q * Q + qz * Q + qx] = sz;
-      }
-#endif
   }
 
   template <int P>
@@ -577,23 +490,11 @@ namespace bp4
     BP4_UNROLL
     for (int i = 0; i < Q; ++i)
       u[i] = row[qz * Q + i];
-#if BP4_EO
     double sx[Q];
     eo_first<Q, Q, -1>(tb.Dfp, tb.Dfm, tb.D, u, sx);
     BP4_UNROLL
     for (int q = 0; q < Q; ++q)
       row[1 * Q * Q + qz * Q + q] = sx[q];
-#else
-    BP4_UNROLL
-    for (int q = 0; q < Q; ++q)
-      {
-        double sx = tb.D[0][q] * u[0];
-        BP4_UNROLL
-        for (int i = 1; i < Q; ++i)
-          sx += tb.D[i][q] * u[i];
-        row[1 * Q * Q + qz * Q + q] = sx;
-      }
-#endif
   }
 
   template <int P>
@@ -604,23 +505,11 @@ namespace bp4
     BP4_UNROLL
     for (int q = 0; q < Q; ++q)
       fx[q] = row[1 * Q * Q + qz * Q + q];
-#if BP4_EO
     double d[Q];
     eo_second<Q, Q, -1>(tb.Dsp, tb.Dsm, tb.D, fx, d);
     BP4_UNROLL
     for (int i = 0; i < Q; ++i)
       row[qz * Q + i] += d[i];
-#else
-    BP4_UNROLL
-    for (int i = 0; i < Q; ++i)
-      {
-        double s = row[qz * Q + i];
-        BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          s += tb.D[i][q] * fx[q];
-        row[qz * Q + i] = s;
-      }
-#endif
   }
 
   template <int P>
@@ -634,24 +523,12 @@ namespace bp4
         v[qz]  = row[0 * Q * Q + qz * Q + qx];
         fz[qz] = row[2 * Q * Q + qz * Q + qx];
       }
-#if BP4_EO
     double sv[N], sf[N];
     eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, v, sv);
     eo_second<N, Q, -1>(tb.Dnsp, tb.Dnsm, tb.Dn, fz, sf);
     BP4_UNROLL
     for (int k = 0; k < N; ++k)
       row[2 * Q * Q + k * Q + qx] = sv[k] + sf[k];
-#else
-    BP4_UNROLL
-    for (int k = 0; k < N; ++k)
-      {
-        double s = tb.S[k][0] * v[0] + tb.Dn[k][0] * fz[0];
-        BP4_UNROLL
-        for (int qz = 1; qz < Q; ++qz)
-          s += tb.S[k][qz] * v[qz] + tb.Dn[k][qz] * fz[qz];
-        row[2 * Q * Q + k * Q + qx] = s;
-      }
-#endif
   }
 
   template <int P>
@@ -662,23 +539,11 @@ namespace bp4
     BP4_UNROLL
     for (int q = 0; q < Q; ++q)
       t[q] = row[2 * Q * Q + k * Q + q];
-#if BP4_EO
     double o[N];
     eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, t, o);
     BP4_UNROLL
     for (int i = 0; i < N; ++i)
       row[k * N + i] = o[i];
-#else
-    BP4_UNROLL
-    for (int i = 0; i < N; ++i)
-      {
-        double s = tb.S[i][0] * t[0];
-        BP4_UNROLL
-        for (int q = 1; q < Q; ++q)
-          s += tb.S[i][q] * t[q];
-        row[k * N + i] = s;
-      }
-#endif
   }
 
   // ---------------------------------------------------------------------------------------
@@ -753,7 +618,6 @@ namespace bp4
 #endif
     for (int c = 0; c < 3; ++c)
       {
-#if BP4_EO
         double *base = work + (c * N) * G::RW + qz * Q + qx; // rows (c, j), j = 0..N-1
         double  gx[Q], gy[Q], gz[Q], v[Q], a0[N], a1[N], a2[N];
         BP4_UNROLL
@@ -789,62 +653,6 @@ namespace bp4
             base[j * G::RW + Q * Q]     = a1[j];
             base[j * G::RW + 2 * Q * Q] = a2[j];
           }
-#else
-        double *base = work + (c * N) * G::RW + qz * Q + qx; // rows (c, j), j = 0..N-1
-        double  gx[Q], gy[Q], gz[Q], v[Q];
-        // y-interpolation of value, xi-derivative and zeta-derivative lines
-        BP4_UNROLL
-        for (int j = 0; j < N; ++j)
-          {
-            const double r0 = base[j * G::RW], r1 = base[j * G::RW + Q * Q], r2 = base[j * G::RW + 2 * Q * Q];
-            BP4_UNROLL
-            for (int q = 0; q < Q; ++q)
-              {
-                const double sjq = tb.S[j][q];
-                v[q]  = j == 0 ? sjq * r0 : v[q] + sjq * r0;
-                gx[q] = j == 0 ? sjq * r1 : gx[q] + sjq * r1;
-                gz[q] = j == 0 ? sjq * r2 : gz[q] + sjq * r2;
-              }
-          }
-        // d/deta
-        BP4_UNROLL
-        for (int i = 0; i < Q; ++i)
-          BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          gy[q] = i == 0 ? tb.D[0][q] * v[0] : gy[q] + tb.D[i][q] * v[i];
-        // flux = G grad
-        BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          {
-            const double a = gx[q], b = gy[q], e = gz[q];
-            gx[q] = g00[q] * a + g01[q] * b + g02[q] * e;
-            gy[q] = g01[q] * a + g11[q] * b + g12[q] * e;
-            gz[q] = g02[q] * a + g12[q] * b + g22[q] * e;
-          }
-        // d/deta^T on the eta-flux -> value-like line
-        BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          BP4_UNROLL
-        for (int i = 0; i < Q; ++i)
-          v[i] = q == 0 ? tb.D[i][0] * gy[0] : v[i] + tb.D[i][q] * gy[q];
-        // y-back-interpolation of the three lines
-        BP4_UNROLL
-        for (int j = 0; j < N; ++j)
-          {
-            double o0, o1, o2;
-            BP4_UNROLL
-            for (int q = 0; q < Q; ++q)
-              {
-                const double sjq = tb.S[j][q];
-                o0 = q == 0 ? sjq * v[0] : o0 + sjq * v[q];
-                o1 = q == 0 ? sjq * gx[0] : o1 + sjq * gx[q];
-                o2 = q == 0 ? sjq * gz[0] : o2 + sjq * gz[q];
-              }
-            base[j * G::RW]             = o0;
-            base[j * G::RW + Q * Q]     = o1;
-            base[j * G::RW + 2 * Q * Q] = o2;
-          }
-#endif
       }
   }
 
@@ -992,7 +800,6 @@ namespace bp4
   template <int P, typename Out>
   BP4_HD void phase3_io(const Tab<P> &tb, const double *in, const Out out)
   {
-#if BP4_EO
     using G         = Geom<P>;
     constexpr int N = G::N, Q = G::Q, HN = N / 2, HQ = Q / 2;
     // X = (even part of S^T v) + (odd part of Dn^T fz), Y = (odd of S^T v) + (even of Dn^T fz):
@@ -1079,53 +886,6 @@ namespace bp4
               out((N - 1 - k) * N + i, o[i]);
           }
       }
-#else
-    using G         = Geom<P>;
-    constexpr int N = G::N, Q = G::Q;
-    double        t[N][Q];
-    BP4_UNROLL
-    for (int k = 0; k < N; ++k)
-      BP4_UNROLL
-    for (int q = 0; q < Q; ++q)
-      t[k][q] = 0.;
-    BP4_UNROLL
-    for (int qz = 0; qz < Q; ++qz)
-      {
-        double v[Q], fx[Q], fz[Q];
-        BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          {
-            v[q]  = in[0 * Q * Q + qz * Q + q];
-            fx[q] = in[1 * Q * Q + qz * Q + q];
-            fz[q] = in[2 * Q * Q + qz * Q + q];
-          }
-        BP4_UNROLL
-        for (int i = 0; i < Q; ++i)
-          {
-            double s = v[i];
-            BP4_UNROLL
-            for (int q = 0; q < Q; ++q)
-              s += tb.D[i][q] * fx[q];
-            v[i] = s;
-          }
-        BP4_UNROLL
-        for (int k = 0; k < N; ++k)
-          BP4_UNROLL
-        for (int q = 0; q < Q; ++q)
-          t[k][q] += tb.S[k][qz] * v[q] + tb.Dn[k][qz] * fz[q];
-      }
-    BP4_UNROLL
-    for (int k = 0; k < N; ++k)
-      BP4_UNROLL
-    for (int i = 0; i < N; ++i)
-      {
-        double s = tb.S[i][0] * t[k][0];
-        BP4_UNROLL
-        for (int q = 1; q < Q; ++q)
-          s += tb.S[i][q] * t[k][q];
-        out(k * N + i, s);
-      }
-#endif
   }
 
   template <int P>

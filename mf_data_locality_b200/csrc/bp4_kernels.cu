@@ -31,7 +31,6 @@ namespace bp4
   // cell kernels
   // ---------------------------------------------------------------------------------------
   constexpr int kGatherUnroll = 4;
-  constexpr int kPlainUnroll  = 9;
 
   template <int P, int CPB>
   __device__ __forceinline__ void load_tables(CellSmem<P, CPB> &sm, const uint32_t *dtab)
