@@ -3,6 +3,8 @@
 // check the shared-memory indexing and the contraction algebra of the device code against
 // the oracle without a GPU.  Never linked into the product library.
 #include <cstdint>
+#include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <array>
 #include <vector>
@@ -155,4 +157,96 @@ extern "C" void emu_tables(int p, double *S, double *Dn, double *D, double *xq, 
 #define T(PP) case PP: { bp4::Tab<PP> tb; bp4::fill_tab<PP>(tb); memcpy(S, tb.S, sizeof(tb.S)); memcpy(Dn, tb.Dn, sizeof(tb.Dn)); memcpy(D, tb.D, sizeof(tb.D)); memcpy(xq, tb.xq, sizeof(tb.xq)); memcpy(wq, tb.wq, sizeof(tb.wq)); } break;
   switch (p) { T(2) T(3) T(4) T(5) T(6) T(7) T(8) }
 #undef T
+}
+
+// even-odd 1-D contractions against the dense sums, for every matrix and both directions:
+// returns the largest |eo - dense| over random inputs (scaled by the largest |dense| entry)
+template <int P>
+static double eo_check()
+{
+  constexpr int N = P + 1, Q = P + 2;
+  bp4::Tab<P>   tb;
+  bp4::fill_tab<P>(tb);
+  double   worst = 0., scale = 1e-300;
+  uint64_t st    = 0x9E3779B97F4A7C15ull + P;
+  auto     rnd   = [&]() {
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    return double(int64_t(st >> 11)) / double(1ll << 52) - 1.0;
+  };
+  auto cmp = [&](const double got, const double want) {
+    worst = std::max(worst, std::fabs(got - want));
+    scale = std::max(scale, std::fabs(want));
+  };
+  for (int rep = 0; rep < 8; ++rep)
+    {
+      double xn[N], xq[Q], o_q[Q], o_n[N], o_qq[Q];
+      for (double &v : xn)
+        v = rnd();
+      for (double &v : xq)
+        v = rnd();
+      bp4::eo_first<N, Q, 1>(tb.Sfp, tb.Sfm, tb.S, xn, o_q);
+      for (int q = 0; q < Q; ++q)
+        {
+          double s = 0;
+          for (int i = 0; i < N; ++i)
+            s += tb.S[i][q] * xn[i];
+          cmp(o_q[q], s);
+        }
+      bp4::eo_first<N, Q, -1>(tb.Dnfp, tb.Dnfm, tb.Dn, xn, o_q);
+      for (int q = 0; q < Q; ++q)
+        {
+          double s = 0;
+          for (int i = 0; i < N; ++i)
+            s += tb.Dn[i][q] * xn[i];
+          cmp(o_q[q], s);
+        }
+      bp4::eo_first<Q, Q, -1>(tb.Dfp, tb.Dfm, tb.D, xq, o_qq);
+      for (int q = 0; q < Q; ++q)
+        {
+          double s = 0;
+          for (int i = 0; i < Q; ++i)
+            s += tb.D[i][q] * xq[i];
+          cmp(o_qq[q], s);
+        }
+      bp4::eo_second<N, Q, 1>(tb.Ssp, tb.Ssm, tb.S, xq, o_n);
+      for (int i = 0; i < N; ++i)
+        {
+          double s = 0;
+          for (int q = 0; q < Q; ++q)
+            s += tb.S[i][q] * xq[q];
+          cmp(o_n[i], s);
+        }
+      bp4::eo_second<N, Q, -1>(tb.Dnsp, tb.Dnsm, tb.Dn, xq, o_n);
+      for (int i = 0; i < N; ++i)
+        {
+          double s = 0;
+          for (int q = 0; q < Q; ++q)
+            s += tb.Dn[i][q] * xq[q];
+          cmp(o_n[i], s);
+        }
+      bp4::eo_second<Q, Q, -1>(tb.Dsp, tb.Dsm, tb.D, xq, o_qq);
+      for (int i = 0; i < Q; ++i)
+        {
+          double s = 0;
+          for (int q = 0; q < Q; ++q)
+            s += tb.D[i][q] * xq[q];
+          cmp(o_qq[i], s);
+        }
+    }
+  return worst / scale;
+}
+
+extern "C" double emu_eo_check(int p)
+{
+  switch (p)
+    {
+      case 2: return eo_check<2>();
+      case 3: return eo_check<3>();
+      case 4: return eo_check<4>();
+      case 5: return eo_check<5>();
+      case 6: return eo_check<6>();
+      case 7: return eo_check<7>();
+      case 8: return eo_check<8>();
+    }
+  return 1e300;
 }

@@ -47,3 +47,11 @@ def test_device_phases_match_oracle(emu, p, s):
     got2 = np.zeros(rd.n_owned)
     assert emu.emu_vmult_cells_fine(p, C.c_long(rd.n_cells), _p(e), _p(vt), _p(v), _p(got2)) == 0
     assert rel_l2(got2, want) <= 1e-13
+
+
+@pytest.mark.parametrize("p", [2, 3, 4, 5, 6, 7, 8])
+def test_even_odd_contractions_match_dense_sums(emu, p):
+    """eo_first / eo_second (bp4_cell.cuh) against the plain sums for S, Dn, D, both directions:
+    exercises the odd/even node counts, the middle row/column cases and both symmetry signs."""
+    emu.emu_eo_check.restype = C.c_double
+    assert emu.emu_eo_check(p) <= 2e-14
