@@ -10,8 +10,8 @@
 #ifndef BP4_P2_CALL_FROM
 #  define BP4_P2_CALL_FROM 6 // degrees >= this call phase 2 out of line
 #endif
-#ifndef BP4_GU
-#  define BP4_GU 32 // gather slots in flight per group (>= slots per batch: one latency)
+#ifndef BP4_PIPE_GATHER
+#  define BP4_PIPE_GATHER(P) ((P) == 4)
 #endif
 #ifndef BP4_SU
 #  define BP4_SU 6 // scatter unroll
@@ -163,50 +163,60 @@ namespace bp4
       }
     __syncthreads();
 
+    // gather (vector_access_reduced.h:175-258): consecutive threads walk an entity's contiguous
+    // DoF segment.  Thread tid owns elements tid + r * kThreads of EVERY cell of the batch, so the
+    // table entry is decoded once per r and the (cell, r) slots unroll with compile-time cell
+    // offsets: ~7 instructions per element, all loads of the batch in flight together.  Cells
+    // missing from a ragged last batch carry invalid entity indices (fetch_meta) and gather zeros.
+    // With kPipe the gather is software-pipelined: the loads of batch i+1 are issued
+    // (gather_issue) before the scatter of batch i and land in registers while the scatter runs;
+    // they are stored to the work rows (gather_store) once the scatter has released them.
+    // Measured: Q4 +3 %, Q5 -2 %, Q8 -4 % (the extra live registers spill there) -> Q4 only.
+    constexpr bool kPipe = BP4_PIPE_GATHER(P);
+    constexpr int R = (G::DOF + kThreads - 1) / kThreads, S = CPB * R;
+    // only the last r can run past the end of the cell
+    const bool last_on = tid < G::DOF - (R - 1) * kThreads;
+    auto       on      = [&](const int r) { return r < R - 1 || last_on; };
+    double     gv[S];
+    auto       gather_issue = [&](const int bf) {
+      uint32_t tt[R], idx[S];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
+#pragma unroll
+      for (int s1 = 0; s1 < S; ++s1)
+        {
+          const int      cell = s1 / R, r = s1 % R;
+          const uint32_t base = sm.eidx[bf][cell][dtab_ent(tt[r])];
+          idx[s1] = on(r) && base != 0xFFFFFFFFu ? base + dtab_rel(tt[r]) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+      for (int s1 = 0; s1 < S; ++s1)
+        gv[s1] = idx[s1] != 0xFFFFFFFFu ? __ldg(a.src + idx[s1]) : 0.;
+    };
+    auto gather_store = [&]() {
+      uint32_t tt[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
+#pragma unroll
+      for (int s1 = 0; s1 < S; ++s1)
+        {
+          const int cell = s1 / R, r = s1 % R;
+          if (on(r))
+            sm.work[cell * G::WORK + dtab_off_work<P>(tt[r])] = gv[s1];
+        }
+    };
+
     for (int i = 0; i < my_n; ++i)
       {
         uint64_t  cell0;
         const int nc = batch_cells(i, cell0), bf = i & 1;
         BP4_TICK(0)
-        // gather (vector_access_reduced.h:175-258): consecutive threads walk an entity's
-        // contiguous DoF segment.  Thread tid owns elements tid + r * kThreads of EVERY cell of
-        // the batch, so the table entry is decoded once per r and the (cell, r) slots unroll with
-        // compile-time cell offsets: ~7 instructions per element, all loads of a group of GU
-        // slots in flight together.  Cells missing from a ragged last batch carry invalid entity
-        // indices (fetch_meta) and gather zeros.
-        constexpr int GU = BP4_GU, R = (G::DOF + kThreads - 1) / kThreads, S = CPB * R;
-        // only the last r can run past the end of the cell
-        const bool last_on = tid < G::DOF - (R - 1) * kThreads;
-        auto       on      = [&](const int r) { return r < R - 1 || last_on; };
-        uint32_t   tt[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
-#pragma unroll
-        for (int s0 = 0; s0 < S; s0 += GU)
+        if (!kPipe || i == 0)
           {
-            double   v[GU];
-            uint32_t idx[GU];
-#pragma unroll
-            for (int u = 0; u < GU; ++u)
-              if (s0 + u < S)
-                {
-                  const int      cell = (s0 + u) / R, r = (s0 + u) % R;
-                  const uint32_t base = sm.eidx[bf][cell][dtab_ent(tt[r])];
-                  idx[u] = on(r) && base != 0xFFFFFFFFu ? base + dtab_rel(tt[r]) : 0xFFFFFFFFu;
-                }
-#pragma unroll
-            for (int u = 0; u < GU; ++u)
-              if (s0 + u < S)
-                v[u] = idx[u] != 0xFFFFFFFFu ? __ldg(a.src + idx[u]) : 0.;
-#pragma unroll
-            for (int u = 0; u < GU; ++u)
-              if (s0 + u < S)
-                {
-                  const int cell = (s0 + u) / R, r = (s0 + u) % R;
-                  if (on(r))
-                    sm.work[cell * G::WORK + dtab_off_work<P>(tt[r])] = v[u];
-                }
+            gather_issue(bf);
+            gather_store();
           }
         BP4_TICK(1)
         __syncthreads();
@@ -277,9 +287,12 @@ namespace bp4
         BP4_TICK(2)
         // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13) is
         // touched by this cell only -> plain store
+        if (kPipe && i + 1 < my_n)
+          gather_issue(bf ^ 1); // in flight during the scatter
         constexpr int SU = BP4_SU;
+        uint32_t      tt[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) // read again: nothing is kept in registers across phase 2
+        for (int r = 0; r < R; ++r)
           tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
 #pragma unroll
         for (int s0 = 0; s0 < S; s0 += SU)
@@ -308,6 +321,8 @@ namespace bp4
         BP4_TICK(6)
         __syncthreads();
         BP4_TICK(2)
+        if (kPipe && i + 1 < my_n)
+          gather_store(); // the barrier after it is the one at the top of the next iteration
       }
     BP4_TICK_FLUSH
   }
