@@ -11,7 +11,7 @@
 #  define BP4_P2_CALL_FROM 6 // degrees >= this call phase 2 out of line
 #endif
 #ifndef BP4_PIPE_GATHER
-#  define BP4_PIPE_GATHER(P) ((P) == 4)
+#  define BP4_PIPE_GATHER(P) ((P) <= 4)
 #endif
 #ifndef BP4_SU
 #  define BP4_SU 6 // scatter unroll
@@ -171,7 +171,7 @@ namespace bp4
     // With kPipe the gather is software-pipelined: the loads of batch i+1 are issued
     // (gather_issue) before the scatter of batch i and land in registers while the scatter runs;
     // they are stored to the work rows (gather_store) once the scatter has released them.
-    // Measured: Q4 +3 %, Q5 -2 %, Q8 -4 % (the extra live registers spill there) -> Q4 only.
+    // Measured: Q2 +4 %, Q3 +1 %, Q4 +3 %, Q5 -2 %, Q8 -4 % (the extra live registers spill there).
     constexpr bool kPipe = BP4_PIPE_GATHER(P);
     constexpr int R = (G::DOF + kThreads - 1) / kThreads, S = CPB * R;
     // only the last r can run past the end of the cell
