@@ -43,3 +43,26 @@ def test_run_cg_solver_plugin(plugin, p, s, rel_tol, bp4_lib, c_oracle_lib):
     assert it2 == it and rel_l2(x2, x) <= 1e-9
     prob.set_solver()
     prob.close()
+
+
+def test_cli_verbose_output(bp4_lib):
+    """`bench <degree> <s> 0`: the non-compact prints of run_templated (benchmark.h:149-154,
+    178-182) -- the preconditioner's diagonal norm (checked against the oracle) and the setup time;
+    `bench <degree> <s>`: the one-line table row (benchmark.h:217-225)."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "mf_data_locality_b200", "benchmark_precond_merged", "bench")
+    out = subprocess.run([exe, "3", "9", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"Norm of diagonal for preconditioner: ([0-9.eE+-]+)", out.stdout)
+    assert m and "Setup time:" in out.stdout
+    rd, _ = single(3, 9)
+    want = np.linalg.norm(O.finish_inverse_diagonal(O.inverse_diagonal(rd)))
+    assert abs(float(m.group(1)) - want) <= 1e-5 * want  # printed with six significant digits
+    row = subprocess.run([exe, "3", "9"], capture_output=True, text=True, timeout=300)
+    assert row.returncode == 0, row.stderr
+    cols = [c.strip() for c in row.stdout.strip().splitlines()[-1].split("|")]
+    assert cols[0] == "3" and cols[1] == "5" and int(cols[2]) == rd.n_cells and int(cols[3]) == rd.n_owned
+    assert 1 <= int(cols[6]) <= 100
