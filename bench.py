@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--degree", type=int, default=4)
     ap.add_argument("--s", type=int, default=18)
-    ap.add_argument("--cpu-s", type=int, default=15, help="mesh size of the bounded CPU sample")
+    ap.add_argument("--cpu-s", type=int, default=17, help="mesh size of the bounded CPU sample")
     ap.add_argument("--solver", default="merged", choices=["merged", "plain"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
