@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""bench.py -- BP4 merged-CG throughput of the B200-native hot path (BASELINE.json metric).
+"""bench.py -- BP4 CG throughput of the B200-native hot path (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--degree P] [--s S] [--solver merged|plain]
+                  [--mode weak|strong] [--sweep none|default|full]
   python bench.py --impl reference ...      # the reference algorithm's CPU restatement on host cores
 
 A "step" is one call of the reference's `run_cg_solver` plugin (benchmark.h:193: x0 = 0,
@@ -10,10 +11,16 @@ reference's own `dofs/s/it` column (benchmark.h:222): n_dofs * n_iterations / so
 
   value     device-timed (CUDA events on the solver's stream), right-hand side resident in HBM
   e2e       same call with HOST buffers: b uploaded and x downloaded inside the timed region
-  roofline  merged cell kernel: algorithmic bytes (58.67 B/DoF + 300 B/cell) over the
-            CUDA-event duration of its launches in the timed region, vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (C/OpenMP restatement of the reference algorithm, kind "port":
-            the real reference needs deal.II + p4est + MPI, absent here) on a bounded sample
+  roofline  dominant kernel (the cell kernel): algorithmic bytes (16 B/DoF + 300 B/cell
+            for the operator, + 42.67 B per DoF whose vector updates run inside the loop) over the
+            CUDA-event duration of its launches in the timed region, vs MEASURED_PEAKS.json;
+            roofline.iteration = the whole merged iteration (58.67 B/DoF + 300 B/cell) over the
+            device time of one iteration
+  cpu_baseline  the CPU oracle (C/OpenMP restatement of the reference algorithm, kind "port": the
+            real reference needs deal.II + p4est + MPI, absent here) on a bounded sample
+  sweep     (N = 1) the other BASELINE.json configs, one timed solve each: Q3 s=15 plain, Q6 s=18
+            merged, Q2..Q8 at ~100 M DoFs (merged; plain too with --sweep full)
+Multi-GPU: --mode weak (default) runs s + log2(N) (fixed DoFs per GPU); --mode strong keeps s.
 One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
@@ -32,6 +39,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "BP4 CG GDoF/s (DoFs x iterations / s)"
 UNIT = "GDoF/s"
+# BASELINE.json configs[3]: Q2..Q8 at ~100 M DoFs
+DEGREE_SWEEP = [(2, 22), (3, 20), (4, 19), (5, 18), (6, 17), (7, 16), (8, 16)]
 
 
 def n_dofs_of(p, s):
@@ -46,12 +55,35 @@ def algorithmic_bytes_per_iteration(p, s, merged=True):
     return (58.0 + 2.0 / 3.0 if merged else 138.0 + 2.0 / 3.0) * nd + 300.0 * nc
 
 
+def cell_kernel_bytes(n_dofs, n_cells, n_private):
+    """operator apply 16 B/DoF + 300 B/cell; the in-loop do_cg_update4b/3b add the remaining
+    58.67 - 16 B/DoF of the merged iteration on the DoFs they cover"""
+    return 16.0 * n_dofs + 300.0 * n_cells + (58.0 + 2.0 / 3.0 - 16.0) * n_private
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_cores():
+    """physical cores this process may run on (SMT siblings counted once); torchrun's
+    OMP_NUM_THREADS=1 is deliberately ignored: the CPU arm uses the whole host"""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+    seen = set()
+    for c in cpus:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                seen.add(f.read().strip())
+        except OSError:
+            seen.add(str(c))
+    return max(1, len(seen))
 
 
 class ClockSampler:
@@ -91,44 +123,61 @@ class ClockSampler:
                 "samples": len(sm), "reasons": reasons}
 
 
-def cpu_oracle_run(p, s, merged, steps, warmup, max_its=100):
-    """time the CPU oracle's CG (C/OpenMP restatement of the reference algorithm) on host cores"""
-    from oracle import bp4_oracle as O
-    from oracle import c_oracle
-    c_oracle.build()
-    rd = O.build_problem(p, s)[0]
-    co = c_oracle.COracle(rd)
-    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
-    for _ in range(warmup):
-        co.cg(rd.rhs, prec, merged, max_steps=min(max_its, 5))
-    t0 = time.perf_counter()
-    its = 0
-    for _ in range(steps):
-        _, it, _ = co.cg(rd.rhs, prec, merged, max_steps=max_its)
-        its += it
-    dt = time.perf_counter() - t0
-    nd, _ = n_dofs_of(p, s)
-    return nd * its / dt * 1e-9, dt / steps, c_oracle.lib().oracle_num_threads(), its // steps
+class CpuArm:
+    """the CPU oracle's CG (C/OpenMP restatement of the reference algorithm: even-odd, z-layer-wise
+    cell kernel; merged variant with the vector updates per cell-batch range inside the loop,
+    one chunk of ranges per thread) on this box's host cores"""
+
+    def __init__(self, p, s, merged):
+        from oracle import bp4_oracle as O
+        from oracle import c_oracle
+        c_oracle.build()
+        self.lib = c_oracle.lib()
+        self.cores = host_cores()
+        self.lib.oracle_set_num_threads(self.cores)
+        self.lib.oracle_set_fast(1)
+        self.p, self.s, self.merged = p, s, merged
+        self.rd = O.build_problem(p, s)[0]
+        self.co = c_oracle.COracle(self.rd)
+        self.prec = O.finish_inverse_diagonal(O.inverse_diagonal(self.rd))
+        self.threads = self.lib.oracle_num_threads()
+
+    def step(self, max_its):
+        t0 = time.perf_counter()
+        _, it, _ = self.co.cg(self.rd.rhs, self.prec, self.merged, max_steps=max_its, blocked=self.merged)
+        return it, time.perf_counter() - t0
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the real reference cannot be
-    built here) on this box's host cores, same metric/config, bounded sample."""
+    built here) on this box's host cores: same metric, degree, mesh and solver; every step is a
+    bounded sample (--cpu-iters CG iterations of the same problem instead of 100)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    p = args.degree
-    s = min(args.s, args.cpu_s)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    s_gpu = args.s + (max(0, world.bit_length() - 1) if args.mode == "weak" else 0)
+    s = min(s_gpu, args.cpu_s)          # the numpy set-up of the oracle needs ~0.2 kB per DoF
     merged = args.solver == "merged"
-    val, sec, cores, its = cpu_oracle_run(p, s, merged, max(1, min(args.steps, 2)), min(args.warmup, 1))
-    nd, nc = n_dofs_of(p, s)
-    sample = f"degree {p}, s={s} ({nc} cells, {nd} DoFs) instead of s={args.s}; {its} CG iterations per step"
+    arm = CpuArm(args.degree, s, merged)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    for _ in range(warmup):
+        arm.step(min(args.cpu_iters, 3))
+    its, sec = 0, 0.0
+    for _ in range(steps):
+        it, dt = arm.step(args.cpu_iters)
+        its += it
+        sec += dt
+    nd, nc = n_dofs_of(args.degree, s)
+    val = nd * its / sec * 1e-9
+    sample = (f"degree {args.degree}, s={s} ({nc} cells, {nd} DoFs)"
+              + (f" instead of s={s_gpu}" if s != s_gpu else "")
+              + f"; {its // steps} CG iterations per step instead of 100; {arm.threads} OpenMP threads")
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-           "steps": max(1, min(args.steps, 2)), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic",
-           "config": workload_config(args, 1),
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "steps": steps, "warmup": warmup, "ms_per_step": sec / steps * 1e3,
+           "higher_is_better": True, "scaling": args.mode, "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": workload_config(args, 1, s),
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": arm.threads, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -142,9 +191,50 @@ def workload_config(args, n_gpus, s_run=None):
                         f"Jacobi, RHS i%8), Renumber(0,1,2)",
             "degree": args.degree, "s": s_run, "n_dofs": nd, "n_dofs_per_gpu": nd // n_gpus, "solver": args.solver,
             "parallelism": "single GPU" if n_gpus == 1 else
-            f"domain decomposition over {n_gpus} GPUs (contiguous chunks of the cell order), NCCL ghost "
-            f"exchange + 7-double all-reduce per iteration; weak scaling s = {args.s} + log2(N)",
+            f"domain decomposition over {n_gpus} GPUs (contiguous chunks of the cell order), ghost "
+            f"exchange + 7-double all-reduce per iteration; {args.mode} scaling"
+            + (f" s = {args.s} + log2(N)" if args.mode == "weak" else f" at fixed s = {args.s}"),
             "l2": "vectors (%.0f MB per GPU each) exceed the 126 MB L2; no flush needed" % (nd * 8 / 1e6 / n_gpus)}
+
+
+def timed_solves(prob, stream, steps, barrier):
+    """device time of `steps` plugin calls with the right-hand side resident in HBM"""
+    import torch
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    iters = 0
+    for _ in range(steps):
+        _, it = prob.run_cg_solver(None, want_x=False)
+        iters += it
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1), iters
+
+
+def sweep_entry(name, p, s, solver, peak, local_rank):
+    """one timed solve (after one warm-up solve) of another BASELINE config on this GPU"""
+    import ctypes as C
+    import torch
+    from mf_data_locality_b200 import capi, host
+    t0 = time.perf_counter()
+    prob = host.Problem(p, s, plugin=solver, device=local_rank)
+    setup = time.perf_counter() - t0
+    ctx = C.c_void_p(prob.ctx_handle())
+    sp = C.c_void_p()
+    capi.lib().bp4_ctx_stream(ctx, C.byref(sp))
+    stream = torch.cuda.ExternalStream(sp.value or 0, device=local_rank)
+    prob.run_cg_solver(None, want_x=False)
+    ms, iters = timed_solves(prob, stream, 1, torch.cuda.synchronize)
+    nd, nc = prob.n_dofs, prob.n_cells_global
+    byts = algorithmic_bytes_per_iteration(p, s, solver == "merged")
+    it_ms = ms / max(iters, 1)
+    out = {"config": name, "degree": p, "s": s, "solver": solver, "n_dofs": nd, "iterations": iters,
+           "value": nd * iters / (ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_iteration": it_ms,
+           "iteration_roofline_frac": byts / (it_ms * 1e-3) * 1e-9 / peak, "setup_seconds": setup,
+           "steps": 1, "warmup": 1}
+    prob.close()
+    return out
 
 
 def main():
@@ -155,8 +245,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--degree", type=int, default=4)
     ap.add_argument("--s", type=int, default=18)
-    ap.add_argument("--cpu-s", type=int, default=17, help="mesh size of the bounded CPU sample")
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong"],
+                    help="weak: s + log2(N) on N GPUs (fixed DoFs per GPU); strong: s on any N")
+    ap.add_argument("--cpu-s", type=int, default=18, help="largest mesh of the CPU sample")
+    ap.add_argument("--cpu-iters", type=int, default=10, help="CG iterations per CPU step (bounded sample)")
     ap.add_argument("--solver", default="merged", choices=["merged", "plain"])
+    ap.add_argument("--sweep", default="default", choices=["none", "default", "full"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -183,7 +277,7 @@ def main():
 
     # weak scaling: the mesh grows with the GPU count (s + log2 N: twice the cells per doubling,
     # SURVEY 8d config 5), partitioned along the renumbered cell order, one partition per GPU
-    s_run = args.s + max(0, world.bit_length() - 1)
+    s_run = args.s + (max(0, world.bit_length() - 1) if args.mode == "weak" else 0)
     nccl_id = None
     if world > 1:
         idt = torch.tensor(list(capi.unique_id() if rank == 0 else bytes(128)), dtype=torch.uint8, device="cuda")
@@ -197,7 +291,10 @@ def main():
     L.bp4_ctx_stream(ctx, C.byref(stream_ptr))
     stream = torch.cuda.ExternalStream(stream_ptr.value or 0, device=local_rank)
     n_dofs = prob.n_dofs
-    kernel_id = capi.K_MERGED if args.solver == "merged" else capi.K_VMULT
+    fused_flag, n_priv, n_units = C.c_int(), C.c_uint64(), C.c_uint64()
+    L.bp4_fused_info(ctx, C.byref(fused_flag), C.byref(n_priv), C.byref(n_units))
+    merged = args.solver == "merged"
+    fused = merged and bool(fused_flag.value)
 
     def barrier():
         if world > 1:
@@ -211,31 +308,22 @@ def main():
     L.bp4_profile_enable(ctx, 1)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    iters = 0
-    for _ in range(args.steps):
-        _, it = prob.run_cg_solver(None, want_x=False)
-        iters += it
-    e1.record(stream)
-    barrier()
+    ms_local, iters = timed_solves(prob, stream, args.steps, barrier)
     clocks = sampler.stop()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    ms = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    kms, kcnt = C.c_double(), C.c_uint64()
-    L.bp4_profile_get(ctx, kernel_id, C.byref(kms), C.byref(kcnt))
-    kernel_name = "cell_kernel_merged (fused pre + cells + post)" if kernel_id == capi.K_MERGED else "cell_kernel_plain"
-    if kcnt.value == 0:   # merged solver running its three-kernel variant: the cell kernel dominates
-        kernel_id, kernel_name = capi.K_VMULT, "cell_kernel_plain (merged CG = pre + cell + post kernels)"
-        L.bp4_profile_get(ctx, kernel_id, C.byref(kms), C.byref(kcnt))
     parts = {}
-    for nm, kid in (("cells", capi.K_VMULT), ("merged", capi.K_MERGED), ("pre", capi.K_PRE), ("post", capi.K_POST), ("blas1", capi.K_BLAS1)):
+    for nm, kid in (("cells", capi.K_VMULT), ("cells_with_updates", capi.K_MERGED), ("pre", capi.K_PRE),
+                    ("post", capi.K_POST), ("blas1", capi.K_BLAS1)):
         a_, b_ = C.c_double(), C.c_uint64()
         L.bp4_profile_get(ctx, kid, C.byref(a_), C.byref(b_))
         parts[nm] = {"ms_total": a_.value, "launches": int(b_.value)}
+    kkey = "cells_with_updates" if fused else "cells"
+    kms, kcnt = parts[kkey]["ms_total"], parts[kkey]["launches"]
+    kernel_name = ("cell_kernel<P,CPB,true> (operator + in-loop do_cg_update4b/3b on range-private DoFs)" if fused
+                   else "cell_kernel<P,CPB,false> (operator apply)")
     launches = C.c_uint64()
     L.bp4_launch_count(ctx, C.byref(launches))
     L.bp4_profile_enable(ctx, 0)
@@ -265,61 +353,80 @@ def main():
         return
 
     peak, peak_src = measured_peak()
-    merged = args.solver == "merged"
-    # per launch = per GPU: this rank's share of the DoFs and cells
-    share = prob.n_owned / n_dofs
-    fused = kernel_id == capi.K_MERGED
-    alg_bytes = (algorithmic_bytes_per_iteration(args.degree, s_run, True) if fused else
-                 16.0 * n_dofs + 300.0 * (1 << s_run)) * share
+    # per launch = per GPU: this rank's DoFs and cells
+    alg_bytes = cell_kernel_bytes(prob.n_owned, prob.n_cells, int(n_priv.value) if fused else 0)
     # whole CG iteration against the same roof: SURVEY 8(d) bytes per iteration over the
     # device time of one iteration (all kernels, exchanges and the host round trip for the sums)
-    it_bytes = algorithmic_bytes_per_iteration(args.degree, s_run, merged) * share
+    it_bytes = algorithmic_bytes_per_iteration(args.degree, s_run, merged) * prob.n_owned / n_dofs
     it_ms = total_ms / max(iters, 1)
-    avg_ms = kms.value / max(kcnt.value, 1)
+    # with the overlapped exchange a loop is three launches (cell partitions): per-loop time
+    loops = max(iters, 1) * args.steps // args.steps if merged else max(kcnt, 1)
+    avg_ms = kms / max(iters if merged else kcnt, 1)
     achieved = alg_bytes / (avg_ms * 1e-3) * 1e-9 if avg_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    traffic, fp64 = None, None
+    tpath = os.path.join(ROOT, "profiles", "kernel_counters.json")
+    if os.path.exists(tpath):          # ncu captures of the committed kernels (scripts/ncu_counters.py)
         with open(tpath) as f:
-            traffic = json.load(f).get(f"{args.solver}_q{args.degree}_s{args.s}")
+            kc = json.load(f).get(f"q{args.degree}_{'fused' if fused else 'plain'}")
+        if kc:
+            traffic = kc.get("dram_bytes_per_dof", 0) * prob.n_owned or None
+            ipd = kc.get("fp64_lane_instr_per_dof")
+            if ipd and avg_ms > 0:
+                pk = 148 * 64 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6
+                fp64 = {"instr_per_dof": ipd, "source": kc.get("source"), "peak_lane_instr_per_s": pk,
+                        "frac": ipd * prob.n_owned / (avg_ms * 1e-3) / pk}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel": kernel_name, "kernels_in_timed_region": parts,
-                "kernel_ms_avg": avg_ms, "kernel_launches": int(kcnt.value),
-                "kernel_share_of_step": kms.value / total_ms if total_ms else None,
+                "kernel_ms_avg": avg_ms, "kernel_launches": int(kcnt),
+                "kernel_share_of_step": kms / total_ms if total_ms else None,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                # second roof: the cell kernel is FP64-pipe bound.  336 FP64
-                # warp-lane instructions per DoF were counted by ncu at Q4 (533.9 M FP64 warp instructions per apply,
-                # profiles/r01_final3_cell_kernel_q4_s18.txt + its source page); the peak is
-                # 148 SMs x 64 lanes x sm_max_mhz
-                "fp64_pipe": ({"instr_per_dof": 336, "peak_lane_instr_per_s": 148 * 64 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6,
-                               "frac": 336.0 * prob.n_owned / (avg_ms * 1e-3) /
-                                       (148 * 64 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6)}
-                              if args.degree == 4 and avg_ms > 0 and not fused else None),
+                "fused": fused, "dofs_updated_in_loop": int(n_priv.value) if fused else 0,
+                # second roof: the cell kernel is FP64-pipe bound
+                "fp64_pipe": fp64,
                 "iteration": {"algorithmic_bytes": it_bytes, "ms": it_ms,
                               "achieved": it_bytes / (it_ms * 1e-3) * 1e-9,
                               "frac": it_bytes / (it_ms * 1e-3) * 1e-9 / peak}}
+
+    setup_seconds = prob.setup_seconds
+    sweep = None
+    if world == 1 and args.sweep != "none":
+        prob.close()                     # free HBM before the larger configs
+        torch.cuda.empty_cache()
+        todo = [("configs[0] Q3 s=15 plain CG", 3, 15, "plain"), ("configs[2] Q6 s=18 merged CG", 6, 18, "merged")]
+        todo += [(f"configs[3] Q{p} s={s} merged CG", p, s, "merged") for p, s in DEGREE_SWEEP]
+        if args.sweep == "full":
+            todo += [(f"configs[3] Q{p} s={s} plain CG", p, s, "plain") for p, s in DEGREE_SWEEP]
+        sweep = []
+        for name, p, s, solver in todo:
+            try:
+                sweep.append(sweep_entry(name, p, s, solver, peak, local_rank))
+            except Exception as e:       # the sweep is reported, never required
+                sweep.append({"config": name, "error": str(e)})
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
             s_cpu = min(args.s, args.cpu_s)
-            val, sec, cores, its = cpu_oracle_run(args.degree, s_cpu, merged, 1, 1)
+            arm = CpuArm(args.degree, s_cpu, merged)
+            arm.step(2)
+            its, sec = arm.step(args.cpu_iters)
             nd_c, nc_c = n_dofs_of(args.degree, s_cpu)
-            cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"CPU oracle (C/OpenMP restatement of the reference algorithm), degree {args.degree}, "
-                             f"s={s_cpu} ({nc_c} cells, {nd_c} DoFs), 1 solve of {its} iterations, {sec:.1f} s"}
+            cpu = {"value": nd_c * its / sec * 1e-9, "unit": UNIT, "cores": arm.threads, "kind": "port",
+                   "sample": f"CPU oracle (C/OpenMP restatement of the reference algorithm: even-odd, layer-wise "
+                             f"cells; vector updates per cell-batch range inside the loop), degree {args.degree}, "
+                             f"s={s_cpu} ({nc_c} cells, {nd_c} DoFs), {its} CG iterations instead of 100, {sec:.1f} s"}
         except Exception as e:  # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "scaling": args.mode, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": workload_config(args, world, s_run), "iterations_per_step": iters // args.steps,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(prob.n_owned * 8),
                    "d2h_bytes_per_step": int(prob.n_owned * 8)},
            "gpu_launches": int(launches.value), "clocks": clocks, "roofline": roofline,
-           "cpu_baseline": cpu, "setup_seconds": prob.setup_seconds}
+           "cpu_baseline": cpu, "setup_seconds": setup_seconds, "sweep": sweep}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -78,6 +78,19 @@ typedef struct bp4_desc
    * ghost values / ghost contributions is overlapped with them.  0/0 = no overlap.           */
   uint64_t n_cells_before_comm;
   uint64_t n_cells_comm;
+  /* cell-batch ranges of the loop (MatrixFree task_info.cell_partition_data, as walked by
+   * renumber_dofs_for_mf.h:622-671) and the owned DoFs PRIVATE to each of them: touched by the
+   * cells of exactly one range, unconstrained, not shared with another rank.  These are the
+   * DoF ranges on which MatrixFree::cell_loop runs the pre/post hooks of
+   * vmult_with_merged_sums right around the range's own cells (poisson_operator.h:339-364).
+   * Renumber(0,1,2) numbers them first and range by range (renumber_dofs_for_mf.h:556-590), so
+   * range r owns the contiguous run [range_private_offset[r], range_private_offset[r+1]).
+   * range_cell_offset[r] = first cell of range r, [0] = 0, [n_ranges] = n_cells; ranges do not
+   * straddle the cell partitions above.  n_ranges = 0 (or an all-zero private table): the
+   * vector updates are streamed over the whole vector before/after the cell loop instead.    */
+  uint64_t        n_ranges;
+  const uint64_t *range_cell_offset;    /* [n_ranges + 1] */
+  const uint64_t *range_private_offset; /* [n_ranges + 1] local DoF indices, multiples of 3 */
 } bp4_desc;
 
 const char *bp4_last_error(void);
@@ -92,6 +105,8 @@ int bp4_ctx_stream(bp4_ctx *ctx, void **stream);
 
 /* ---- vectors: initialize_dof_vector (poisson_operator.h:298-302), reinit/operator= ------- */
 int bp4_vec_alloc(bp4_ctx *ctx, uint64_t n, bp4_vec **v); /* zero-initialised, n doubles */
+/* reinit(v, omit_zeroing_entries = true), solver_cg_optimized.h:215-217: contents undefined */
+int bp4_vec_alloc_uninitialized(bp4_ctx *ctx, uint64_t n, bp4_vec **v);
 int bp4_vec_free(bp4_ctx *ctx, bp4_vec *v);
 int bp4_vec_size(const bp4_vec *v, uint64_t *n);
 int bp4_vec_set_zero(bp4_ctx *ctx, bp4_vec *v);                            /* v = 0 */
@@ -104,13 +119,13 @@ int bp4_vec_device_ptr(bp4_ctx *ctx, bp4_vec *v, double **dev);            /* cu
 int bp4_vmult(bp4_ctx *ctx, bp4_vec *dst, const bp4_vec *src);
 /* LaplaceOperator::vmult_with_merged_sums (poisson_operator.h:327-377): pre-update of
  * x,g,d (do_cg_update4b, solver_cg_optimized.h:65), h = A d, the seven sums
- * (do_cg_update3b, :12), reduced over all ranks into out[7].  prec holds n_owned/3 entries. */
+ * (do_cg_update3b, :12), reduced over all ranks into out[7].  prec holds n_owned/3 entries.
+ * With range tables in the descriptor the two vector kernels run INSIDE the cell loop on the
+ * DoFs private to each cell-batch range (every vector is streamed once there) and as two
+ * streaming kernels on the remaining DoFs (shared between ranges or ranks, Dirichlet).       */
 int bp4_vmult_merged(bp4_ctx *ctx, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h,
                      const bp4_vec *prec, double alpha, double beta, double alpha_old,
                      double beta_old, double out[7]);
-/* which merged implementation bp4_vmult_merged runs: 0 = three kernels (pre, cells, post),
- * 1 = single fused kernel; default 0 until the fused kernel is the faster one.  Both give the same sums up to rounding.              */
-int bp4_set_merged_variant(bp4_ctx *ctx, int variant);
 /* 1/diag of the scalar GLL(p+1) Laplacian per node, 1 where 0:
  * LaplaceOperator::compute_inverse_diagonal + extraction (poisson_operator.h:392-426,
  * benchmark.h:141-147).  out holds n_owned/3 entries.                                       */
@@ -139,11 +154,16 @@ int bp4_comm_init(bp4_ctx *ctx, int rank, int n_ranks, const unsigned char id[BP
 int bp4_update_ghost_values(bp4_ctx *ctx, bp4_vec *v);   /* owners -> ghost copies            */
 int bp4_compress_add(bp4_ctx *ctx, bp4_vec *v);          /* ghost contributions -> owners, +=  */
 
-/* ---- measurement hooks (bench.py roofline / gpu_launches) ------------------------------- */
+/* ---- measurement / developer hooks (not part of the drop-in surface) ------------------- */
+/* fused = 1: do_cg_update4b/3b inside the cell kernel (default when the descriptor carried range
+ * tables with private DoFs; environment BP4_FUSED=0 turns it off at creation), 0: streamed
+ * over the whole vector by pre_kernel / post_kernel.  Same sums up to summation order.      */
+int bp4_debug_set_fused(bp4_ctx *ctx, int on);
+int bp4_fused_info(bp4_ctx *ctx, int *fused, uint64_t *n_private, uint64_t *n_units);
 typedef enum bp4_kernel_id
 {
-  BP4_K_VMULT  = 0, /* plain cell kernel   */
-  BP4_K_MERGED = 1, /* fused merged kernel */
+  BP4_K_VMULT  = 0, /* cell kernel, plain                                   */
+  BP4_K_MERGED = 1, /* cell kernel with the in-loop vector updates (fused) */
   BP4_K_PRE    = 2,
   BP4_K_POST   = 3,
   BP4_K_BLAS1  = 4,

@@ -29,7 +29,9 @@ class _Desc(C.Structure):
                 ("n_constrained", C.c_uint64), ("constrained", C.c_void_p),
                 ("n_peers", C.c_int), ("peer_rank", C.c_void_p), ("import_offset", C.c_void_p),
                 ("export_offset", C.c_void_p), ("export_index", C.c_void_p),
-                ("n_cells_before_comm", C.c_uint64), ("n_cells_comm", C.c_uint64)]
+                ("n_cells_before_comm", C.c_uint64), ("n_cells_comm", C.c_uint64),
+                ("n_ranges", C.c_uint64), ("range_cell_offset", C.c_void_p),
+                ("range_private_offset", C.c_void_p)]
 
 
 _lib = None
@@ -38,7 +40,7 @@ EXPORTS = [
     "bp4_last_error", "bp4_device_count", "bp4_ctx_create", "bp4_ctx_destroy", "bp4_ctx_synchronize",
     "bp4_ctx_stream", "bp4_vec_alloc", "bp4_vec_free", "bp4_vec_size", "bp4_vec_set_zero",
     "bp4_vec_upload", "bp4_vec_download", "bp4_vec_device_ptr", "bp4_vmult", "bp4_vmult_merged",
-    "bp4_set_merged_variant", "bp4_inverse_diagonal", "bp4_jacobi_vmult", "bp4_x_finalize_even",
+    "bp4_vec_alloc_uninitialized", "bp4_debug_set_fused", "bp4_fused_info", "bp4_inverse_diagonal", "bp4_jacobi_vmult", "bp4_x_finalize_even",
     "bp4_equ", "bp4_add", "bp4_sadd", "bp4_dot", "bp4_add_and_dot", "bp4_l2_norm", "bp4_all_zero",
     "bp4_comm_unique_id", "bp4_comm_init", "bp4_update_ghost_values", "bp4_compress_add",
     "bp4_profile_enable", "bp4_profile_reset", "bp4_profile_get", "bp4_launch_count",
@@ -122,7 +124,10 @@ class Context:
     (poisson_operator.h:101-293)."""
 
     def __init__(self, degree, entity_index, vertices, n_owned, n_ghost=0, constrained=None,
-                 device=0, peers=None):
+                 device=0, peers=None, ranges=None, partitions=None):
+        """ranges = (range_cell_offset, range_private_offset): cell-batch ranges of the loop and
+        the DoF runs private to them (bp4_desc::n_ranges); partitions = (n_cells_before_comm,
+        n_cells_comm) of the overlapped ghost exchange"""
         ei = np.ascontiguousarray(entity_index, dtype=np.uint32).reshape(-1, 27)
         vt = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 8, 3)
         assert len(ei) == len(vt)
@@ -141,17 +146,36 @@ class Context:
             d.n_peers, d.peer_rank, d.import_offset = len(pr), _ptr(pr), _ptr(io)
             d.export_offset, d.export_index = _ptr(eo), _ptr(ex)
             keep += [pr, io, eo, ex]
+        if ranges is not None:
+            rc = np.ascontiguousarray(ranges[0], dtype=np.uint64)
+            rp = np.ascontiguousarray(ranges[1], dtype=np.uint64)
+            assert len(rc) == len(rp)
+            d.n_ranges, d.range_cell_offset, d.range_private_offset = len(rc) - 1, _ptr(rc), _ptr(rp)
+            keep += [rc, rp]
+        if partitions is not None:
+            d.n_cells_before_comm, d.n_cells_comm = int(partitions[0]), int(partitions[1])
         self.h = C.c_void_p()
         _chk(lib().bp4_ctx_create(C.byref(d), C.byref(self.h)))
         self.degree, self.n_cells = int(degree), len(ei)
         self.n_owned, self.n_ghost = int(n_owned), int(n_ghost)
         self.n_local = self.n_owned + self.n_ghost
 
+    @classmethod
+    def from_handle(cls, handle, degree, n_cells, n_owned, n_ghost=0):
+        """view of a context owned by someone else (the C++ host's LaplaceOperator); close() is a no-op"""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p(handle)
+        self.degree, self.n_cells = int(degree), int(n_cells)
+        self.n_owned, self.n_ghost = int(n_owned), int(n_ghost)
+        self.n_local = self.n_owned + self.n_ghost
+        self.borrowed = True
+        return self
+
     # ---- lifetime -----------------------------------------------------------------
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "borrowed", False):
             lib().bp4_ctx_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def synchronize(self):
         _chk(lib().bp4_ctx_synchronize(self.h))
@@ -177,8 +201,14 @@ class Context:
                                     beta_old, out))
         return np.array(out[:])
 
-    def set_merged_variant(self, v: int):
-        _chk(lib().bp4_set_merged_variant(self.h, C.c_int(v)))
+    def set_fused(self, on: bool):
+        """developer hook: in-loop vector updates on (default with range tables) / off"""
+        _chk(lib().bp4_debug_set_fused(self.h, C.c_int(1 if on else 0)))
+
+    def fused_info(self):
+        f, npriv, nu = C.c_int(), C.c_uint64(), C.c_uint64()
+        _chk(lib().bp4_fused_info(self.h, C.byref(f), C.byref(npriv), C.byref(nu)))
+        return bool(f.value), int(npriv.value), int(nu.value)
 
     def inverse_diagonal(self) -> Vector:
         v = Vector(self, self.n_owned // 3)

@@ -7,7 +7,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <map>
 #include <string>
 #include <vector>
@@ -51,12 +54,18 @@ namespace
     }                                                                                         \
   while (0)
 
+// Which form of vmult_with_merged_sums a context starts with when the descriptor carries range
+// tables: 1 = vector updates inside the cell loop, 0 = streamed before/after it.  Set from the
+// B200 measurements in profiles/README.md; bp4_debug_set_fused / BP4_FUSED override it.
+#ifndef BP4_FUSED_DEFAULT
+#  define BP4_FUSED_DEFAULT 0
+#endif
+
 struct bp4_vec
 {
-  double  *buf[2] = {nullptr, nullptr}; // ping-pong pair (second one allocated on demand)
-  int      cur    = 0;
-  uint64_t n      = 0;
-  double  *p() const { return buf[cur]; }
+  double  *buf = nullptr;
+  uint64_t n   = 0;
+  double  *p() const { return buf; }
 };
 
 struct ProfEvent
@@ -75,16 +84,20 @@ struct bp4_ctx
   int          overlap = 1;
   cudaStream_t stream = nullptr;
   uint32_t    *d_entity = nullptr, *d_constrained = nullptr, *d_walk = nullptr;
-  uint16_t    *d_stage_tab = nullptr; // TMA variant: slot[28] + inverse table
   double      *d_coef = nullptr, *d_gll = nullptr;
   double      *d_acc  = nullptr; // [8] reduction scratch
   int         *d_flag = nullptr;
+  uint32_t    *d_sched = nullptr; // [4] unit counters of the cell-kernel launches of one loop
+  uint32_t     stagger_ns = 0;    // developer knob BP4_STAGGER_NS
   double      *h_acc  = nullptr; // pinned [8]
   int         *h_flag = nullptr; // pinned
-  int          merged_variant = 0; // 0 three kernels, 1 fused, 2 fused + warp-specialised
-  int          cell_variant   = 2; // plain cell kernel: 0 TMA, 1 warp-specialised, 2 classic (default), 3 cp.async prefetch
-  uint8_t     *d_meta = nullptr;     // fused kernel: per-cell entity meta bytes [n_cells][28]
-  uint32_t    *d_counters = nullptr; // fused kernel: arrival counters [n_nodes]
+  // fused merged loop (vmult_with_merged_sums): units of whole cell-batch ranges, their batches
+  // and the private DoF runs the vector updates are hooked to (bp4_kernels.cuh, BatchDesc)
+  int             fused      = 0;      // 1: do_cg_update4b/3b on private DoFs inside the cell kernel
+  uint64_t        n_private  = 0;      // [0, n_private) are private to one range, the rest is streamed
+  uint32_t        unit_part[4] = {0, 0, 0, 0}; // first unit of the three cell partitions (+ end)
+  bp4::BatchDesc *d_batch      = nullptr;
+  uint32_t       *d_unit_batch = nullptr;
   // multi-GPU
   ncclComm_t            comm = nullptr;
   int                   rank = 0, n_ranks = 1;
@@ -135,21 +148,28 @@ namespace
 
   int drain_events(bp4_ctx *c)
   {
-    for (auto &ev : c->events)
+    cudaError_t err = cudaSuccess;
+    for (auto &ev : c->events) // every event pair is released, also after a failure
       {
-        CU(cudaEventSynchronize(ev.b));
         float ms = 0;
-        CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
-        c->prof_ms[ev.id] += ms;
+        if (err == cudaSuccess)
+          err = cudaEventSynchronize(ev.b);
+        if (err == cudaSuccess)
+          err = cudaEventElapsedTime(&ms, ev.a, ev.b);
+        if (err == cudaSuccess)
+          c->prof_ms[ev.id] += ms;
         cudaEventDestroy(ev.a);
         cudaEventDestroy(ev.b);
       }
     c->events.clear();
+    CU(err);
     return 0;
   }
 
-  // zero-initialised buffer of n doubles, from the pool when one of that size is cached
-  int pooled_alloc(bp4_ctx *c, uint64_t n, double **out)
+  // buffer of n doubles, from the pool when one of that size is cached; zeroed on request only
+  // (SolverCGFullMerge takes its temporaries with omit_zeroing_entries = true,
+  // solver_cg_optimized.h:215-217)
+  int pooled_alloc(bp4_ctx *c, uint64_t n, double **out, bool zero)
   {
     auto it = c->pool.find(n);
     if (it != c->pool.end())
@@ -158,15 +178,9 @@ namespace
         c->pool.erase(it);
       }
     else
-      CU(cudaMalloc(out, sizeof(double) * (n + 2))); // + 2: pad doubles of the TMA bulk copies
-    CU(cudaMemsetAsync(*out, 0, sizeof(double) * (n + 2), c->stream));
-    return 0;
-  }
-
-  int ensure_second(bp4_ctx *c, bp4_vec *v)
-  {
-    if (!v->buf[1])
-      return pooled_alloc(c, v->n, &v->buf[1]);
+      CU(cudaMalloc(out, sizeof(double) * (n + 2))); // + 2: slack for 16-byte aligned bulk prefetches
+    if (zero)
+      CU(cudaMemsetAsync(*out, 0, sizeof(double) * n, c->stream));
     return 0;
   }
 
@@ -195,41 +209,66 @@ int bp4_device_count(int *count)
   return 0;
 }
 
-int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
+// cut the cell-batch ranges of one cell partition [pc0, pc1) into units (a few whole ranges,
+// about `target` cells) and the units into batches of cpb cells; see BatchDesc
+static void build_units(const std::vector<uint32_t> &range_cell, const std::vector<uint32_t> &range_priv,
+                        size_t r0, size_t r1, uint32_t cpb, uint32_t target,
+                        std::vector<bp4::BatchDesc> &batches, std::vector<uint32_t> &unit_batch)
 {
-  if (!d || !out)
-    return fail(BP4_ERR_ARG, "null argument");
-  if (d->degree < 2 || d->degree > 8)
-    return fail(BP4_ERR_ARG, "degree %d not supported (2..8)", d->degree);
-  if (d->n_owned % 3 || d->n_ghost % 3)
-    return fail(BP4_ERR_ARG, "n_owned/n_ghost must be multiples of 3");
-  if (d->n_owned + d->n_ghost >= 0xFFFFFFFFull)
-    return fail(BP4_ERR_ARG, "local vector exceeds 32-bit local indices (poisson_operator.h:693)");
-  if (d->n_cells && (!d->entity_index || !d->vertices))
-    return fail(BP4_ERR_ARG, "entity_index/vertices missing");
-  int ndev = 0;
-  CU(cudaGetDeviceCount(&ndev));
-  if (ndev == 0)
-    return fail(BP4_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
-  CU(cudaSetDevice(d->device));
-  bp4_ctx *c = new bp4_ctx;
+  size_t r = r0;
+  while (r < r1)
+    {
+      size_t re = r + 1;
+      while (re < r1 && range_cell[re] - range_cell[r] < target)
+        ++re;
+      unit_batch.push_back((uint32_t)batches.size());
+      const uint32_t uc0 = range_cell[r], uc1 = range_cell[re];
+      for (uint32_t cb = uc0; cb < uc1; cb += cpb)
+        {
+          const uint32_t  ce = std::min(cb + cpb, uc1);
+          bp4::BatchDesc b{};
+          b.cell0   = cb;
+          b.n_cells = ce - cb;
+          // ranges whose first cell lies in [cb, ce): pre; whose end lies in (cb, ce]: post
+          size_t f0 = r, f1, l0, l1;
+          while (f0 < re && range_cell[f0] < cb)
+            ++f0;
+          f1 = f0;
+          while (f1 < re && range_cell[f1] < ce)
+            ++f1;
+          l0 = r;
+          while (l0 < re && range_cell[l0 + 1] <= cb)
+            ++l0;
+          l1 = l0;
+          while (l1 < re && range_cell[l1 + 1] <= ce)
+            ++l1;
+          b.pre_begin  = range_priv[f0];
+          b.pre_end    = range_priv[f1];
+          b.post_begin = range_priv[l0];
+          b.post_end   = range_priv[l1];
+          batches.push_back(b);
+        }
+      r = re;
+    }
+}
+
+static uint32_t gcd_u32(uint32_t a, uint32_t b) { return b ? gcd_u32(b, a % b) : a; }
+
+static int ctx_create_impl(const bp4_desc *d, bp4_ctx *c)
+{
   c->degree  = d->degree;
   c->device  = d->device;
   c->n_cells = d->n_cells;
   c->n_owned = d->n_owned;
   c->n_ghost = d->n_ghost;
   c->n_constrained = d->n_constrained;
-  // the classic kernel is the fastest (or tied) plain cell kernel at every degree on B200
-  // (profiles/README.md); the other variants stay selectable with bp4_set_merged_variant
-  c->cell_variant = 2;
   c->n_before      = d->n_cells_before_comm;
   c->n_comm        = d->n_cells_comm;
   if (c->n_before + c->n_comm > c->n_cells)
-    {
-      delete c;
-      return fail(BP4_ERR_ARG, "cell partitions exceed n_cells");
-    }
+    return fail(BP4_ERR_ARG, "cell partitions exceed n_cells");
   CU(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, d->device));
+  if (const char *e = getenv("BP4_STAGGER_NS"))
+    c->stagger_ns = (uint32_t)atoi(e);
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
@@ -239,11 +278,6 @@ int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
   CU(bp4::launch_init_degree(d->degree, walk));
   CU(cudaMalloc(&c->d_walk, sizeof(uint32_t) * walk.size()));
   CU(cudaMemcpy(c->d_walk, walk.data(), sizeof(uint32_t) * walk.size(), cudaMemcpyHostToDevice));
-
-  std::vector<uint16_t> stab;
-  CU(bp4::launch_stage_tables(d->degree, stab));
-  CU(cudaMalloc(&c->d_stage_tab, sizeof(uint16_t) * stab.size()));
-  CU(cudaMemcpy(c->d_stage_tab, stab.data(), sizeof(uint16_t) * stab.size(), cudaMemcpyHostToDevice));
 
   const size_t nc = d->n_cells ? d->n_cells : 1;
   CU(cudaMalloc(&c->d_entity, sizeof(uint32_t) * 27 * nc));
@@ -283,8 +317,60 @@ int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
   CU(cudaMalloc(&c->d_acc, sizeof(double) * 8));
   CU(cudaMemset(c->d_acc, 0, sizeof(double) * 8));
   CU(cudaMalloc(&c->d_flag, sizeof(int)));
+  CU(cudaMalloc(&c->d_sched, sizeof(uint32_t) * 4));
   CU(cudaMallocHost(&c->h_acc, sizeof(double) * 8));
   CU(cudaMallocHost(&c->h_flag, sizeof(int)));
+
+  // cell-batch ranges and their private DoF runs -> units and batches of the fused merged loop
+  if (d->n_ranges > 0)
+    {
+      if (!d->range_cell_offset || !d->range_private_offset)
+        return fail(BP4_ERR_ARG, "range tables missing");
+      std::vector<uint32_t> rc(d->n_ranges + 1), rp(d->n_ranges + 1);
+      for (uint64_t r = 0; r <= d->n_ranges; ++r)
+        {
+          rc[r] = (uint32_t)d->range_cell_offset[r];
+          rp[r] = (uint32_t)d->range_private_offset[r];
+          if (r && (rc[r] <= rc[r - 1] || rp[r] < rp[r - 1]))
+            return fail(BP4_ERR_ARG, "range tables must be increasing (range %llu)", (unsigned long long)r);
+          if (rp[r] % 3)
+            return fail(BP4_ERR_ARG, "private DoF runs must start at a node (multiple of 3)");
+        }
+      if (rc[0] != 0 || rc[d->n_ranges] != d->n_cells || rp[0] != 0 || rp[d->n_ranges] > d->n_owned)
+        return fail(BP4_ERR_ARG, "range tables do not cover [0, n_cells) / exceed n_owned");
+      // the three cell partitions of the overlapped exchange must fall on range boundaries
+      const uint64_t cut[4] = {0, c->n_before, c->n_before + c->n_comm, c->n_cells};
+      size_t         rcut[4];
+      for (int k = 0; k < 4; ++k)
+        {
+          rcut[k] = std::lower_bound(rc.begin(), rc.end(), (uint32_t)cut[k]) - rc.begin();
+          if (rc[rcut[k]] != cut[k])
+            return fail(BP4_ERR_ARG, "a cell-batch range straddles a cell partition boundary");
+        }
+      const uint32_t cpb = (uint32_t)bp4::cells_per_block(d->degree);
+      const uint32_t rsz = rc[1] - rc[0];
+      uint32_t       target = cpb / gcd_u32(cpb, rsz) * rsz; // lcm: whole ranges in whole batches
+      while (target > 64 && target > rsz)
+        target -= rsz;
+      std::vector<bp4::BatchDesc> batches;
+      std::vector<uint32_t>       unit_batch;
+      for (int k = 0; k < 3; ++k)
+        {
+          c->unit_part[k] = (uint32_t)unit_batch.size();
+          build_units(rc, rp, rcut[k], rcut[k + 1], cpb, target, batches, unit_batch);
+        }
+      c->unit_part[3] = (uint32_t)unit_batch.size();
+      unit_batch.push_back((uint32_t)batches.size());
+      CU(cudaMalloc(&c->d_batch, sizeof(bp4::BatchDesc) * (batches.size() ? batches.size() : 1)));
+      CU(cudaMalloc(&c->d_unit_batch, sizeof(uint32_t) * unit_batch.size()));
+      CU(cudaMemcpy(c->d_batch, batches.data(), sizeof(bp4::BatchDesc) * batches.size(), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(c->d_unit_batch, unit_batch.data(), sizeof(uint32_t) * unit_batch.size(),
+                    cudaMemcpyHostToDevice));
+      c->n_private = rp[d->n_ranges];
+      c->fused     = BP4_FUSED_DEFAULT && c->n_private > 0;
+      if (const char *e = getenv("BP4_FUSED")) // developer knob: 0 = pre kernel + cells + post kernel
+        c->fused = c->n_private > 0 && atoi(e) != 0;
+    }
 
   // ghost exchange plan
   if (d->n_peers > 0)
@@ -299,6 +385,34 @@ int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
       CU(cudaMalloc(&c->d_sendbuf, sizeof(double) * (ne ? ne : 1)));
       CU(cudaMalloc(&c->d_recvbuf, sizeof(double) * (ne ? ne : 1)));
     }
+  return 0;
+}
+
+int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
+{
+  if (!d || !out)
+    return fail(BP4_ERR_ARG, "null argument");
+  if (d->degree < 2 || d->degree > 8)
+    return fail(BP4_ERR_ARG, "degree %d not supported (2..8)", d->degree);
+  if (d->n_owned % 3 || d->n_ghost % 3)
+    return fail(BP4_ERR_ARG, "n_owned/n_ghost must be multiples of 3");
+  if (d->n_owned + d->n_ghost >= 0xFFFFFFFFull)
+    return fail(BP4_ERR_ARG, "local vector exceeds 32-bit local indices (poisson_operator.h:693)");
+  if (d->n_cells && (!d->entity_index || !d->vertices))
+    return fail(BP4_ERR_ARG, "entity_index/vertices missing");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev == 0)
+    return fail(BP4_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  CU(cudaSetDevice(d->device));
+  bp4_ctx *c = new bp4_ctx;
+  if (int e = ctx_create_impl(d, c))
+    {
+      const std::string msg = g_err; // bp4_ctx_destroy must not clobber the message
+      bp4_ctx_destroy(c);
+      g_err = msg;
+      return e;
+    }
   *out = c;
   return 0;
 }
@@ -308,7 +422,8 @@ int bp4_ctx_destroy(bp4_ctx *c)
   if (!c)
     return 0;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
   drain_events(c);
   if (c->comm)
     ncclCommDestroy(c->comm);
@@ -317,22 +432,26 @@ int bp4_ctx_destroy(bp4_ctx *c)
   cudaFree(c->d_entity);
   cudaFree(c->d_constrained);
   cudaFree(c->d_walk);
-  cudaFree(c->d_stage_tab);
   cudaFree(c->d_coef);
   cudaFree(c->d_gll);
   cudaFree(c->d_acc);
   cudaFree(c->d_flag);
-  cudaFree(c->d_meta);
-  cudaFree(c->d_counters);
+  cudaFree(c->d_sched);
+  cudaFree(c->d_batch);
+  cudaFree(c->d_unit_batch);
   cudaFree(c->d_export);
   cudaFree(c->d_sendbuf);
   cudaFree(c->d_recvbuf);
   cudaFreeHost(c->h_acc);
   cudaFreeHost(c->h_flag);
-  cudaEventDestroy(c->ev_a);
-  cudaEventDestroy(c->ev_b);
-  cudaStreamDestroy(c->comm_stream);
-  cudaStreamDestroy(c->stream);
+  if (c->ev_a)
+    cudaEventDestroy(c->ev_a);
+  if (c->ev_b)
+    cudaEventDestroy(c->ev_b);
+  if (c->comm_stream)
+    cudaStreamDestroy(c->comm_stream);
+  if (c->stream)
+    cudaStreamDestroy(c->stream);
   delete c;
   return 0;
 }
@@ -353,14 +472,14 @@ int bp4_ctx_stream(bp4_ctx *c, void **stream)
   return 0;
 }
 
-int bp4_vec_alloc(bp4_ctx *c, uint64_t n, bp4_vec **out)
+static int vec_alloc(bp4_ctx *c, uint64_t n, bp4_vec **out, bool zero)
 {
   if (!c || !out)
     return fail(BP4_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   bp4_vec *v = new bp4_vec;
   v->n       = n;
-  if (int e = pooled_alloc(c, n, &v->buf[0]))
+  if (int e = pooled_alloc(c, n, &v->buf, zero))
     {
       delete v;
       return e;
@@ -369,18 +488,20 @@ int bp4_vec_alloc(bp4_ctx *c, uint64_t n, bp4_vec **out)
   return 0;
 }
 
+int bp4_vec_alloc(bp4_ctx *c, uint64_t n, bp4_vec **out) { return vec_alloc(c, n, out, true); }
+int bp4_vec_alloc_uninitialized(bp4_ctx *c, uint64_t n, bp4_vec **out) { return vec_alloc(c, n, out, false); }
+
 int bp4_vec_free(bp4_ctx *c, bp4_vec *v)
 {
   if (!v)
     return 0;
-  for (double *b : v->buf)
-    if (b)
-      {
-        if (c) // stream order makes reuse safe: the next user's memset is queued behind our work
-          c->pool.emplace(v->n, b);
-        else
-          cudaFree(b);
-      }
+  if (v->buf)
+    {
+      if (c) // stream order makes reuse safe: the next user's work is queued behind ours
+        c->pool.emplace(v->n, v->buf);
+      else
+        cudaFree(v->buf);
+    }
   delete v;
   return 0;
 }
@@ -442,38 +563,80 @@ static int check_len(const bp4_ctx *c, const bp4_vec *v, const char *name)
   return 0;
 }
 
-// cell loop over the cells [begin, end): dst += sum_cells A_cell src on the local vector
-static int cell_range(bp4_ctx *c, double *dst, const double *src, uint64_t begin, uint64_t end)
+// BLAS-1 operands must hold at least the owned entries
+static int check_owned(const bp4_ctx *c, const bp4_vec *v, const char *name)
 {
+  if (!v)
+    return fail(BP4_ERR_ARG, "%s is null", name);
+  if (v->n < c->n_owned)
+    return fail(BP4_ERR_ARG, "%s has %llu entries, need n_owned = %llu", name, (unsigned long long)v->n,
+                (unsigned long long)c->n_owned);
+  return 0;
+}
+
+// BLAS-1 sweeps the owned entries, or the whole operand when it is shorter (the per-node
+// diagonal holds n_owned/3 entries: diag_mat.diagonal.l2_norm(), benchmark.h:151)
+static uint64_t sweep_len(const bp4_ctx *c, std::initializer_list<const bp4_vec *> vs)
+{
+  uint64_t n = c->n_owned;
+  for (const bp4_vec *v : vs)
+    n = std::min<uint64_t>(n, v->n);
+  return n;
+}
+
+// scalars and vectors of one vmult_with_merged_sums call, for the fused cell loop
+struct MergedCall
+{
+  double *x, *g, *d;
+  const double *prec;
+  double  alpha, beta, alpha_old, beta_old;
+};
+
+// cell loop over the cell partition `part` (0..2, or -1 = all cells): dst += sum_cells A_cell src
+// on the local vector; with `m` the private DoFs of the ranges get their do_cg_update4b/3b inside
+static int cell_range(bp4_ctx *c, double *dst, const double *src, int part, const MergedCall *m)
+{
+  const uint64_t cut[4] = {0, c->n_before, c->n_before + c->n_comm, c->n_cells};
+  const uint64_t begin = part < 0 ? 0 : cut[part], end = part < 0 ? c->n_cells : cut[part + 1];
   if (end <= begin)
     return 0;
-  bp4::CellArgs a;
-  a.entity_index = c->d_entity + 27 * begin;
-  a.coef         = c->d_coef + 24 * begin;
-  a.dtab         = c->d_walk;
-  a.n_cells      = end - begin;
-  a.src          = src;
-  a.dst          = dst;
-  Timed t(c, BP4_K_VMULT);
-  if (c->cell_variant == 1)
-    CU(bp4::launch_cell_ws(c->degree, nullptr, &a, c->sms, c->stream));
-  else if (c->cell_variant == 2)
-    CU(bp4::launch_cell_plain(c->degree, a, c->sms, c->stream));
-  else if (c->cell_variant == 3)
-    CU(bp4::launch_cell_pf(c->degree, a, c->sms, c->stream));
-  else if (c->cell_variant == 4)
-    CU(bp4::launch_cell_trio(c->degree, a, c->sms, c->stream));
+  bp4::CellArgs a{};
+  a.dtab  = c->d_walk;
+  a.src   = src;
+  a.dst   = dst;
+  a.sched = c->d_sched + (part < 0 ? 0 : part);
+  a.stagger_ns = c->stagger_ns;
+  if (m)
+    {
+      const uint32_t u0 = part < 0 ? c->unit_part[0] : c->unit_part[part],
+                     u1 = part < 0 ? c->unit_part[3] : c->unit_part[part + 1];
+      a.entity_index = c->d_entity;
+      a.coef         = c->d_coef;
+      a.n_cells      = c->n_cells;
+      a.batch        = c->d_batch;
+      a.unit_batch   = c->d_unit_batch + u0;
+      a.n_units      = u1 - u0;
+      a.r            = m->g;
+      a.p            = m->d;
+      a.x            = m->x;
+      a.prec         = m->prec;
+      a.alpha        = m->alpha;
+      a.beta         = m->beta;
+      a.first        = m->alpha == 0. ? 1 : 0;
+      a.update_x     = (m->alpha != 0. && m->alpha_old != 0.) ? 1 : 0;
+      a.c1           = a.update_x ? m->alpha + m->alpha_old / m->beta_old : 0.;
+      a.c2           = a.update_x ? m->alpha_old / m->beta_old : 0.;
+      a.acc          = c->d_acc;
+      Timed t(c, BP4_K_MERGED);
+      CU(bp4::launch_cell(c->degree, true, a, c->sms, c->stream));
+    }
   else
     {
-      bp4::TmaArgs t;
-      t.entity_index = a.entity_index;
-      t.coef         = a.coef;
-      t.slot         = c->d_stage_tab;
-      t.itab         = c->d_stage_tab + 28;
-      t.n_cells      = a.n_cells;
-      t.src          = src;
-      t.dst          = dst;
-      CU(bp4::launch_cell_tma(c->degree, t, c->sms, c->stream));
+      a.entity_index = c->d_entity + 27 * begin;
+      a.coef         = c->d_coef + 24 * begin;
+      a.n_cells      = end - begin;
+      Timed t(c, BP4_K_VMULT);
+      CU(bp4::launch_cell(c->degree, false, a, c->sms, c->stream));
     }
   return 0;
 }
@@ -487,15 +650,15 @@ static int exchange_compress_on(bp4_ctx *c, double *v, cudaStream_t st);
 //   pack | interior part 1 || send/recv ghosts | ghost-touching cells | interior part 2 ||
 //   send/recv contributions | unpack-add.
 // dst must already be zero where the cells accumulate (owned and ghost slots).
-static int cell_loop(bp4_ctx *c, double *dst, const double *src)
+static int cell_loop(bp4_ctx *c, double *dst, const double *src, const MergedCall *m)
 {
+  CU(cudaMemsetAsync(c->d_sched, 0, sizeof(uint32_t) * 4, c->stream));
   if (c->peer.empty())
-    return cell_range(c, dst, src, 0, c->n_cells);
+    return cell_range(c, dst, src, -1, m);
   if (!c->comm)
     return fail(BP4_ERR_STATE, "ghost exchange not initialised (bp4_comm_init)");
   const uint64_t ne      = c->export_off.back();
   const bool     overlap = c->overlap && c->n_comm > 0;
-  const uint64_t n1 = overlap ? c->n_before : 0, n2 = overlap ? c->n_before + c->n_comm : c->n_cells;
   {
     Timed t(c, BP4_K_BLAS1);
     CU(bp4::launch_pack(ne, c->d_export, src, c->d_sendbuf, c->stream));
@@ -505,18 +668,25 @@ static int cell_loop(bp4_ctx *c, double *dst, const double *src)
   if (int e = exchange_ghosts_on(c, const_cast<double *>(src), c->comm_stream))
     return e;
   CU(cudaEventRecord(c->ev_b, c->comm_stream));
-  if (int e = cell_range(c, dst, src, 0, n1))
-    return e;
+  if (overlap)
+    if (int e = cell_range(c, dst, src, 0, m))
+      return e;
   CU(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
-  if (int e = cell_range(c, dst, src, n1, n2))
+  if (overlap)
+    {
+      if (int e = cell_range(c, dst, src, 1, m))
+        return e;
+    }
+  else if (int e = cell_range(c, dst, src, -1, m))
     return e;
   CU(cudaEventRecord(c->ev_a, c->stream));
   CU(cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
   if (int e = exchange_compress_on(c, dst, c->comm_stream))
     return e;
   CU(cudaEventRecord(c->ev_b, c->comm_stream));
-  if (int e = cell_range(c, dst, src, n2, c->n_cells))
-    return e;
+  if (overlap)
+    if (int e = cell_range(c, dst, src, 2, m))
+      return e;
   CU(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
   {
     Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
@@ -538,8 +708,9 @@ int bp4_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src)
     return e;
   if (dst == src)
     return fail(BP4_ERR_ARG, "vmult: dst aliases src");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(dst->p(), 0, sizeof(double) * (c->n_owned + c->n_ghost), c->stream));
-  if (int e = cell_loop(c, dst->p(), src->p()))
+  if (int e = cell_loop(c, dst->p(), src->p(), nullptr))
     return e;
   {
     Timed t(c, BP4_K_BLAS1);
@@ -548,15 +719,26 @@ int bp4_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src)
   return 0;
 }
 
-int bp4_set_merged_variant(bp4_ctx *c, int variant)
+int bp4_debug_set_fused(bp4_ctx *c, int on)
 {
-  if (!c || variant < 0 || variant > 14)
-    return fail(BP4_ERR_ARG, "bad variant");
-  // merged: 0 three kernels, 1 fused, 2 fused + warp-specialised;
-  // plain cell kernel: +0 TMA bulk gather/scatter (default), +3 warp-specialised, +6 classic,
-  // +9 cp.async prefetch, +12 trio (256 threads, three lanes per y-line in phase 2)
-  c->merged_variant = variant % 3;
-  c->cell_variant   = variant / 3;
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  if (on && c->n_private == 0)
+    return fail(BP4_ERR_STATE, "no private DoF runs: the context was created without range tables");
+  c->fused = on != 0;
+  return 0;
+}
+
+int bp4_fused_info(bp4_ctx *c, int *fused, uint64_t *n_private, uint64_t *n_units)
+{
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  if (fused)
+    *fused = c->fused;
+  if (n_private)
+    *n_private = c->n_private;
+  if (n_units)
+    *n_units = c->unit_part[3];
   return 0;
 }
 
@@ -571,75 +753,27 @@ int bp4_vmult_merged(bp4_ctx *c, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *h,
       return e;
   if (!prec || prec->n < c->n_owned / 3)
     return fail(BP4_ERR_ARG, "prec needs n_owned/3 entries");
+  CU(cudaSetDevice(c->device));
   const uint64_t n = c->n_owned;
-  if (c->merged_variant >= 1 && c->peer.empty())
-    {
-      // single fused kernel; g, d, h ping-pong between two buffers each
-      if (!c->d_meta)
-        {
-          const uint64_t n_nodes = n / 3 ? n / 3 : 1;
-          uint32_t      *owner   = nullptr;
-          CU(cudaMalloc(&c->d_meta, 28 * (c->n_cells ? c->n_cells : 1)));
-          CU(cudaMalloc(&c->d_counters, sizeof(uint32_t) * n_nodes));
-          CU(cudaMalloc(&owner, sizeof(uint32_t) * n_nodes));
-          c->launches += 2;
-          CU(bp4::launch_build_meta(c->n_cells, n_nodes, c->d_entity, c->d_counters, owner, c->d_meta,
-                                    c->stream));
-          CU(cudaStreamSynchronize(c->stream));
-          CU(cudaFree(owner));
-        }
-      for (bp4_vec *v : {g, d, h})
-        if (int e = ensure_second(c, v))
-          return e;
-      CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 7, c->stream));
-      bp4::MergedArgs a;
-      a.entity_index = c->d_entity;
-      a.coef         = c->d_coef;
-      a.dtab         = c->d_walk;
-      a.meta         = c->d_meta;
-      a.counters     = c->d_counters;
-      a.n_cells      = c->n_cells;
-      a.r_old        = g->buf[g->cur];
-      a.p_old        = d->buf[d->cur];
-      a.h_old        = h->buf[h->cur];
-      a.r_new        = g->buf[g->cur ^ 1];
-      a.p_new        = d->buf[d->cur ^ 1];
-      a.h_new        = h->buf[h->cur ^ 1];
-      a.x            = x->p();
-      a.prec         = prec->p();
-      a.alpha        = alpha;
-      a.beta         = beta;
-      a.update_x     = (alpha != 0. && alpha_old != 0.) ? 1 : 0;
-      a.c1           = a.update_x ? alpha + alpha_old / beta_old : 0.;
-      a.c2           = a.update_x ? alpha_old / beta_old : 0.;
-      a.acc          = c->d_acc;
-      {
-        Timed t(c, BP4_K_MERGED);
-        if (c->merged_variant == 2)
-          CU(bp4::launch_cell_ws(c->degree, &a, nullptr, c->sms, c->stream));
-        else
-          CU(bp4::launch_cell_merged(c->degree, a, c->sms, c->stream));
-      }
-      g->cur ^= 1;
-      d->cur ^= 1;
-      h->cur ^= 1;
-      return reduce_to_host(c, 7, out);
-    }
-  // three-kernel variant: pre sweep, cell loop, post sweep
+  // DoFs private to one cell-batch range get do_cg_update4b / do_cg_update3b inside the cell
+  // kernel; the rest of the vector -- shared between ranges or ranks, Dirichlet -- is streamed
+  // before / after the loop (with the fused path off: everything)
+  const uint64_t tail = c->fused ? c->n_private : 0;
   {
     Timed t(c, BP4_K_PRE);
-    CU(bp4::launch_pre(n, h->p(), x->p(), g->p(), d->p(), prec->p(), alpha, beta, alpha_old, beta_old,
-                       c->sms, c->stream));
+    CU(bp4::launch_pre(tail, n, h->p(), x->p(), g->p(), d->p(), prec->p(), alpha, beta, alpha_old, beta_old,
+                       c->d_acc, c->sms, c->stream));
   }
   if (c->n_ghost)
     CU(cudaMemsetAsync(h->p() + n, 0, sizeof(double) * c->n_ghost, c->stream));
-  if (int e = cell_loop(c, h->p(), d->p()))
+  MergedCall m{x->p(), g->p(), d->p(), prec->p(), alpha, beta, alpha_old, beta_old};
+  if (int e = cell_loop(c, h->p(), d->p(), c->fused ? &m : nullptr))
     return e;
-  CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 7, c->stream));
-  {
-    Timed t(c, BP4_K_POST);
-    CU(bp4::launch_post(n, g->p(), d->p(), h->p(), prec->p(), c->d_acc, c->sms, c->stream));
-  }
+  if (n > tail)
+    {
+      Timed t(c, BP4_K_POST);
+      CU(bp4::launch_post(tail, n, g->p(), d->p(), h->p(), prec->p(), c->d_acc, c->sms, c->stream));
+    }
   return reduce_to_host(c, 7, out);
 }
 
@@ -674,6 +808,7 @@ int bp4_jacobi_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src, const bp4_vec
   if (dst->n < c->n_owned || src->n < c->n_owned || 3 * diag->n < c->n_owned)
     return fail(BP4_ERR_ARG, "Dimension mismatch %llu vs 3 x %llu", (unsigned long long)dst->n,
                 (unsigned long long)diag->n);
+  CU(cudaSetDevice(c->device));
   Timed t(c, BP4_K_BLAS1);
   CU(bp4::launch_jacobi(c->n_owned, dst->p(), src->p(), diag->p(), c->sms, c->stream));
   return 0;
@@ -684,6 +819,15 @@ int bp4_x_finalize_even(bp4_ctx *c, bp4_vec *x, const bp4_vec *d, const bp4_vec 
 {
   if (!c || !x || !d || !g || !prec)
     return fail(BP4_ERR_ARG, "null argument");
+  if (int e = check_owned(c, x, "x"))
+    return e;
+  if (int e = check_owned(c, d, "d"))
+    return e;
+  if (int e = check_owned(c, g, "g"))
+    return e;
+  if (3 * prec->n < c->n_owned)
+    return fail(BP4_ERR_ARG, "prec needs n_owned/3 entries");
+  CU(cudaSetDevice(c->device));
   Timed t(c, BP4_K_BLAS1);
   CU(bp4::launch_xfinal(c->n_owned, x->p(), d->p(), g->p(), prec->p(), c1, c2, c->sms, c->stream));
   return 0;
@@ -693,8 +837,9 @@ int bp4_equ(bp4_ctx *c, bp4_vec *dst, double a, const bp4_vec *src)
 {
   if (!c || !dst || !src)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   Timed t(c, BP4_K_BLAS1);
-  CU(bp4::launch_sadd(c->n_owned, dst->p(), 0., a, src->p(), c->sms, c->stream));
+  CU(bp4::launch_sadd(sweep_len(c, {dst, src}), dst->p(), 0., a, src->p(), c->sms, c->stream));
   return 0;
 }
 
@@ -702,8 +847,9 @@ int bp4_add(bp4_ctx *c, bp4_vec *dst, double a, const bp4_vec *src)
 {
   if (!c || !dst || !src)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   Timed t(c, BP4_K_BLAS1);
-  CU(bp4::launch_sadd(c->n_owned, dst->p(), 1., a, src->p(), c->sms, c->stream));
+  CU(bp4::launch_sadd(sweep_len(c, {dst, src}), dst->p(), 1., a, src->p(), c->sms, c->stream));
   return 0;
 }
 
@@ -711,8 +857,9 @@ int bp4_sadd(bp4_ctx *c, bp4_vec *dst, double s, double a, const bp4_vec *src)
 {
   if (!c || !dst || !src)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   Timed t(c, BP4_K_BLAS1);
-  CU(bp4::launch_sadd(c->n_owned, dst->p(), s, a, src->p(), c->sms, c->stream));
+  CU(bp4::launch_sadd(sweep_len(c, {dst, src}), dst->p(), s, a, src->p(), c->sms, c->stream));
   return 0;
 }
 
@@ -720,10 +867,11 @@ int bp4_dot(bp4_ctx *c, const bp4_vec *a, const bp4_vec *b, double *result)
 {
   if (!c || !a || !b || !result)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
   {
     Timed t(c, BP4_K_BLAS1);
-    CU(bp4::launch_dot(c->n_owned, a->p(), b->p(), c->d_acc, c->sms, c->stream));
+    CU(bp4::launch_dot(sweep_len(c, {a, b}), a->p(), b->p(), c->d_acc, c->sms, c->stream));
   }
   return reduce_to_host(c, 1, result);
 }
@@ -732,10 +880,11 @@ int bp4_add_and_dot(bp4_ctx *c, bp4_vec *g, double a, const bp4_vec *h, const bp
 {
   if (!c || !g || !h || !w || !result)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
   {
     Timed t(c, BP4_K_BLAS1);
-    CU(bp4::launch_add_and_dot(c->n_owned, g->p(), a, h->p(), w->p(), c->d_acc, c->sms, c->stream));
+    CU(bp4::launch_add_and_dot(sweep_len(c, {g, h, w}), g->p(), a, h->p(), w->p(), c->d_acc, c->sms, c->stream));
   }
   return reduce_to_host(c, 1, result);
 }
@@ -753,10 +902,11 @@ int bp4_all_zero(bp4_ctx *c, const bp4_vec *v, int *result)
 {
   if (!c || !v || !result)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
   {
     Timed t(c, BP4_K_BLAS1);
-    CU(bp4::launch_nonzero(c->n_owned, v->p(), c->d_flag, c->sms, c->stream));
+    CU(bp4::launch_nonzero(sweep_len(c, {v}), v->p(), c->d_flag, c->sms, c->stream));
   }
   if (c->comm)
     NC(ncclAllReduce(c->d_flag, c->d_flag, 1, ncclInt, ncclMax, c->comm, c->stream));

@@ -279,37 +279,6 @@ namespace bp4
     return dtab_row(t) * Geom<P>::RW + dtab_inrow(t);
   }
 
-  // entity-ordered staging used by the TMA variant: entity a owns the slot
-  // [slot(a), slot(a) + r2(n_a + 2)) of a cell's stage; the data start at slot(a) + (b & 1) where b
-  // is the entity's first global DoF, so that smem and global addresses share their 16-byte phase
-  template <int P>
-  struct Stage
-  {
-    BP4_HD static constexpr int r2(const int x) { return (x + 1) & ~1; }
-    static constexpr int M    = P - 1;
-    static constexpr int SIZE = 8 * r2(3 + 2) + 12 * r2(3 * M + 2) + 6 * r2(3 * M * M + 2) + r2(3 * M * M * M + 2);
-    BP4_HD static constexpr int n_dofs(const int a)
-    {
-      return 3 * (a % 3 == 1 ? M : 1) * ((a / 3) % 3 == 1 ? M : 1) * (a / 9 == 1 ? M : 1);
-    }
-  };
-  // slot[a] (first slot, even) and the inverse table itab[kk][row] = entity | rel << 5
-  template <int P>
-  inline void build_stage_tables(uint16_t *slot, uint16_t *itab)
-  {
-    int o = 0;
-    for (int a = 0; a < 27; ++a)
-      {
-        slot[a] = (uint16_t)o;
-        o += Stage<P>::r2(Stage<P>::n_dofs(a) + 2);
-      }
-    uint32_t dtab[Geom<P>::DOF];
-    build_dof_table<P>(dtab);
-    for (int r = 0; r < Geom<P>::DOF; ++r)
-      itab[dtab_inrow(dtab[r]) * Geom<P>::ROWS + dtab_row(dtab[r])] =
-        (uint16_t)(dtab_ent(dtab[r]) | (dtab_rel(dtab[r]) << 5));
-  }
-
   // ---------------------------------------------------------------------------------------
   // phase 1: item = row (c, j).  dofs_row[k][i] -> work_row[{0,1,2}][qz][qx]
   // ---------------------------------------------------------------------------------------
@@ -323,33 +292,6 @@ namespace bp4
     double *p;
     BP4_HD void operator()(const int kk, const double v) const { p[kk] = v; }
   };
-  // entity-ordered staging (the layout TMA bulk copies fill and drain): position of
-  // (row, kk) = off[entity] + offset inside the entity, both looked up in shared memory
-  struct StageIn
-  {
-    const double   *stage;
-    const uint16_t *itab; // [N*N][rows] entity | rel << 5
-    const uint16_t *off;  // [27] first slot of every entity of this cell
-    int             row, rows;
-    BP4_HD double operator()(const int kk) const
-    {
-      const uint32_t t = itab[kk * rows + row];
-      return stage[off[t & 31u] + (t >> 5)];
-    }
-  };
-  struct StageOut
-  {
-    double         *stage;
-    const uint16_t *itab;
-    const uint16_t *off;
-    int             row, rows;
-    BP4_HD void operator()(const int kk, const double v) const
-    {
-      const uint32_t t               = itab[kk * rows + row];
-      stage[off[t & 31u] + (t >> 5)] = v;
-    }
-  };
-
   template <int P, typename In>
   BP4_HD void phase1_io(const Tab<P> &tb, const In in, double *out)
   {
@@ -655,138 +597,6 @@ namespace bp4
           }
       }
   }
-
-  // ---------------------------------------------------------------------------------------
-  // phase 2, three lanes per y-line ("trio"): lane c of the trio owns component c of the line
-  // (qx, qz); the six metric entries G of the line's Q points are computed cooperatively
-  // (lane c does the points q = c, c+3, ...) and broadcast inside the trio with warp shuffles.
-  // Same arithmetic as phase2() per component, but only ~1/3 of the registers per thread, so
-  // twice as many warps fit on an SM.  Must be executed by all lanes named in `mask` (lanes
-  // without work pass active = false: they run on clamped addresses and skip the stores).
-  // ---------------------------------------------------------------------------------------
-#ifdef __CUDACC__
-  template <int P>
-  __device__ __forceinline__ void phase2_trio(const Tab<P> &tb, const double *cf, double *work, const int qx,
-                                              const int qz, const int c, const int trio_lane0,
-                                              const unsigned mask, const bool active, const double x,
-                                              const double z, const double wxz)
-  {
-    using G          = Geom<P>;
-    constexpr int N  = G::N, Q = G::Q;
-    constexpr int NP = (Q + 2) / 3; // points per lane
-    double        mg[6][NP];
-    {
-      double A[3], B[3], R1[3], Cc[3], Dd[3];
-#  pragma unroll
-      for (int d = 0; d < 3; ++d)
-        {
-          const double v1 = cf[3 + d], v3 = cf[6 + d], v4 = cf[9 + d], v9 = cf[12 + d],
-                       v10 = cf[15 + d], v12 = cf[18 + d], v13 = cf[21 + d];
-          A[d]  = v1 + z * v10;
-          B[d]  = v4 + z * v13;
-          R1[d] = (v3 + z * v12) + x * B[d];
-          Cc[d] = v9 + x * v10;
-          Dd[d] = v12 + x * v13;
-        }
-#  pragma unroll
-      for (int k = 0; k < NP; ++k)
-        {
-          // my k-th point: q = c + 3k (clamped for the lanes whose last point does not exist)
-          double y = 0., wy = 0.;
-#  pragma unroll
-          for (int cc = 0; cc < 3; ++cc)
-            if (cc + 3 * k < Q && c == cc)
-              {
-                y  = tb.xq[cc + 3 * k];
-                wy = tb.wq[cc + 3 * k];
-              }
-          double r0[3], r2[3];
-#  pragma unroll
-          for (int d = 0; d < 3; ++d)
-            {
-              r0[d] = A[d] + y * B[d];
-              r2[d] = Cc[d] + y * Dd[d];
-            }
-          double k0[3], k1[3], k2[3];
-          k0[0] = R1[1] * r2[2] - R1[2] * r2[1];
-          k0[1] = R1[2] * r2[0] - R1[0] * r2[2];
-          k0[2] = R1[0] * r2[1] - R1[1] * r2[0];
-          k1[0] = r2[1] * r0[2] - r2[2] * r0[1];
-          k1[1] = r2[2] * r0[0] - r2[0] * r0[2];
-          k1[2] = r2[0] * r0[1] - r2[1] * r0[0];
-          k2[0] = r0[1] * R1[2] - r0[2] * R1[1];
-          k2[1] = r0[2] * R1[0] - r0[0] * R1[2];
-          k2[2] = r0[0] * R1[1] - r0[1] * R1[0];
-          const double det = r0[0] * k0[0] + r0[1] * k0[1] + r0[2] * k0[2];
-          const double sc  = (wxz * wy) * rcp_nobranch(det);
-          mg[0][k]         = sc * (k0[0] * k0[0] + k0[1] * k0[1] + k0[2] * k0[2]);
-          mg[1][k]         = sc * (k0[0] * k1[0] + k0[1] * k1[1] + k0[2] * k1[2]);
-          mg[2][k]         = sc * (k0[0] * k2[0] + k0[1] * k2[1] + k0[2] * k2[2]);
-          mg[3][k]         = sc * (k1[0] * k1[0] + k1[1] * k1[1] + k1[2] * k1[2]);
-          mg[4][k]         = sc * (k1[0] * k2[0] + k1[1] * k2[1] + k1[2] * k2[2]);
-          mg[5][k]         = sc * (k2[0] * k2[0] + k2[1] * k2[1] + k2[2] * k2[2]);
-        }
-    }
-    double *base = work + (c * N) * G::RW + qz * Q + qx;
-    double  gx[Q], gy[Q], gz[Q], v[Q];
-#  pragma unroll
-    for (int j = 0; j < N; ++j)
-      {
-        const double r0 = base[j * G::RW], r1 = base[j * G::RW + Q * Q], r2 = base[j * G::RW + 2 * Q * Q];
-#  pragma unroll
-        for (int q = 0; q < Q; ++q)
-          {
-            const double sjq = tb.S[j][q];
-            v[q]  = j == 0 ? sjq * r0 : v[q] + sjq * r0;
-            gx[q] = j == 0 ? sjq * r1 : gx[q] + sjq * r1;
-            gz[q] = j == 0 ? sjq * r2 : gz[q] + sjq * r2;
-          }
-      }
-#  pragma unroll
-    for (int i = 0; i < Q; ++i)
-#  pragma unroll
-      for (int q = 0; q < Q; ++q)
-        gy[q] = i == 0 ? tb.D[0][q] * v[0] : gy[q] + tb.D[i][q] * v[i];
-    // flux = G grad, G of point q comes from trio lane q % 3
-#  pragma unroll
-    for (int q = 0; q < Q; ++q)
-      {
-        const int src = trio_lane0 + q % 3;
-        double    g[6];
-#  pragma unroll
-        for (int e = 0; e < 6; ++e)
-          g[e] = __shfl_sync(mask, mg[e][q / 3], src);
-        const double a = gx[q], b = gy[q], e2 = gz[q];
-        gx[q] = g[0] * a + g[1] * b + g[2] * e2;
-        gy[q] = g[1] * a + g[3] * b + g[4] * e2;
-        gz[q] = g[2] * a + g[4] * b + g[5] * e2;
-      }
-#  pragma unroll
-    for (int q = 0; q < Q; ++q)
-#  pragma unroll
-      for (int i = 0; i < Q; ++i)
-        v[i] = q == 0 ? tb.D[i][0] * gy[0] : v[i] + tb.D[i][q] * gy[q];
-    if (active)
-      {
-#  pragma unroll
-        for (int j = 0; j < N; ++j)
-          {
-            double o0, o1, o2;
-#  pragma unroll
-            for (int q = 0; q < Q; ++q)
-              {
-                const double sjq = tb.S[j][q];
-                o0 = q == 0 ? sjq * v[0] : o0 + sjq * v[q];
-                o1 = q == 0 ? sjq * gx[0] : o1 + sjq * gx[q];
-                o2 = q == 0 ? sjq * gz[0] : o2 + sjq * gz[q];
-              }
-            base[j * G::RW]             = o0;
-            base[j * G::RW + Q * Q]     = o1;
-            base[j * G::RW + 2 * Q * Q] = o2;
-          }
-      }
-  }
-#endif
 
   // ---------------------------------------------------------------------------------------
   // phase 3: item = row (c, j).  work_row[{0,1,2}][qz][qx] -> dofs_row[k][i]

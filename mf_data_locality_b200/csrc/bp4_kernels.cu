@@ -1,6 +1,7 @@
 // bp4_kernels.cu -- kernel definitions and launchers (sm_100a, FP64).  See bp4_kernels.cuh.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "bp4_kernels.cuh"
 #include "bp4_launch.h"
@@ -19,6 +20,15 @@
 #ifndef BP4_FINE_FROM
 #  define BP4_FINE_FROM 6
 #endif
+#ifndef BP4_KU
+#  define BP4_KU 4 // DoFs per thread and sweep of the in-loop do_cg_update4b / 3b
+#endif
+#ifndef BP4_DYNAMIC
+#  define BP4_DYNAMIC 1 // batches / units are claimed from an atomic counter instead of strided
+#endif
+#ifndef BP4_L2_PREFETCH
+#  define BP4_L2_PREFETCH 1 // bulk L2 prefetch of the next-but-one batch's private DoFs
+#endif
 
 namespace bp4
 {
@@ -26,11 +36,6 @@ namespace bp4
   // matrix entry becomes a c[bank][offset] operand of a DFMA, no load instruction
   template <int P>
   __constant__ Tab<P> c_tab;
-
-  // ---------------------------------------------------------------------------------------
-  // cell kernels
-  // ---------------------------------------------------------------------------------------
-  constexpr int kGatherUnroll = 4;
 
   template <int P, int CPB>
   __device__ __forceinline__ void load_tables(CellSmem<P, CPB> &sm, const uint32_t *dtab)
@@ -42,30 +47,8 @@ namespace bp4
         sm.xq[threadIdx.x] = c_tab<P>.xq[threadIdx.x];
         sm.wq[threadIdx.x] = c_tab<P>.wq[threadIdx.x];
       }
-  }
-
-  // phases 1-3 on the nc cells staged in the work rows (in place), with the barriers between them
-  template <int P, int CPB>
-  __device__ __forceinline__ void apply_staged(CellSmem<P, CPB> &sm, const int nc)
-  {
-    using G          = Geom<P>;
-    constexpr int Q  = G::Q;
-    const Tab<P> &tb = c_tab<P>;
-    const int     tid = threadIdx.x;
-    for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-      phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
-    __syncthreads();
-    for (int it = tid; it < nc * G::ITEMS2; it += kThreads)
-      {
-        const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
-        const int qz = r / Q, qx = r % Q;
-        phase2<P>(tb, sm.coef[0][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
-                  sm.wq[qx] * sm.wq[qz]);
-      }
-    __syncthreads();
-    for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-      phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
-    __syncthreads();
+    if (threadIdx.x < 8)
+      sm.red[threadIdx.x] = 0.;
   }
 
   // optional per-phase clock accounting (compile with -DBP4_PHASE_TIMING, run with
@@ -75,10 +58,30 @@ namespace bp4
 #  define BP4_TICK_INIT unsigned long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long t0 = clock64();
 #  define BP4_TICK(k) { const long long t1 = clock64(); tc[k] += t1 - t0; t0 = t1; }
 #  define BP4_TICK_FLUSH if ((threadIdx.x & 31) == 0) for (int k = 0; k < 8; ++k) atomicAdd(&g_phase_clk[k], tc[k]);
+  // per-block timeline of the first kTraceBatches batches (BP4_TRACE=<file>): globaltimer at the
+  // top of the batch, after phase 3, after the scatter, at the end of the memory window; + SM id
+  constexpr int kTraceBatches = 48;
+  __device__ unsigned long long *g_trace;
+  __device__ __forceinline__ unsigned long long gtime()
+  {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+  }
+  __device__ __forceinline__ unsigned smid()
+  {
+    unsigned r;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+    return r;
+  }
+#  define BP4_TRACE(i, k)                                                                     \
+    if (g_trace && threadIdx.x == 0 && (i) < kTraceBatches)                                   \
+      g_trace[((size_t)blockIdx.x * kTraceBatches + (i)) * 5 + (k)] = (k) == 4 ? smid() : gtime();
 #else
 #  define BP4_TICK_INIT
 #  define BP4_TICK(k)
 #  define BP4_TICK_FLUSH
+#  define BP4_TRACE(i, k)
 #endif
 
   // Phase 2 as a real call for the high degrees: its ~100 live doubles get a register allocation
@@ -93,17 +96,68 @@ namespace bp4
               reinterpret_cast<double *>(smem_raw + work_off), qx, qz, x, z, wxz);
   }
 
-  // Classic cell kernel: every warp does every phase; two blocks per SM overlap one block's
-  // memory phases with the other's FP64 phases.  The memory phases are kept short:
+  __device__ __forceinline__ double warp_sum(double v)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+
+  // the seven merged sums of do_cg_update3b (solver_cg_optimized.h:37-44) for one entry
+  __device__ __forceinline__ void post_terms(double (&s)[7], const double ri, const double di,
+                                             const double hi, const double pr)
+  {
+    const double zi = pr * hi;
+    s[0] += di * hi;
+    s[1] += hi * hi;
+    s[2] += ri * hi;
+    s[3] += ri * ri;
+    s[4] += ri * zi;
+    s[5] += hi * zi;
+    s[6] += ri * pr * ri;
+  }
+
+  // i / 3 for 32-bit i without an integer division
+  __device__ __forceinline__ uint32_t div3(const uint32_t i) { return __umulhi(i, 0xAAAAAAABu) >> 1; }
+
+  // TMA-unit prefetch of [p, p + bytes) into L2; no register, no scoreboard, no completion
+  __device__ __forceinline__ void l2_prefetch_span(const double *v, const uint32_t begin, const uint32_t end)
+  {
+    if (end <= begin)
+      return;
+    const uint64_t lo = (uint64_t)(v + begin) & ~uint64_t(15);
+    const uint32_t bytes = (uint32_t)((((uint64_t)(v + end) + 15) & ~uint64_t(15)) - lo);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"(bytes) : "memory");
+  }
+
+  // ---------------------------------------------------------------------------------------
+  // The cell kernel.  Every warp does every phase; two (or three) blocks per SM overlap one
+  // block's memory phases with the other's FP64 phases.  The memory phases are kept short:
   //  * the next batch's metadata (27 indices + 24 coefficients per cell) is loaded into
   //    registers before phase 1 and parked in the other half of a double buffer after phase 3;
   //  * the gather issues all loads of the batch before the first use (one latency, not many);
   //  * the scatter reads its table/index/value operands for several DoFs before the REDs go out.
-  template <int P, int CPB>
-  __global__ void __launch_bounds__(kThreads, Cfg<P>::BLOCKS) cell_kernel_plain(const CellArgs a)
+  //
+  // FUSED = LaplaceOperator::vmult_with_merged_sums (poisson_operator.h:327-377) in the cell
+  // loop.  The reference hooks do_cg_update4b "before the first touch" and do_cg_update3b "after
+  // the last touch" of a DoF range into MatrixFree::cell_loop; Renumber(0,1,2) has made the DoFs
+  // touched by exactly one cell-batch range a contiguous run per range
+  // (renumber_dofs_for_mf.h:556-590).  Here a thread block owns whole ranges (a "unit" = a few
+  // consecutive ranges, cut into batches of CPB cells), so those runs are private to the block:
+  //   before the batch that holds a range's first cell is gathered -> do_cg_update4b on the run
+  //   (streamed, coalesced; r, p, x updated in place, h zeroed), one batch ahead of its use;
+  //   after the batch that holds its last cell has been scattered -> __threadfence, barrier,
+  //   do_cg_update3b on the run while h, r, p are still in L2; 7 sums -> warp -> block -> acc.
+  // No counters, no ping-pong buffers, no inter-block ordering.  The DoFs shared between ranges
+  // (and between ranks, and the Dirichlet ones) are the tail [n_private, n_owned) of the vector:
+  // pre_kernel / post_kernel stream them before / after this kernel.
+  // ---------------------------------------------------------------------------------------
+  template <int P, int CPB, bool FUSED>
+  __global__ void __launch_bounds__(kThreads, Cfg<P>::BLOCKS) cell_kernel(const CellArgs a)
   {
     using G         = Geom<P>;
-    constexpr int Q = G::Q, NN = G::N * G::N;
+    constexpr int Q = G::Q;
     // high degrees: phases 1 and 3 as one sweep per 1-D contraction (see phase1a)
     constexpr bool kFine = P >= BP4_FINE_FROM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -113,31 +167,91 @@ namespace bp4
     load_tables<P, CPB>(sm, a.dtab);
     BP4_TICK_INIT
 
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      my_n =
-      n_batches > blockIdx.x ? (int)((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-    auto batch_cells = [&](const int i, uint64_t &cell0) {
-      cell0 = ((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x) * CPB;
-      return (int)min((uint64_t)CPB, a.n_cells - cell0);
+    // ---- work list of this block: a unit is one batch (plain) or the batches
+    // [unit_batch[u], unit_batch[u+1]) of whole ranges (fused).  Units are claimed dynamically
+    // (BP4_DYNAMIC): the first one is blockIdx.x, the following ones come from an atomic counter,
+    // a few units ahead of their use so that the claim's latency never shows.  The two blocks of
+    // an SM run at different speeds (the warp scheduler favours one of them: measured 10.2 vs
+    // 14.1 us per batch at Q4), a static split would leave the slower one with a long tail.
+    struct It
+    {
+      uint32_t j, u, b, b_end; // j = position in this block's unit sequence
+      bool     valid;
     };
+    const uint32_t n_units = FUSED ? a.n_units : (uint32_t)((a.n_cells + CPB - 1) / CPB);
+    const bool     dynamic = BP4_DYNAMIC && a.sched != nullptr;
+    auto           unit_at = [&](const uint32_t j) {
+      return dynamic ? sm.units[j & 7u] : blockIdx.x + j * gridDim.x;
+    };
+    auto claim_ahead = [&](const uint32_t j_cur) { // thread 0 only; visible after the next barrier
+      if (dynamic)
+        while (sm.n_claimed < j_cur + 5u)
+          {
+            sm.units[sm.n_claimed & 7u] = gridDim.x + atomicAdd(a.sched, 1u);
+            ++sm.n_claimed;
+          }
+    };
+    auto enter = [&](It &it) {
+      it.u     = unit_at(it.j);
+      it.valid = it.u < n_units;
+      if (FUSED && it.valid)
+        {
+          it.b     = __ldg(a.unit_batch + it.u);
+          it.b_end = __ldg(a.unit_batch + it.u + 1);
+        }
+    };
+    auto advance = [&](It it) {
+      if (FUSED && it.valid && it.b + 1 < it.b_end)
+        {
+          ++it.b;
+          return it;
+        }
+      if (it.valid)
+        {
+          ++it.j;
+          enter(it);
+        }
+      return it;
+    };
+    struct Batch
+    {
+      uint32_t cell0;
+      int      nc;
+      uint32_t pre_b, pre_e, post_b, post_e;
+    };
+    auto describe = [&](const It &it) {
+      Batch d;
+      if (FUSED)
+        {
+          const uint4 w0 = __ldg(reinterpret_cast<const uint4 *>(a.batch + it.b));
+          const uint4 w1 = __ldg(reinterpret_cast<const uint4 *>(a.batch + it.b) + 1);
+          d.cell0 = w0.x, d.nc = (int)w0.y, d.pre_b = w0.z, d.pre_e = w0.w, d.post_b = w1.x, d.post_e = w1.y;
+        }
+      else
+        {
+          d.cell0 = it.u * CPB;
+          d.nc    = (int)min((uint64_t)CPB, a.n_cells - (uint64_t)d.cell0);
+          d.pre_b = d.pre_e = d.post_b = d.post_e = 0;
+        }
+      return d;
+    };
+
     // metadata items of a batch handled by this thread: at most ME indices and MC coefficients
     constexpr int ME = (CPB * 27 + kThreads - 1) / kThreads, MC = (CPB * 24 + kThreads - 1) / kThreads;
     uint32_t      me[ME];
     double        mc[MC];
-    auto          fetch_meta = [&](const int i) {
-      uint64_t  cell0;
-      const int nc = batch_cells(i, cell0);
+    auto          fetch_meta = [&](const Batch &d) {
 #pragma unroll
       for (int u = 0; u < ME; ++u)
         {
           const int k = tid + u * kThreads;
-          me[u]       = k < nc * 27 ? __ldg(a.entity_index + cell0 * 27 + k) : 0xFFFFFFFFu;
+          me[u]       = k < d.nc * 27 ? __ldg(a.entity_index + (uint64_t)d.cell0 * 27 + k) : 0xFFFFFFFFu;
         }
 #pragma unroll
       for (int u = 0; u < MC; ++u)
         {
           const int k = tid + u * kThreads;
-          mc[u]       = k < nc * 24 ? __ldg(a.coef + cell0 * 24 + k) : 0.;
+          mc[u]       = k < d.nc * 24 ? __ldg(a.coef + (uint64_t)d.cell0 * 24 + k) : 0.;
         }
     };
     auto park_meta = [&](const int bf) {
@@ -156,12 +270,6 @@ namespace bp4
             sm.coef[bf][k / 24][k % 24] = mc[u];
         }
     };
-    if (my_n > 0)
-      {
-        fetch_meta(0);
-        park_meta(0);
-      }
-    __syncthreads();
 
     // gather (vector_access_reduced.h:175-258): consecutive threads walk an entity's contiguous
     // DoF segment.  Thread tid owns elements tid + r * kThreads of EVERY cell of the batch, so the
@@ -169,9 +277,10 @@ namespace bp4
     // offsets: ~7 instructions per element, all loads of the batch in flight together.  Cells
     // missing from a ragged last batch carry invalid entity indices (fetch_meta) and gather zeros.
     // With kPipe the gather is software-pipelined: the loads of batch i+1 are issued
-    // (gather_issue) before the scatter of batch i and land in registers while the scatter runs;
-    // they are stored to the work rows (gather_store) once the scatter has released them.
-    // Measured: Q2 +4 %, Q3 +1 %, Q4 +3 %, Q5 -2 %, Q8 -4 % (the extra live registers spill there).
+    // (gather_issue) right after the scatter of batch i and land in registers while the block
+    // does other memory work; they are stored to the work rows (gather_store) afterwards.
+    // The fused kernel reads the direction through L2 (ld.cg): it was written by this block's
+    // own do_cg_update4b moments ago.
     constexpr bool kPipe = BP4_PIPE_GATHER(P);
     constexpr int R = (G::DOF + kThreads - 1) / kThreads, S = CPB * R;
     // only the last r can run past the end of the cell
@@ -192,7 +301,7 @@ namespace bp4
         }
 #pragma unroll
       for (int s1 = 0; s1 < S; ++s1)
-        gv[s1] = idx[s1] != 0xFFFFFFFFu ? __ldg(a.src + idx[s1]) : 0.;
+        gv[s1] = idx[s1] != 0xFFFFFFFFu ? (FUSED ? __ldcg(a.src + idx[s1]) : __ldg(a.src + idx[s1])) : 0.;
     };
     auto gather_store = [&]() {
       uint32_t tt[R];
@@ -208,12 +317,166 @@ namespace bp4
         }
     };
 
-    for (int i = 0; i < my_n; ++i)
+    // do_cg_update4b<3,double,true> (solver_cg_optimized.h:65-161) on the private run [pb, pe).
+    // The first sweep (KU entries per thread) is split into issue / finish so that its loads
+    // are in flight together with the gather's while the scatter goes out.
+    constexpr int KU = BP4_KU;
+    struct Sweep
+    {
+      double pr[KU], rr[KU], pp[KU], hh[KU], xx[KU];
+    };
+    auto pre_load = [&](Sweep &w, const uint32_t base, const uint32_t pe) {
+#pragma unroll
+      for (int k = 0; k < KU; ++k)
+        {
+          const uint32_t i  = base + k * kThreads;
+          const bool     ok = i < pe;
+          w.pr[k] = ok ? __ldg(a.prec + div3(i)) : 0.;
+          w.rr[k] = ok ? __ldcg(a.r + i) : 0.;
+          w.pp[k] = (ok && !a.first) ? __ldcg(a.p + i) : 0.;
+          w.hh[k] = (ok && !a.first) ? __ldcg(a.dst + i) : 0.;
+          w.xx[k] = (ok && a.update_x) ? __ldcg(a.x + i) : 0.;
+        }
+    };
+    auto pre_store = [&](const Sweep &w, const uint32_t base, const uint32_t pe) {
+#pragma unroll
+      for (int k = 0; k < KU; ++k)
+        {
+          const uint32_t i = base + k * kThreads;
+          if (i < pe)
+            {
+              if (a.first)
+                a.p[i] = -w.pr[k] * w.rr[k];
+              else
+                {
+                  if (a.update_x)
+                    a.x[i] = w.xx[k] + (a.c1 * w.pp[k] + a.c2 * w.pr[k] * w.rr[k]);
+                  const double rn = w.rr[k] + a.alpha * w.hh[k];
+                  a.r[i]          = rn;
+                  a.p[i]          = a.beta * w.pp[k] - w.pr[k] * rn;
+                }
+              a.dst[i] = 0.;
+            }
+        }
+    };
+    // everything after the first sweep (or all of it when `from_first`)
+    auto pre_rest = [&](const uint32_t pb, const uint32_t pe, const bool from_first) {
+      for (uint32_t base = pb + tid + (from_first ? 0 : KU * kThreads); base < pe; base += KU * kThreads)
+        {
+          Sweep w;
+          pre_load(w, base, pe);
+          pre_store(w, base, pe);
+        }
+    };
+    // do_cg_update3b<3,double> (solver_cg_optimized.h:12-61) on the private run [pb, pe)
+    auto post_load = [&](Sweep &w, const uint32_t base, const uint32_t pe) {
+#pragma unroll
+      for (int k = 0; k < KU; ++k)
+        {
+          const uint32_t i  = base + k * kThreads;
+          const bool     ok = i < pe;
+          w.pr[k] = ok ? __ldg(a.prec + div3(i)) : 0.;
+          w.rr[k] = ok ? __ldcg(a.r + i) : 0.;
+          w.pp[k] = ok ? __ldcg(a.p + i) : 0.;
+          w.hh[k] = ok ? __ldcg(a.dst + i) : 0.;
+        }
+    };
+    auto post_finish = [&](const Sweep &first, const uint32_t pb, const uint32_t pe, const bool have_first) {
+      if (pe <= pb)
+        return;
+      double s[7] = {0., 0., 0., 0., 0., 0., 0.};
+      if (have_first)
+#pragma unroll
+        for (int k = 0; k < KU; ++k)
+          post_terms(s, first.rr[k], first.pp[k], first.hh[k], first.pr[k]);
+      for (uint32_t base = pb + tid + (have_first ? KU * kThreads : 0); base < pe; base += KU * kThreads)
+        {
+          Sweep w;
+          post_load(w, base, pe);
+#pragma unroll
+          for (int k = 0; k < KU; ++k)
+            post_terms(s, w.rr[k], w.pp[k], w.hh[k], w.pr[k]);
+        }
+#pragma unroll
+      for (int k = 0; k < 7; ++k)
+        {
+          s[k] = warp_sum(s[k]);
+          if ((tid & 31) == 0)
+            atomicAdd(&sm.red[k], s[k]);
+        }
+    };
+    auto prefetch_pre = [&](const Batch &d) {
+      if (BP4_L2_PREFETCH && tid < 5)
+        {
+          if (tid == 0)
+            l2_prefetch_span(a.r, d.pre_b, d.pre_e);
+          else if (tid == 1 && !a.first)
+            l2_prefetch_span(a.p, d.pre_b, d.pre_e);
+          else if (tid == 2 && !a.first)
+            l2_prefetch_span(a.dst, d.pre_b, d.pre_e);
+          else if (tid == 3 && a.update_x)
+            l2_prefetch_span(a.x, d.pre_b, d.pre_e);
+          else if (tid == 4)
+            l2_prefetch_span(a.prec, div3(d.pre_b), div3(d.pre_e));
+        }
+    };
+
+    // cur = the batch in the work rows, nxt = the one being gathered, nn = the one whose private
+    // runs get their pre-update now (two batches ahead of their gather), n3 = L2 prefetch
+    if (tid == 0)
       {
-        uint64_t  cell0;
-        const int nc = batch_cells(i, cell0), bf = i & 1;
+        sm.units[0]  = blockIdx.x;
+        sm.n_claimed = 1;
+        claim_ahead(0);
+      }
+    // All blocks start together and do the same amount of work per batch, so without help they
+    // reach their memory windows together: HBM sees bursts and idles in between (trace:
+    // 0..294 of 296 blocks in the window at any one time).  A start offset spread over about one
+    // batch period de-phases them once; with equal periods they stay de-phased.
+    if (a.stagger_ns)
+      __nanosleep((unsigned)(((unsigned long long)(blockIdx.x * 2654435761u) * a.stagger_ns) >> 32));
+    __syncthreads();
+    It cur_it;
+    cur_it.j = 0, cur_it.b = cur_it.b_end = 0;
+    enter(cur_it);
+    Batch cur{}, nxt{}, nn{};
+    It    nxt_it = cur_it, nn_it = cur_it;
+    if (cur_it.valid)
+      {
+        cur = describe(cur_it);
+        fetch_meta(cur);
+        park_meta(0);
+        nxt_it = advance(cur_it);
+        nn_it  = nxt_it;
+        if (nxt_it.valid)
+          {
+            nxt   = describe(nxt_it);
+            nn_it = advance(nxt_it);
+            if (nn_it.valid)
+              nn = describe(nn_it);
+          }
+        if (FUSED)
+          {
+            pre_rest(cur.pre_b, cur.pre_e, true);
+            if (nxt_it.valid)
+              pre_rest(nxt.pre_b, nxt.pre_e, true);
+            if (nn_it.valid)
+              prefetch_pre(nn);
+          }
+      }
+    __syncthreads();
+    if (kPipe && cur_it.valid)
+      {
+        gather_issue(0);
+        gather_store();
+      }
+    uint32_t done_b = 0, done_e = 0; // private runs completed by the previous batch: post pending
+
+    for (int i = 0; cur_it.valid; ++i)
+      {
+        const int nc = cur.nc, bf = i & 1;
         BP4_TICK(0)
-        if (!kPipe || i == 0)
+        if (!kPipe)
           {
             gather_issue(bf);
             gather_store();
@@ -221,8 +484,12 @@ namespace bp4
         BP4_TICK(1)
         __syncthreads();
         BP4_TICK(2)
-        if (i + 1 < my_n)
-          fetch_meta(i + 1); // lands during the phases
+        BP4_TRACE(i, 0)
+        BP4_TRACE(i, 4)
+        if (tid == 0)
+          claim_ahead(cur_it.j);
+        if (nxt_it.valid)
+          fetch_meta(nxt); // lands during the phases
         // phase 1/3 items are handed out from the LAST thread downwards: the ragged final round
         // of phase 2 lands on the first warps, so the two kinds of partial rounds end up on
         // different warps (= different SM sub-partitions) instead of piling up on warp 0
@@ -280,460 +547,105 @@ namespace bp4
             for (int it = tid; it < n_rows * G::N; it += kThreads)
               phase3c<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
           }
-        if (i + 1 < my_n)
+        if (nxt_it.valid)
           park_meta(bf ^ 1);
+        // the previous batch's REDs and this block's earlier pre-updates were issued a whole
+        // batch ago: the fence that orders them before the loads below has nothing to wait for
+        if (FUSED)
+          __threadfence();
         BP4_TICK(5)
         __syncthreads();
         BP4_TICK(2)
+        BP4_TRACE(i, 1)
+        // ---- memory window.  Loads are issued in groups that stay in flight together: the
+        // finished ranges' r, p, h (post) with the next batch's gather, then the scatter goes out
+        // while they travel; the pre-update's operands are requested before the barrier that
+        // releases the work rows and consumed after the gathered values have been parked.
+        Sweep      wpost, wpre;
+        const bool do_pre  = FUSED && nn_it.valid && nn.pre_e > nn.pre_b;
+        const bool do_post = FUSED && done_e > done_b;
+        if (do_post)
+          post_load(wpost, done_b + tid, done_e);
+        if (kPipe && nxt_it.valid)
+          gather_issue(bf ^ 1); // the next batch's DoFs (pre-updated one round ago)
         // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13) is
         // touched by this cell only -> plain store
-        if (kPipe && i + 1 < my_n)
-          gather_issue(bf ^ 1); // in flight during the scatter
-        constexpr int SU = BP4_SU;
-        uint32_t      tt[R];
+        {
+          constexpr int SU = BP4_SU;
+          uint32_t      tt[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-          tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
+          for (int r = 0; r < R; ++r)
+            tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
 #pragma unroll
-        for (int s0 = 0; s0 < S; s0 += SU)
-          {
-            double   v[SU];
-            uint32_t adr[SU];
+          for (int s0 = 0; s0 < S; s0 += SU)
+            {
+              double   v[SU];
+              uint32_t adr[SU];
 #pragma unroll
-            for (int u = 0; u < SU; ++u)
-              if (s0 + u < S)
-                {
-                  const int      cell = (s0 + u) / R, r = (s0 + u) % R;
-                  const uint32_t base = sm.eidx[bf][cell][dtab_ent(tt[r])];
-                  adr[u] = on(r) && base != 0xFFFFFFFFu ? base + dtab_rel(tt[r]) : 0xFFFFFFFFu;
-                  v[u]   = sm.work[cell * G::WORK + dtab_off_work<P>(tt[r])];
-                }
+              for (int u = 0; u < SU; ++u)
+                if (s0 + u < S)
+                  {
+                    const int      cell = (s0 + u) / R, r = (s0 + u) % R;
+                    const uint32_t base = sm.eidx[bf][cell][dtab_ent(tt[r])];
+                    adr[u] = on(r) && base != 0xFFFFFFFFu ? base + dtab_rel(tt[r]) : 0xFFFFFFFFu;
+                    v[u]   = sm.work[cell * G::WORK + dtab_off_work<P>(tt[r])];
+                  }
 #pragma unroll
-            for (int u = 0; u < SU; ++u)
-              if (s0 + u < S && adr[u] != 0xFFFFFFFFu)
-                {
-                  if (dtab_ent(tt[(s0 + u) % R]) == 13u)
-                    a.dst[adr[u]] = v[u];
-                  else
-                    atomicAdd(a.dst + adr[u], v[u]);
-                }
-          }
+              for (int u = 0; u < SU; ++u)
+                if (s0 + u < S && adr[u] != 0xFFFFFFFFu)
+                  {
+                    if (dtab_ent(tt[(s0 + u) % R]) == 13u)
+                      a.dst[adr[u]] = v[u];
+                    else
+                      atomicAdd(a.dst + adr[u], v[u]);
+                  }
+            }
+        }
         BP4_TICK(6)
+        BP4_TRACE(i, 2)
+        const It n3_it = nn_it.valid ? advance(nn_it) : nn_it;
+        Batch    n3{};
+        if (n3_it.valid)
+          n3 = describe(n3_it);
+        if (FUSED)
+          {
+            post_finish(wpost, done_b, done_e, do_post);
+            if (do_pre)
+              pre_load(wpre, nn.pre_b + tid, nn.pre_e);
+          }
+        BP4_TICK(7)
         __syncthreads();
         BP4_TICK(2)
-        if (kPipe && i + 1 < my_n)
+        BP4_TRACE(i, 3)
+        if (kPipe && nxt_it.valid)
           gather_store(); // the barrier after it is the one at the top of the next iteration
+        if (FUSED)
+          {
+            if (do_pre)
+              {
+                pre_store(wpre, nn.pre_b + tid, nn.pre_e);
+                pre_rest(nn.pre_b, nn.pre_e, false);
+              }
+            if (n3_it.valid)
+              prefetch_pre(n3);
+            done_b = cur.post_b, done_e = cur.post_e;
+          }
+        cur_it = nxt_it, cur = nxt;
+        nxt_it = nn_it, nxt = nn;
+        nn_it = n3_it, nn = n3;
+      }
+    if (FUSED)
+      {
+        // the last batch's private runs
+        __threadfence();
+        __syncthreads();
+        Sweep w;
+        post_finish(w, done_b, done_e, false);
+        __syncthreads();
+        if (tid < 7)
+          atomicAdd(a.acc + tid, sm.red[tid]);
       }
     BP4_TICK_FLUSH
-  }
-
-  template <int P, int CPB>
-  __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_pf(const CellArgs a)
-  {
-    using G         = Geom<P>;
-    constexpr int Q = G::Q;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PfSmem<P, CPB> &sm  = *reinterpret_cast<PfSmem<P, CPB> *>(smem_raw);
-    const int       tid = threadIdx.x;
-    const Tab<P>   &tb  = c_tab<P>;
-    for (int i = tid; i < G::DOF; i += kThreads)
-      sm.dtab[i] = a.dtab[i];
-    if (tid < Q)
-      {
-        sm.xq[tid] = tb.xq[tid];
-        sm.wq[tid] = tb.wq[tid];
-      }
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      my_n =
-      n_batches > blockIdx.x ? (int)((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-    auto batch_cells = [&](const int i, uint64_t &cell0) {
-      cell0 = ((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x) * CPB;
-      return (int)min((uint64_t)CPB, a.n_cells - cell0);
-    };
-    auto load_meta = [&](const int i) {
-      uint64_t  cell0;
-      const int nc = batch_cells(i, cell0), bf = i & 1;
-      for (int k = tid; k < nc * 27; k += kThreads)
-        sm.eidx[bf][k / 27][k % 27] = a.entity_index[cell0 * 27 + k];
-      for (int k = tid; k < nc * 24; k += kThreads)
-        sm.coef[bf][k / 24][k % 24] = a.coef[cell0 * 24 + k];
-    };
-    // asynchronous gather of batch i into sm.dofs (vector_access_reduced.h:175-258)
-    auto issue_gather = [&](const int i) {
-      uint64_t  cell0;
-      const int nc = batch_cells(i, cell0), bf = i & 1;
-      const int total = nc * G::DOF;
-      for (int m = tid; m < total; m += kThreads)
-        {
-          const int      cell = m / G::DOF;
-          const uint32_t t    = sm.dtab[m - cell * G::DOF];
-          const uint32_t base = sm.eidx[bf][cell][dtab_ent(t)];
-          const bool     ok   = base != 0xFFFFFFFFu;
-          const double  *g    = a.src + (ok ? (size_t)base + dtab_rel(t) : 0);
-          const uint32_t sa =
-            (uint32_t)__cvta_generic_to_shared(sm.dofs + cell * G::DOFS + dtab_off<P>(t));
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g), "r"(ok ? 8 : 0)
-                       : "memory");
-        }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    if (my_n > 0)
-      load_meta(0);
-    __syncthreads();
-    if (my_n > 0)
-      issue_gather(0);
-
-    for (int i = 0; i < my_n; ++i)
-      {
-        uint64_t  cell0;
-        const int nc = batch_cells(i, cell0), bf = i & 1;
-        if (i + 1 < my_n)
-          load_meta(i + 1);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-          phase1<P>(tb, sm.dofs + it * G::RD, sm.work + it * G::RW);
-        __syncthreads();
-        if (i + 1 < my_n)
-          issue_gather(i + 1);
-        {
-          // full rounds first; the ragged tail rotates over the warps from batch to batch
-          const int n2 = nc * G::ITEMS2, full = (n2 / kThreads) * kThreads;
-          const int rot = (tid + 32 * (i & 3)) & (kThreads - 1);
-          for (int it = tid; it < full + kThreads; it += kThreads)
-            {
-              const int item = it < full ? it : full + rot;
-              if (item < n2)
-                {
-                  const int cell = item / G::ITEMS2, r = item % G::ITEMS2;
-                  const int qz = r / Q, qx = r % Q;
-                  phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
-                            sm.wq[qx] * sm.wq[qz]);
-                }
-            }
-        }
-        __syncthreads();
-        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-          phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
-        __syncthreads();
-        // scatter-add (vector_access_reduced.h:437-521); interior entity: plain store
-        const int total = nc * G::DOF;
-        for (int m = tid; m < total; m += kThreads)
-          {
-            const int      cell = m / G::DOF;
-            const uint32_t t    = sm.dtab[m - cell * G::DOF];
-            const uint32_t ent  = dtab_ent(t);
-            const uint32_t base = sm.eidx[bf][cell][ent];
-            if (base != 0xFFFFFFFFu)
-              {
-                const double v = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
-                double      *p = a.dst + (size_t)base + dtab_rel(t);
-                if (ent == 13u)
-                  *p = v;
-                else
-                  atomicAdd(p, v);
-              }
-          }
-        __syncthreads();
-      }
-  }
-
-  template <int P, int CPB>
-  __global__ void __launch_bounds__(kTrioThreads, kBlocksPerSM) cell_kernel_trio(const CellArgs a)
-  {
-    using G         = Geom<P>;
-    constexpr int Q = G::Q;
-    constexpr int T = kTrioThreads;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
-    const int         tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const Tab<P>     &tb  = c_tab<P>;
-    for (int i = tid; i < G::DOF; i += T)
-      sm.dtab[i] = a.dtab[i];
-    if (tid < Q)
-      {
-        sm.xq[tid] = tb.xq[tid];
-        sm.wq[tid] = tb.wq[tid];
-      }
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    for (uint64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x)
-      {
-        const uint64_t cell0 = batch * CPB;
-        const int      nc    = (int)min((uint64_t)CPB, a.n_cells - cell0);
-        for (int i = tid; i < nc * 27; i += T)
-          sm.eidx[0][i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
-        for (int i = tid; i < nc * 24; i += T)
-          sm.coef[0][i / 24][i % 24] = a.coef[cell0 * 24 + i];
-        __syncthreads();
-        constexpr int U     = 6;
-        const int     total = nc * G::DOF;
-        for (int m0 = tid; m0 < total; m0 += T * U)
-          {
-            double   v[U];
-            uint32_t off[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-              {
-                const int m = m0 + u * T;
-                v[u]        = 0.;
-                off[u]      = 0;
-                if (m < total)
-                  {
-                    const int      cell = m / G::DOF;
-                    const uint32_t t    = sm.dtab[m - cell * G::DOF];
-                    const uint32_t base = sm.eidx[0][cell][dtab_ent(t)];
-                    off[u]              = cell * G::WORK + dtab_off_work<P>(t);
-                    if (base != 0xFFFFFFFFu)
-                      v[u] = __ldg(a.src + (size_t)base + dtab_rel(t));
-                  }
-              }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-              if (m0 + u * T < total)
-                sm.work[off[u]] = v[u];
-          }
-        __syncthreads();
-        for (int it = tid; it < nc * G::ITEMS13; it += T)
-          phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
-        __syncthreads();
-        {
-          // 10 trios (lines) per warp, lanes 30 and 31 idle; every warp runs the same number of
-          // rounds so that the shuffles are always executed by the full trio mask
-          const int n_lines = nc * G::ITEMS2;
-          const int rounds  = (n_lines + 10 * (T / 32) - 1) / (10 * (T / 32));
-          const int trio = lane / 3, c = lane - 3 * trio;
-          for (int r = 0; r < rounds; ++r)
-            {
-              if (lane < 30)
-                {
-                  const int  line   = (r * (T / 32) + warp) * 10 + trio;
-                  const bool active = line < n_lines;
-                  const int  l      = active ? line : 0;
-                  const int  cell = l / G::ITEMS2, rr = l % G::ITEMS2;
-                  const int  qz = rr / Q, qx = rr % Q;
-                  phase2_trio<P>(tb, sm.coef[0][cell], sm.work + cell * G::WORK, qx, qz, c, 3 * trio, 0x3FFFFFFFu,
-                                 active, sm.xq[qx], sm.xq[qz], sm.wq[qx] * sm.wq[qz]);
-                }
-            }
-        }
-        __syncthreads();
-        for (int it = tid; it < nc * G::ITEMS13; it += T)
-          phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
-        __syncthreads();
-        for (int m = tid; m < total; m += T)
-          {
-            const int      cell = m / G::DOF;
-            const uint32_t t    = sm.dtab[m - cell * G::DOF];
-            const uint32_t ent  = dtab_ent(t);
-            const uint32_t base = sm.eidx[0][cell][ent];
-            if (base != 0xFFFFFFFFu)
-              {
-                const double v = sm.work[cell * G::WORK + dtab_off_work<P>(t)];
-                double      *p = a.dst + (size_t)base + dtab_rel(t);
-                if (ent == 13u)
-                  *p = v;
-                else
-                  atomicAdd(p, v);
-              }
-          }
-        __syncthreads();
-      }
-  }
-
-  // ---- mbarrier / bulk-copy wrappers (PTX ISA: mbarrier, cp.async.bulk, cp.reduce.async.bulk) ----
-  __device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count)
-  {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __device__ __forceinline__ void mbar_arrive(const uint32_t bar)
-  {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-  }
-  __device__ __forceinline__ void mbar_arrive_expect_tx(const uint32_t bar, const uint32_t bytes)
-  {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-  }
-  __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t parity)
-  {
-    asm volatile("{\n\t.reg .pred p;\n"
-                 "WAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@p bra DONE_%=;\n\t"
-                 "bra WAIT_%=;\n"
-                 "DONE_%=:\n\t}" ::"r"(bar),
-                 "r"(parity)
-                 : "memory");
-  }
-  __device__ __forceinline__ void bulk_load(const uint32_t smem_dst, const void *gmem_src, const uint32_t bytes,
-                                            const uint32_t bar)
-  {
-    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
-                 "l"(gmem_src), "r"(bytes), "r"(bar)
-                 : "memory");
-  }
-  __device__ __forceinline__ void bulk_reduce_add_f64(void *gmem_dst, const uint32_t smem_src, const uint32_t bytes)
-  {
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gmem_dst),
-                 "r"(smem_src), "r"(bytes)
-                 : "memory");
-  }
-
-  template <int P, int CPB>
-  __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_tma(const TmaArgs a)
-  {
-    using G          = Geom<P>;
-    using St         = Stage<P>;
-    constexpr int Q  = G::Q;
-    constexpr int NN = G::N * G::N;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TmaSmem<P, CPB> &sm   = *reinterpret_cast<TmaSmem<P, CPB> *>(smem_raw);
-    const int        tid  = threadIdx.x;
-    const Tab<P>    &tb   = c_tab<P>;
-    const uint32_t   mbar = (uint32_t)__cvta_generic_to_shared(&sm.mbar);
-    for (int i = tid; i < NN * G::ROWS; i += kThreads)
-      sm.itab[i] = a.itab[i];
-    if (tid < 27)
-      sm.slot[tid] = a.slot[tid];
-    if (tid < Q)
-      {
-        sm.xq[tid] = tb.xq[tid];
-        sm.wq[tid] = tb.wq[tid];
-      }
-    if (tid == 0)
-      mbar_init(mbar, CPB * 27); // every (cell, entity) item arrives once per batch
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      my_n =
-      n_batches > blockIdx.x ? (int)((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-    auto batch_cells = [&](const int i, uint64_t &cell0) {
-      cell0 = ((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x) * CPB;
-      return (int)min((uint64_t)CPB, a.n_cells - cell0);
-    };
-    auto load_meta = [&](const int i) {
-      uint64_t  cell0;
-      const int nc = batch_cells(i, cell0), bf = i & 1;
-      for (int k = tid; k < nc * 27; k += kThreads)
-        sm.eidx[bf][k / 27][k % 27] = a.entity_index[cell0 * 27 + k];
-      for (int k = tid; k < nc * 24; k += kThreads)
-        sm.coef[bf][k / 24][k % 24] = a.coef[cell0 * 24 + k];
-    };
-    // gather of batch i: one bulk copy per valid entity, zero-fill for Dirichlet entities
-    auto issue_loads = [&](const int i) {
-      uint64_t  cell0;
-      const int nc = batch_cells(i, cell0), bf = i & 1;
-      for (int k = tid; k < CPB * 27; k += kThreads)
-        {
-          const int cell = k / 27, e = k % 27;
-          if (cell >= nc)
-            {
-              mbar_arrive(mbar);
-              continue;
-            }
-          const uint32_t b    = sm.eidx[bf][cell][e];
-          const uint32_t slot = sm.slot[e];
-          const int      n    = St::n_dofs(e);
-          double        *dst  = sm.stage_in + cell * St::SIZE + slot;
-          if (b == 0xFFFFFFFFu)
-            {
-              sm.off[bf][cell][e] = (uint16_t)slot;
-              for (int q = 0; q < n; ++q)
-                dst[q] = 0.;
-              mbar_arrive(mbar);
-            }
-          else
-            {
-              const uint32_t par  = b & 1u;
-              sm.off[bf][cell][e] = (uint16_t)(slot + par);
-              const uint32_t bytes = (uint32_t)St::r2(n + (int)par) * 8u;
-              mbar_arrive_expect_tx(mbar, bytes);
-              bulk_load((uint32_t)__cvta_generic_to_shared(dst), a.src + (b - par), bytes, mbar);
-            }
-        }
-    };
-
-    if (my_n > 0)
-      load_meta(0);
-    __syncthreads();
-    if (my_n > 0)
-      issue_loads(0);
-
-    for (int i = 0; i < my_n; ++i)
-      {
-        uint64_t  cell0;
-        const int nc = batch_cells(i, cell0), bf = i & 1;
-        mbar_wait(mbar, (uint32_t)(i & 1));                               // stage_in(i) has landed
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // reduces of batch i-1 left stage_out
-        __syncthreads();
-        if (i + 1 < my_n)
-          load_meta(i + 1);
-        // pads of the output stage must add 0.0
-        for (int k = tid; k < nc * 27; k += kThreads)
-          {
-            const int cell = k / 27, e = k % 27;
-            double   *o    = sm.stage_out + cell * St::SIZE + sm.slot[e];
-            const int n    = St::n_dofs(e);
-            o[0]           = 0.;
-            o[n]           = 0.;
-            o[n + 1]       = 0.;
-          }
-        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-          {
-            const int cell = it / G::ROWS, row = it % G::ROWS;
-            phase1_io<P>(tb, StageIn{sm.stage_in + cell * St::SIZE, sm.itab, sm.off[bf][cell], row, G::ROWS},
-                         sm.work + it * G::RW);
-          }
-        __syncthreads();
-        if (i + 1 < my_n)
-          issue_loads(i + 1);
-        {
-          const int n2 = nc * G::ITEMS2, full = (n2 / kThreads) * kThreads;
-          const int rot = (tid + 32 * (i & 3)) & (kThreads - 1);
-          for (int it = tid; it < full + kThreads; it += kThreads)
-            {
-              const int item = it < full ? it : full + rot;
-              if (item < n2)
-                {
-                  const int cell = item / G::ITEMS2, r = item % G::ITEMS2;
-                  const int qz = r / Q, qx = r % Q;
-                  phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
-                            sm.wq[qx] * sm.wq[qz]);
-                }
-            }
-        }
-        __syncthreads();
-        for (int it = tid; it < nc * G::ITEMS13; it += kThreads)
-          {
-            const int cell = it / G::ROWS, row = it % G::ROWS;
-            phase3_io<P>(tb, sm.work + it * G::RW,
-                         StageOut{sm.stage_out + cell * St::SIZE, sm.itab, sm.off[bf][cell], row, G::ROWS});
-          }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes -> async proxy reads
-        __syncthreads();
-        // scatter-add: one bulk reduction per valid entity
-        for (int k = tid; k < nc * 27; k += kThreads)
-          {
-            const int      cell = k / 27, e = k % 27;
-            const uint32_t b    = sm.eidx[bf][cell][e];
-            if (b == 0xFFFFFFFFu)
-              continue;
-            const uint32_t par   = b & 1u;
-            const uint32_t bytes = (uint32_t)St::r2(St::n_dofs(e) + (int)par) * 8u;
-            bulk_reduce_add_f64(a.dst + (b - par),
-                                (uint32_t)__cvta_generic_to_shared(sm.stage_out + cell * St::SIZE + sm.slot[e]),
-                                bytes);
-          }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-
-  __device__ __forceinline__ double warp_sum(double v)
-  {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
   }
 
   // block-reduce K partial sums and atomically add them to acc[0..K)
@@ -764,659 +676,26 @@ namespace bp4
       }
   }
 
-  // the seven merged sums of do_cg_update3b (solver_cg_optimized.h:37-44) for one entry
-  __device__ __forceinline__ void post_terms(double (&s)[7], const double ri, const double di,
-                                             const double hi, const double pr)
-  {
-    const double zi = pr * hi;
-    s[0] += di * hi;
-    s[1] += hi * hi;
-    s[2] += ri * hi;
-    s[3] += ri * ri;
-    s[4] += ri * zi;
-    s[5] += hi * zi;
-    s[6] += ri * pr * ri;
-  }
-
-  // Fused merged kernel = LaplaceOperator::vmult_with_merged_sums (poisson_operator.h:327-377)
-  // in ONE launch.  The reference runs do_cg_update4b on a DoF range "before its first
-  // touch" and do_cg_update3b "after its last touch" of a sequential cell loop; thread blocks
-  // have no such order, so
-  //   pre : every cell recomputes r' = r + alpha h, p' = beta p - P r' for the DoFs it gathers
-  //         from read-only old buffers; the entity's OWNER cell writes r', p' (to the ping-pong
-  //         partners) and x (in place).
-  //   post: cells scatter-add into h'; after a __threadfence each cell bumps one arrival
-  //         counter per shared entity; the cell that completes an entity (last toucher) reads
-  //         h', r', p' back through L2, accumulates the seven sums and zeroes the entity's
-  //         slots in the old h buffer, which is next iteration's h'.  Cell-interior DoFs
-  //         (touched once) are plain-stored and summed straight from shared memory.
-  template <int P, int CPB>
-  __global__ void __launch_bounds__(kThreads, kBlocksPerSM) cell_kernel_merged(const MergedArgs a)
-  {
-    using G = Geom<P>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
-    const int         tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    load_tables<P, CPB>(sm, a.dtab);
-    double     s[7]     = {0., 0., 0., 0., 0., 0., 0.};
-    const bool first_it = a.alpha == 0.;
-
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    for (uint64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x)
-      {
-        const uint64_t cell0 = batch * CPB;
-        const int      nc    = (int)min((uint64_t)CPB, a.n_cells - cell0);
-        for (int i = tid; i < nc * 27; i += kThreads)
-          {
-            sm.eidx[0][i / 27][i % 27] = a.entity_index[cell0 * 27 + i];
-            sm.meta[i / 27][i % 27] = a.meta[cell0 * 28 + (i / 27) * 28 + i % 27];
-          }
-        for (int i = tid; i < nc * 24; i += kThreads)
-          sm.coef[0][i / 24][i % 24] = a.coef[cell0 * 24 + i];
-        if (tid == 0)
-          sm.n_chunks = 0;
-        __syncthreads();
-
-        // gather + do_cg_update4b (solver_cg_optimized.h:65-161)
-        for (int cell = 0; cell < nc; ++cell)
-          {
-            const uint32_t *eidx = sm.eidx[0][cell];
-            const uint8_t  *meta = sm.meta[cell];
-            double         *dofs = sm.work + cell * G::WORK;
-            for (int r0 = tid; r0 < G::DOF; r0 += kThreads * kGatherUnroll)
-              {
-                double   rv[kGatherUnroll], pv[kGatherUnroll], hv[kGatherUnroll], dv[kGatherUnroll];
-                uint32_t t[kGatherUnroll], adr[kGatherUnroll];
-                bool     own[kGatherUnroll];
-#pragma unroll
-                for (int u = 0; u < kGatherUnroll; ++u)
-                  {
-                    const int r = r0 + u * kThreads;
-                    adr[u]      = 0xFFFFFFFFu;
-                    own[u]      = false;
-                    rv[u] = pv[u] = hv[u] = dv[u] = 0.;
-                    if (r < G::DOF)
-                      {
-                        t[u]                = sm.dtab[r];
-                        const uint32_t ent  = dtab_ent(t[u]);
-                        const uint32_t base = eidx[ent];
-                        if (base != 0xFFFFFFFFu)
-                          {
-                            adr[u] = base + dtab_rel(t[u]);
-                            own[u] = (meta[ent] & kMetaOwner) != 0;
-                            rv[u]  = a.r_old[adr[u]];
-                            dv[u]  = a.prec[adr[u] / 3u];
-                            if (!first_it)
-                              {
-                                pv[u] = a.p_old[adr[u]];
-                                hv[u] = a.h_old[adr[u]];
-                              }
-                          }
-                      }
-                  }
-#pragma unroll
-                for (int u = 0; u < kGatherUnroll; ++u)
-                  if (r0 + u * kThreads < G::DOF)
-                    {
-                      double pn = 0.;
-                      if (adr[u] != 0xFFFFFFFFu)
-                        {
-                          const double pr = dv[u];
-                          double       ri = rv[u];
-                          if (own[u] && a.update_x)
-                            a.x[adr[u]] += a.c1 * pv[u] + a.c2 * pr * ri;
-                          if (first_it)
-                            pn = -pr * ri;
-                          else
-                            {
-                              ri += a.alpha * hv[u];
-                              pn = a.beta * pv[u] - pr * ri;
-                            }
-                          if (own[u])
-                            {
-                              a.r_new[adr[u]] = ri;
-                              a.p_new[adr[u]] = pn;
-                            }
-                        }
-                      dofs[dtab_off_work<P>(t[u])] = pn;
-                    }
-              }
-          }
-        __syncthreads();
-
-        apply_staged<P, CPB>(sm, nc);
-
-        // scatter: shared entities through L2 atomics, the interior entity by plain store
-        // with its do_cg_update3b terms taken on the spot
-        for (int cell = 0; cell < nc; ++cell)
-          {
-            const uint32_t *eidx = sm.eidx[0][cell];
-            const double   *dofs = sm.work + cell * G::WORK;
-            for (int r0 = tid; r0 < G::DOF; r0 += kThreads * kGatherUnroll)
-              {
-                double rv[kGatherUnroll], pv[kGatherUnroll], dv[kGatherUnroll], hv[kGatherUnroll];
-                bool   inner[kGatherUnroll];
-#pragma unroll
-                for (int u = 0; u < kGatherUnroll; ++u)
-                  {
-                    const int r = r0 + u * kThreads;
-                    inner[u]    = false;
-                    if (r < G::DOF)
-                      {
-                        const uint32_t t    = sm.dtab[r];
-                        const uint32_t ent  = dtab_ent(t);
-                        const uint32_t base = eidx[ent];
-                        if (base != 0xFFFFFFFFu)
-                          {
-                            const double   v   = dofs[dtab_off_work<P>(t)];
-                            const uint32_t adr = base + dtab_rel(t);
-                            if (ent == 13u)
-                              {
-                                a.h_new[adr] = v;
-                                inner[u]     = true;
-                                hv[u]        = v;
-                                rv[u]        = __ldcg(a.r_new + adr);
-                                pv[u]        = __ldcg(a.p_new + adr);
-                                dv[u]        = a.prec[adr / 3u];
-                              }
-                            else
-                              atomicAdd(a.h_new + adr, v);
-                          }
-                      }
-                  }
-#pragma unroll
-                for (int u = 0; u < kGatherUnroll; ++u)
-                  if (inner[u])
-                    post_terms(s, rv[u], pv[u], hv[u], dv[u]);
-              }
-          }
-        __threadfence();
-        __syncthreads();
-
-        // arrival counters: one per shared entity, wrapping at the number of touching cells
-        for (int i = tid; i < nc * 27; i += kThreads)
-          {
-            const int      cell = i / 27, ent = i % 27;
-            const uint32_t base = sm.eidx[0][cell][ent];
-            if (ent == 13 || base == 0xFFFFFFFFu)
-              continue;
-            const uint32_t nt   = (sm.meta[cell][ent] & 15u); // touching cells - 1
-            bool           last = true;
-            if (nt > 0)
-              {
-                last = atomicInc(a.counters + base / 3u, nt) == nt;
-                if (last)
-                  __threadfence();
-              }
-            if (last)
-              {
-                const int ex = ent % 3, ey = (ent / 3) % 3, ez = ent / 9;
-                const int nd = 3 * (ex == 1 ? P - 1 : 1) * (ey == 1 ? P - 1 : 1) * (ez == 1 ? P - 1 : 1);
-                const int nch  = (nd + 31) >> 5;
-                const uint32_t slot = atomicAdd(&sm.n_chunks, (uint32_t)nch);
-                for (int k = 0; k < nch; ++k)
-                  {
-                    sm.chunk_base[slot + k] = base + 32u * k;
-                    sm.chunk_len[slot + k]  = (uint8_t)min(32, nd - 32 * k);
-                  }
-              }
-          }
-        __syncthreads();
-
-        // do_cg_update3b (solver_cg_optimized.h:12-61) on the entities completed by this block
-        const int n_chunks = (int)sm.n_chunks;
-        for (int ch0 = warp; ch0 < n_chunks; ch0 += 4 * (kThreads / 32))
-          {
-            double rv[4], pv[4], hv[4], dv[4];
-            bool   ok[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              {
-                const int ch = ch0 + u * (kThreads / 32);
-                ok[u]        = ch < n_chunks && lane < (int)sm.chunk_len[ch < n_chunks ? ch : 0];
-                if (ok[u])
-                  {
-                    const uint32_t adr = sm.chunk_base[ch] + lane;
-                    hv[u]              = __ldcg(a.h_new + adr);
-                    rv[u]              = __ldcg(a.r_new + adr);
-                    pv[u]              = __ldcg(a.p_new + adr);
-                    dv[u]              = a.prec[adr / 3u];
-                    a.h_old[adr]       = 0.;
-                  }
-              }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (ok[u])
-                post_terms(s, rv[u], pv[u], hv[u], dv[u]);
-          }
-        __syncthreads();
-      }
-    block_accumulate<7>(s, a.acc);
-  }
-
-  // ---------------------------------------------------------------------------------------
-  // warp-specialised cell kernel (plain and merged)
-  // ---------------------------------------------------------------------------------------
-  enum : int
-  {
-    kBarInFull  = 1, // memory -> compute : dofs of batch i gathered
-    kBarInFree  = 2, // compute -> memory : phase 1 done, dofs may be overwritten
-    kBarOutFull = 3, // compute -> memory : phase 3 results of batch i are in the work rows
-    kBarOutFree = 4, // memory -> compute : results read, work rows may be overwritten
-    kBarCompute = 5, // compute warpgroup only
-    kBarMemory  = 6  // memory warpgroup only
-  };
-  __device__ __forceinline__ void bar_sync(const int id, const int n)
-  {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-  }
-  __device__ __forceinline__ void bar_arrive(const int id, const int n)
-  {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
-  }
-
-  struct WsArgs
-  {
-    // mesh
-    const uint32_t *entity_index;
-    const double   *coef;
-    const uint32_t *dtab;
-    uint64_t        n_cells;
-    // plain: dst += A src
-    const double *src;
-    double       *dst;
-    // merged (see MergedArgs)
-    const uint8_t *meta;
-    uint32_t      *counters;
-    const double  *r_old, *p_old;
-    double        *h_old, *r_new, *p_new, *h_new, *x;
-    const double  *prec;
-    double         alpha, beta, c1, c2;
-    int            update_x;
-    double        *acc;
-  };
-
-  template <int P, int CPB, bool MERGED>
-  __global__ void __launch_bounds__(kWsThreads, kBlocksPerSM) cell_kernel_ws(const WsArgs a)
-  {
-    using G         = Geom<P>;
-    constexpr int Q = G::Q;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WsSmem<P, CPB> &sm  = *reinterpret_cast<WsSmem<P, CPB> *>(smem_raw);
-    const int       tid = threadIdx.x;
-    for (int i = tid; i < G::DOF; i += kWsThreads)
-      sm.dtab[i] = a.dtab[i];
-    if (tid < Q)
-      {
-        sm.xq[tid] = c_tab<P>.xq[tid];
-        sm.wq[tid] = c_tab<P>.wq[tid];
-      }
-    __syncthreads();
-
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      my_n =
-      n_batches > blockIdx.x ? (int)((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-    auto batch_cells = [&](const int i, uint64_t &cell0) {
-      cell0 = ((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x) * CPB;
-      return (int)min((uint64_t)CPB, a.n_cells - cell0);
-    };
-
-    if (tid >= 128)
-      {
-        // =========================== memory warpgroup ===================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsRegsMem));
-        const int  t = tid - 128, lane = t & 31, warp = t >> 5;
-        double     s[7]     = {0., 0., 0., 0., 0., 0., 0.};
-        const bool first_it = a.alpha == 0.;
-        constexpr int U     = MERGED ? 2 : 8;
-        for (int i = 0; i <= my_n; ++i)
-          {
-            if (i < my_n)
-              {
-                if (i > 0)
-                  bar_sync(kBarInFree, kWsThreads);
-                uint64_t  cell0;
-                const int nc = batch_cells(i, cell0);
-                const int bf = i & 1;
-                for (int k = t; k < nc * 27; k += 128)
-                  {
-                    sm.eidx[bf][k / 27][k % 27] = a.entity_index[cell0 * 27 + k];
-                    if (MERGED)
-                      sm.meta[bf][k / 27][k % 27] = a.meta[cell0 * 28 + (k / 27) * 28 + k % 27];
-                  }
-                for (int k = t; k < nc * 24; k += 128)
-                  sm.coef[bf][k / 24][k % 24] = a.coef[cell0 * 24 + k];
-                bar_sync(kBarMemory, 128);
-                // gather (+ do_cg_update4b, solver_cg_optimized.h:65-161)
-                const int total = nc * G::DOF;
-                for (int m0 = t; m0 < total; m0 += 128 * U)
-                  {
-                    if (!MERGED)
-                      {
-                        // asynchronous copies (LDGSTS): no registers held, every load of the
-                        // batch in flight at once; src-size 0 zero-fills Dirichlet entities
-#pragma unroll
-                        for (int u = 0; u < U; ++u)
-                          {
-                            const int m = m0 + u * 128;
-                            if (m < total)
-                              {
-                                const int      cell = m / G::DOF;
-                                const uint32_t tb   = sm.dtab[m - cell * G::DOF];
-                                const uint32_t base = sm.eidx[bf][cell][dtab_ent(tb)];
-                                const bool     ok   = base != 0xFFFFFFFFu;
-                                const double  *g    = a.src + (ok ? (size_t)base + dtab_rel(tb) : 0);
-                                const uint32_t sa   = (uint32_t)__cvta_generic_to_shared(
-                                  sm.dofs + cell * G::DOFS + dtab_off<P>(tb));
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g),
-                                             "r"(ok ? 8 : 0)
-                                             : "memory");
-                              }
-                          }
-                      }
-                    else
-                      {
-                        double   rv[U], pv[U], hv[U], dv[U];
-                        uint32_t off[U], adr[U];
-                        bool     own[U];
-#pragma unroll
-                        for (int u = 0; u < U; ++u)
-                          {
-                            const int m = m0 + u * 128;
-                            adr[u]      = 0xFFFFFFFFu;
-                            own[u]      = false;
-                            off[u]      = 0;
-                            rv[u] = pv[u] = hv[u] = dv[u] = 0.;
-                            if (m < total)
-                              {
-                                const int      cell = m / G::DOF;
-                                const uint32_t tb   = sm.dtab[m - cell * G::DOF];
-                                const uint32_t ent  = dtab_ent(tb);
-                                const uint32_t base = sm.eidx[bf][cell][ent];
-                                off[u]              = cell * G::DOFS + dtab_off<P>(tb);
-                                if (base != 0xFFFFFFFFu)
-                                  {
-                                    adr[u] = base + dtab_rel(tb);
-                                    own[u] = (sm.meta[bf][cell][ent] & kMetaOwner) != 0;
-                                    rv[u]  = a.r_old[adr[u]];
-                                    dv[u]  = a.prec[adr[u] / 3u];
-                                    if (!first_it)
-                                      {
-                                        pv[u] = a.p_old[adr[u]];
-                                        hv[u] = a.h_old[adr[u]];
-                                      }
-                                  }
-                              }
-                          }
-#pragma unroll
-                        for (int u = 0; u < U; ++u)
-                          if (m0 + u * 128 < total)
-                            {
-                              double pn = 0.;
-                              if (adr[u] != 0xFFFFFFFFu)
-                                {
-                                  const double pr = dv[u];
-                                  double       ri = rv[u];
-                                  if (own[u] && a.update_x)
-                                    a.x[adr[u]] += a.c1 * pv[u] + a.c2 * pr * ri;
-                                  if (first_it)
-                                    pn = -pr * ri;
-                                  else
-                                    {
-                                      ri += a.alpha * hv[u];
-                                      pn = a.beta * pv[u] - pr * ri;
-                                    }
-                                  if (own[u])
-                                    {
-                                      a.r_new[adr[u]] = ri;
-                                      a.p_new[adr[u]] = pn;
-                                    }
-                                }
-                              sm.dofs[off[u]] = pn;
-                            }
-                      }
-                  }
-                if (!MERGED)
-                  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                bar_arrive(kBarInFull, kWsThreads);
-              }
-            if (i > 0)
-              {
-                bar_sync(kBarOutFull, kWsThreads);
-                uint64_t  cell0;
-                const int nc    = batch_cells(i - 1, cell0);
-                const int bf    = (i - 1) & 1;
-                const int total = nc * G::DOF;
-                // scatter-add (vector_access_reduced.h:437-521); cell-interior entity: plain store
-                for (int m0 = t; m0 < total; m0 += 128 * 4)
-                  {
-                    double rv[4], pv[4], dv[4], hv[4];
-                    bool   inner[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                      {
-                        const int m = m0 + u * 128;
-                        inner[u]    = false;
-                        if (m < total)
-                          {
-                            const int      cell = m / G::DOF;
-                            const uint32_t tb   = sm.dtab[m - cell * G::DOF];
-                            const uint32_t ent  = dtab_ent(tb);
-                            const uint32_t base = sm.eidx[bf][cell][ent];
-                            if (base != 0xFFFFFFFFu)
-                              {
-                                const double   v   = sm.work[cell * G::WORK + dtab_off_work<P>(tb)];
-                                const uint32_t adr = base + dtab_rel(tb);
-                                double        *dst = (MERGED ? a.h_new : a.dst) + adr;
-                                if (ent == 13u)
-                                  {
-                                    *dst = v;
-                                    if (MERGED)
-                                      {
-                                        inner[u] = true;
-                                        hv[u]    = v;
-                                        rv[u]    = __ldcg(a.r_new + adr);
-                                        pv[u]    = __ldcg(a.p_new + adr);
-                                        dv[u]    = a.prec[adr / 3u];
-                                      }
-                                  }
-                                else
-                                  atomicAdd(dst, v);
-                              }
-                          }
-                      }
-                    if (MERGED)
-                      {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                          if (inner[u])
-                            post_terms(s, rv[u], pv[u], hv[u], dv[u]);
-                      }
-                  }
-                __syncwarp();
-                if (i < my_n)
-                  bar_arrive(kBarOutFree, kWsThreads);
-                if (MERGED)
-                  {
-                    // last-toucher protocol, see cell_kernel_merged
-                    __threadfence();
-                    if (t == 0)
-                      sm.n_chunks = 0;
-                    bar_sync(kBarMemory, 128);
-                    for (int k = t; k < nc * 27; k += 128)
-                      {
-                        const int      cell = k / 27, ent = k % 27;
-                        const uint32_t base = sm.eidx[bf][cell][ent];
-                        if (ent == 13 || base == 0xFFFFFFFFu)
-                          continue;
-                        const uint32_t nt   = (sm.meta[bf][cell][ent] & 15u);
-                        bool           last = true;
-                        if (nt > 0)
-                          {
-                            last = atomicInc(a.counters + base / 3u, nt) == nt;
-                            if (last)
-                              __threadfence();
-                          }
-                        if (last)
-                          {
-                            const int ex = ent % 3, ey = (ent / 3) % 3, ez = ent / 9;
-                            const int nd =
-                              3 * (ex == 1 ? P - 1 : 1) * (ey == 1 ? P - 1 : 1) * (ez == 1 ? P - 1 : 1);
-                            const int      nch  = (nd + 31) >> 5;
-                            const uint32_t slot = atomicAdd(&sm.n_chunks, (uint32_t)nch);
-                            for (int q = 0; q < nch; ++q)
-                              {
-                                sm.chunk_base[slot + q] = base + 32u * q;
-                                sm.chunk_len[slot + q]  = (uint8_t)min(32, nd - 32 * q);
-                              }
-                          }
-                      }
-                    bar_sync(kBarMemory, 128);
-                    const int n_chunks = (int)sm.n_chunks;
-                    for (int ch0 = warp; ch0 < n_chunks; ch0 += 4 * 4)
-                      {
-                        double rv[4], pv[4], hv[4], dv[4];
-                        bool   ok[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                          {
-                            const int ch = ch0 + u * 4;
-                            ok[u]        = ch < n_chunks && lane < (int)sm.chunk_len[ch < n_chunks ? ch : 0];
-                            if (ok[u])
-                              {
-                                const uint32_t adr = sm.chunk_base[ch] + lane;
-                                hv[u]              = __ldcg(a.h_new + adr);
-                                rv[u]              = __ldcg(a.r_new + adr);
-                                pv[u]              = __ldcg(a.p_new + adr);
-                                dv[u]              = a.prec[adr / 3u];
-                                a.h_old[adr]       = 0.;
-                              }
-                          }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                          if (ok[u])
-                            post_terms(s, rv[u], pv[u], hv[u], dv[u]);
-                      }
-                    bar_sync(kBarMemory, 128); // chunk list is rewritten by the next batch
-                  }
-              }
-          }
-        if (MERGED)
-          {
-#pragma unroll
-            for (int k = 0; k < 7; ++k)
-              {
-                s[k] = warp_sum(s[k]);
-                if (lane == 0)
-                  sm.red[k][warp] = s[k];
-              }
-            bar_sync(kBarMemory, 128);
-            if (t < 7)
-              atomicAdd(a.acc + t, sm.red[t][0] + sm.red[t][1] + sm.red[t][2] + sm.red[t][3]);
-          }
-      }
-    else
-      {
-        // =========================== compute warpgroup ==================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsRegsComp));
-        const Tab<P> &tb = c_tab<P>;
-        for (int i = 0; i < my_n; ++i)
-          {
-            uint64_t  cell0;
-            const int nc = batch_cells(i, cell0);
-            const int bf = i & 1;
-            bar_sync(kBarInFull, kWsThreads);
-            if (i > 0)
-              bar_sync(kBarOutFree, kWsThreads);
-            // item -> thread maps are rotated by one warp per phase and batch so that the
-            // partially filled last round does not always land on the same warps (each warp
-            // owns one SM sub-partition's FP64 pipe)
-            const int r1 = (tid + 32 * (i & 3)) & 127, r2 = (tid + 32 * ((i + 1) & 3)) & 127,
-                      r3 = (tid + 32 * ((i + 2) & 3)) & 127;
-            for (int it = r1; it < nc * G::ITEMS13; it += 128)
-              phase1<P>(tb, sm.dofs + it * G::RD, sm.work + it * G::RW);
-            __syncwarp();
-            if (i + 1 < my_n)
-              bar_arrive(kBarInFree, kWsThreads);
-            bar_sync(kBarCompute, 128);
-            {
-              // full rounds first; the ragged tail goes to the rotated thread map
-              const int n2 = nc * G::ITEMS2, full = (n2 / 128) * 128;
-              for (int it = tid; it < full + 128; it += 128)
-                {
-                  const int item = it < full ? it : full + r2;
-                  if (item < n2)
-                    {
-                      const int cell = item / G::ITEMS2, r = item % G::ITEMS2;
-                      const int qz = r / Q, qx = r % Q;
-                      phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx],
-                                sm.xq[qz], sm.wq[qx] * sm.wq[qz]);
-                    }
-                }
-            }
-            bar_sync(kBarCompute, 128);
-            for (int it = r3; it < nc * G::ITEMS13; it += 128)
-              phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
-            __syncwarp();
-            bar_arrive(kBarOutFull, kWsThreads);
-          }
-      }
-  }
-
-  // entity meta data of the fused kernel, built on the device from the entity table alone:
-  // touch[first node of entity] = number of local cells holding it, owner = lowest such cell
-  __global__ void __launch_bounds__(256) meta_count_kernel(const uint64_t n_cells,
-                                                           const uint32_t *__restrict__ entity_index,
-                                                           uint32_t *touch, uint32_t *owner)
-  {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cells * 27)
-      return;
-    const uint32_t base = entity_index[i];
-    if (base == 0xFFFFFFFFu)
-      return;
-    atomicAdd(touch + base / 3u, 1u);
-    atomicMin(owner + base / 3u, (uint32_t)(i / 27));
-  }
-
-  __global__ void __launch_bounds__(256) meta_fill_kernel(const uint64_t n_cells,
-                                                          const uint32_t *__restrict__ entity_index,
-                                                          const uint32_t *__restrict__ touch,
-                                                          const uint32_t *__restrict__ owner,
-                                                          uint8_t *meta)
-  {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cells * 27)
-      return;
-    const uint64_t cell = i / 27;
-    const int      ent  = (int)(i % 27);
-    const uint32_t base = entity_index[i];
-    uint8_t        m    = 0;
-    if (base != 0xFFFFFFFFu)
-      {
-        m = (uint8_t)((touch[base / 3u] - 1u) & 15u);
-        if (owner[base / 3u] == (uint32_t)cell)
-          m |= kMetaOwner;
-      }
-    meta[cell * 28 + ent] = m;
-  }
-
   // ---------------------------------------------------------------------------------------
   // streaming kernels
   // ---------------------------------------------------------------------------------------
-  // do_cg_update4b<3,double,true>, solver_cg_optimized.h:65-161, over [0,n)
-  __global__ void __launch_bounds__(256) pre_kernel(const uint64_t n, double *__restrict__ h,
-                                                    double *__restrict__ x, double *__restrict__ r,
-                                                    double *__restrict__ p,
+  // do_cg_update4b<3,double,true>, solver_cg_optimized.h:65-161, over [begin, end): the DoFs that
+  // are not private to one cell-batch range (all of them when the numbering has no such group).
+  // Also clears the reduction scratch of this iteration (stream order: before any post).
+  __global__ void __launch_bounds__(256) pre_kernel(const uint64_t begin, const uint64_t end,
+                                                    double *__restrict__ h, double *__restrict__ x,
+                                                    double *__restrict__ r, double *__restrict__ p,
                                                     const double *__restrict__ prec,
                                                     const double alpha, const double beta,
-                                                    const double alpha_old, const double beta_old)
+                                                    const double alpha_old, const double beta_old,
+                                                    double *acc_to_zero)
   {
+    if (acc_to_zero && blockIdx.x == 0 && threadIdx.x < 8)
+      acc_to_zero[threadIdx.x] = 0.;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const double   c1 = alpha_old != 0. ? alpha + alpha_old / beta_old : 0.;
     const double   c2 = alpha_old != 0. ? alpha_old / beta_old : 0.;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride)
       {
         const double pr = prec[i / 3];
         if (alpha == 0.)
@@ -1435,26 +714,17 @@ namespace bp4
       }
   }
 
-  // do_cg_update3b<3,double>, solver_cg_optimized.h:12-61, over [0,n) -> acc[7]
-  __global__ void __launch_bounds__(256) post_kernel(const uint64_t n, const double *__restrict__ r,
+  // do_cg_update3b<3,double>, solver_cg_optimized.h:12-61, over [begin, end) -> acc[7]
+  __global__ void __launch_bounds__(256) post_kernel(const uint64_t begin, const uint64_t end,
+                                                     const double *__restrict__ r,
                                                      const double *__restrict__ d,
                                                      const double *__restrict__ h,
                                                      const double *__restrict__ prec, double *acc)
   {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     double         s[7]   = {0., 0., 0., 0., 0., 0., 0.};
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-      {
-        const double pr = prec[i / 3], ri = r[i], di = d[i], hi = h[i];
-        const double zi = pr * hi;
-        s[0] += di * hi;
-        s[1] += hi * hi;
-        s[2] += ri * hi;
-        s[3] += ri * ri;
-        s[4] += ri * zi;
-        s[5] += hi * zi;
-        s[6] += ri * pr * ri;
-      }
+    for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride)
+      post_terms(s, r[i], d[i], h[i], prec[i / 3]);
     block_accumulate<7>(s, acc);
   }
 
@@ -1645,6 +915,8 @@ namespace bp4
   }
 
   // ---------------------------------------------------------------------------------------
+
+  // ---------------------------------------------------------------------------------------
   // launchers
   // ---------------------------------------------------------------------------------------
   static inline int stream_grid(uint64_t n, int sms)
@@ -1664,228 +936,93 @@ namespace bp4
     if (e != cudaSuccess)
       return e;
     constexpr int CPB = Cfg<P>::CPB;
-    e = cudaFuncSetAttribute(cell_kernel_plain<P, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(cell_kernel<P, CPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(CellSmem<P, CPB>));
     if (e != cudaSuccess)
       return e;
-    e = cudaFuncSetAttribute(cell_kernel_merged<P, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(CellSmem<P, CPB>));
-    if (e != cudaSuccess)
-      return e;
-    e = cudaFuncSetAttribute(cell_kernel_trio<P, TrioCfg<P>::CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(CellSmem<P, TrioCfg<P>::CPB>));
-    if (e != cudaSuccess)
-      return e;
-    e = cudaFuncSetAttribute(cell_kernel_pf<P, PfCfg<P>::CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(PfSmem<P, PfCfg<P>::CPB>));
-    if (e != cudaSuccess)
-      return e;
-    e = cudaFuncSetAttribute(cell_kernel_tma<P, TmaCfg<P>::CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(TmaSmem<P, TmaCfg<P>::CPB>));
-    if (e != cudaSuccess)
-      return e;
-    constexpr int WCPB = WsCfg<P>::CPB;
-    e = cudaFuncSetAttribute(cell_kernel_ws<P, WCPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(WsSmem<P, WCPB>));
-    if (e != cudaSuccess)
-      return e;
-    return cudaFuncSetAttribute(cell_kernel_ws<P, WCPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(WsSmem<P, WCPB>));
+    return cudaFuncSetAttribute(cell_kernel<P, CPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(CellSmem<P, CPB>));
   }
 
   template <int P>
-  static cudaError_t run_cell_ws(const WsArgs &a, bool merged, int sms, cudaStream_t st)
+  static cudaError_t run_cell(const bool fused, const CellArgs &a, int sms, cudaStream_t st)
   {
-    constexpr int  CPB       = WsCfg<P>::CPB;
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
+    constexpr int  CPB   = Cfg<P>::CPB;
+    const uint64_t units = fused ? a.n_units : (a.n_cells + CPB - 1) / CPB;
+    const int      grid  = (int)std::min<uint64_t>(units, (uint64_t)sms * Cfg<P>::BLOCKS);
     if (grid == 0)
       return cudaSuccess;
-    if (merged)
-      cell_kernel_ws<P, CPB, true><<<grid, kWsThreads, sizeof(WsSmem<P, CPB>), st>>>(a);
-    else
-      cell_kernel_ws<P, CPB, false><<<grid, kWsThreads, sizeof(WsSmem<P, CPB>), st>>>(a);
-    return cudaGetLastError();
-  }
-
-  template <int P>
-  static cudaError_t run_cell_plain(const CellArgs &a, int sms, cudaStream_t st)
-  {
-    constexpr int  CPB       = Cfg<P>::CPB;
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * Cfg<P>::BLOCKS);
-    if (grid == 0)
-      return cudaSuccess;
-    cell_kernel_plain<P, CPB><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
 #ifdef BP4_PHASE_TIMING
+    unsigned long long *d_trace = nullptr;
+    const size_t        n_trace = (size_t)grid * kTraceBatches * 5;
+    if (getenv("BP4_TRACE"))
+      {
+        cudaMalloc(&d_trace, n_trace * 8);
+        cudaMemsetAsync(d_trace, 0, n_trace * 8, st);
+      }
+    cudaMemcpyToSymbolAsync(g_trace, &d_trace, sizeof(d_trace), 0, cudaMemcpyHostToDevice, st);
+#endif
+    if (fused)
+      cell_kernel<P, CPB, true><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
+    else
+      cell_kernel<P, CPB, false><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
+#ifdef BP4_PHASE_TIMING
+    if (d_trace)
+      {
+        cudaStreamSynchronize(st);
+        std::vector<unsigned long long> h(n_trace);
+        cudaMemcpy(h.data(), d_trace, n_trace * 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_trace);
+        if (FILE *f = fopen(getenv("BP4_TRACE"), "ab"))
+          {
+            const unsigned long long hdr[4] = {0xB4B4B4B4ull, (unsigned long long)grid, kTraceBatches, fused ? 1ull : 0ull};
+            fwrite(hdr, 8, 4, f);
+            fwrite(h.data(), 8, n_trace, f);
+            fclose(f);
+          }
+      }
     if (getenv("BP4_PHASE_TIMING"))
       {
         cudaStreamSynchronize(st);
         unsigned long long h[8], z[8] = {0};
         cudaMemcpyFromSymbol(h, g_phase_clk, sizeof(h));
         cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
-        const double tot = double(h[0] + h[1] + h[2] + h[3] + h[4] + h[5] + h[6]);
-        fprintf(stderr, "phase clk share: meta %.1f%% gather %.1f%% barrier %.1f%% P1 %.1f%% P2 %.1f%% P3 %.1f%% scatter %.1f%% | per-warp total %.0f clk\n",
+        double tot = 0;
+        for (int k = 0; k < 8; ++k)
+          tot += double(h[k]);
+        fprintf(stderr, "phase clk share: meta %.1f%% gather %.1f%% barrier %.1f%% P1 %.1f%% P2 %.1f%% P3 %.1f%% scatter %.1f%% post %.1f%% | per-warp total %.0f clk\n",
                 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot,
-                100 * h[5] / tot, 100 * h[6] / tot, tot / (grid * (kThreads / 32)));
+                100 * h[5] / tot, 100 * h[6] / tot, 100 * h[7] / tot, tot / (grid * (kThreads / 32)));
       }
 #endif
     return cudaGetLastError();
   }
 
-  template <int P>
-  static cudaError_t run_cell_trio(const CellArgs &a, int sms, cudaStream_t st)
-  {
-    constexpr int  CPB       = TrioCfg<P>::CPB;
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
-    if (grid == 0)
-      return cudaSuccess;
-    cell_kernel_trio<P, CPB><<<grid, kTrioThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
-    return cudaGetLastError();
-  }
-
-  template <int P>
-  static cudaError_t run_cell_pf(const CellArgs &a, int sms, cudaStream_t st)
-  {
-    constexpr int  CPB       = PfCfg<P>::CPB;
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
-    if (grid == 0)
-      return cudaSuccess;
-    cell_kernel_pf<P, CPB><<<grid, kThreads, sizeof(PfSmem<P, CPB>), st>>>(a);
-    return cudaGetLastError();
-  }
-
-  template <int P>
-  static cudaError_t run_cell_tma(const TmaArgs &a, int sms, cudaStream_t st)
-  {
-    constexpr int  CPB       = TmaCfg<P>::CPB;
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
-    if (grid == 0)
-      return cudaSuccess;
-    cell_kernel_tma<P, CPB><<<grid, kThreads, sizeof(TmaSmem<P, CPB>), st>>>(a);
-    return cudaGetLastError();
-  }
-
-  template <int P>
-  static void stage_tables(std::vector<uint16_t> &out)
-  {
-    out.assign(28 + Geom<P>::N * Geom<P>::N * Geom<P>::ROWS, 0);
-    build_stage_tables<P>(out.data(), out.data() + 28);
-  }
-
-  template <int P>
-  static cudaError_t run_cell_merged(const MergedArgs &a, int sms, cudaStream_t st)
-  {
-    constexpr int  CPB       = Cfg<P>::CPB;
-    const uint64_t n_batches = (a.n_cells + CPB - 1) / CPB;
-    const int      grid      = (int)std::min<uint64_t>(n_batches, (uint64_t)sms * kBlocksPerSM);
-    if (grid == 0)
-      return cudaSuccess;
-    cell_kernel_merged<P, CPB><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
-    return cudaGetLastError();
-  }
-
-#define BP4_DISPATCH(p, CALL)                    \
-  switch (p)                                     \
-    {                                            \
-      case 2: { constexpr int P = 2; CALL; } break; \
-      case 3: { constexpr int P = 3; CALL; } break; \
-      case 4: { constexpr int P = 4; CALL; } break; \
-      case 5: { constexpr int P = 5; CALL; } break; \
-      case 6: { constexpr int P = 6; CALL; } break; \
-      case 7: { constexpr int P = 7; CALL; } break; \
-      case 8: { constexpr int P = 8; CALL; } break; \
-      default: return cudaErrorInvalidValue;     \
+#define BP4_DISPATCH(degree, CALL)         \
+  switch (degree)                          \
+    {                                      \
+      case 2: return CALL(2);              \
+      case 3: return CALL(3);              \
+      case 4: return CALL(4);              \
+      case 5: return CALL(5);              \
+      case 6: return CALL(6);              \
+      case 7: return CALL(7);              \
+      case 8: return CALL(8);              \
+      default: return cudaErrorInvalidValue; \
     }
 
   cudaError_t launch_init_degree(int degree, std::vector<uint32_t> &walk)
   {
-    BP4_DISPATCH(degree, return init_degree<P>(walk));
-    return cudaSuccess;
+#define CALL(P) init_degree<P>(walk)
+    BP4_DISPATCH(degree, CALL)
+#undef CALL
   }
 
-  cudaError_t launch_cell_plain(int degree, const CellArgs &a, int sms, cudaStream_t st)
+  cudaError_t launch_cell(int degree, bool fused, const CellArgs &a, int sms, cudaStream_t st)
   {
-    BP4_DISPATCH(degree, return run_cell_plain<P>(a, sms, st));
-    return cudaSuccess;
-  }
-
-  cudaError_t launch_cell_tma(int degree, const TmaArgs &a, int sms, cudaStream_t st)
-  {
-    BP4_DISPATCH(degree, return run_cell_tma<P>(a, sms, st));
-    return cudaSuccess;
-  }
-
-  // [0,28): slot table, [28, ...): inverse table of the TMA variant
-  cudaError_t launch_stage_tables(int degree, std::vector<uint16_t> &out)
-  {
-    BP4_DISPATCH(degree, stage_tables<P>(out));
-    return cudaSuccess;
-  }
-
-  cudaError_t launch_cell_trio(int degree, const CellArgs &a, int sms, cudaStream_t st)
-  {
-    BP4_DISPATCH(degree, return run_cell_trio<P>(a, sms, st));
-    return cudaSuccess;
-  }
-
-  cudaError_t launch_cell_pf(int degree, const CellArgs &a, int sms, cudaStream_t st)
-  {
-    BP4_DISPATCH(degree, return run_cell_pf<P>(a, sms, st));
-    return cudaSuccess;
-  }
-
-  cudaError_t launch_cell_ws(int degree, const MergedArgs *m, const CellArgs *p, int sms, cudaStream_t st)
-  {
-    WsArgs a{};
-    if (m)
-      {
-        a.entity_index = m->entity_index, a.coef = m->coef, a.dtab = m->dtab, a.n_cells = m->n_cells;
-        a.meta = m->meta, a.counters = m->counters, a.r_old = m->r_old, a.p_old = m->p_old;
-        a.h_old = m->h_old, a.r_new = m->r_new, a.p_new = m->p_new, a.h_new = m->h_new, a.x = m->x;
-        a.prec = m->prec, a.alpha = m->alpha, a.beta = m->beta, a.c1 = m->c1, a.c2 = m->c2;
-        a.update_x = m->update_x, a.acc = m->acc;
-      }
-    else
-      {
-        a.entity_index = p->entity_index, a.coef = p->coef, a.dtab = p->dtab, a.n_cells = p->n_cells;
-        a.src = p->src, a.dst = p->dst;
-      }
-    BP4_DISPATCH(degree, return run_cell_ws<P>(a, m != nullptr, sms, st));
-    return cudaSuccess;
-  }
-
-  cudaError_t launch_cell_merged(int degree, const MergedArgs &a, int sms, cudaStream_t st)
-  {
-    BP4_DISPATCH(degree, return run_cell_merged<P>(a, sms, st));
-    return cudaSuccess;
-  }
-
-  // touch/owner: scratch arrays of n_nodes entries; touch is left ZEROED for use as the
-  // arrival counters of the fused kernel
-  cudaError_t launch_build_meta(uint64_t n_cells, uint64_t n_nodes, const uint32_t *entity_index,
-                                uint32_t *touch, uint32_t *owner, uint8_t *meta, cudaStream_t st)
-  {
-    cudaError_t e = cudaMemsetAsync(touch, 0, sizeof(uint32_t) * n_nodes, st);
-    if (e != cudaSuccess)
-      return e;
-    e = cudaMemsetAsync(owner, 0xFF, sizeof(uint32_t) * n_nodes, st);
-    if (e != cudaSuccess)
-      return e;
-    const uint64_t n = n_cells * 27;
-    if (n)
-      {
-        meta_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_cells, entity_index, touch, owner);
-        meta_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_cells, entity_index, touch, owner,
-                                                                      meta);
-      }
-    e = cudaGetLastError();
-    if (e != cudaSuccess)
-      return e;
-    return cudaMemsetAsync(touch, 0, sizeof(uint32_t) * n_nodes, st);
+#define CALL(P) run_cell<P>(fused, a, sms, st)
+    BP4_DISPATCH(degree, CALL)
+#undef CALL
   }
 
   int cells_per_block(int degree)
@@ -1903,23 +1040,36 @@ namespace bp4
     return 0;
   }
 
-  cudaError_t launch_pre(uint64_t n, double *h, double *x, double *r, double *p, const double *prec,
-                         double alpha, double beta, double alpha_old, double beta_old, int sms,
-                         cudaStream_t st)
+  int blocks_per_sm(int degree)
   {
-    if (n == 0)
-      return cudaSuccess;
-    pre_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, h, x, r, p, prec, alpha, beta, alpha_old,
-                                                     beta_old);
+    switch (degree)
+      {
+        case 2: return Cfg<2>::BLOCKS;
+        case 3: return Cfg<3>::BLOCKS;
+        case 4: return Cfg<4>::BLOCKS;
+        case 5: return Cfg<5>::BLOCKS;
+        case 6: return Cfg<6>::BLOCKS;
+        case 7: return Cfg<7>::BLOCKS;
+        case 8: return Cfg<8>::BLOCKS;
+      }
+    return 0;
+  }
+
+  cudaError_t launch_pre(uint64_t begin, uint64_t end, double *h, double *x, double *r, double *p,
+                         const double *prec, double alpha, double beta, double alpha_old,
+                         double beta_old, double *acc_to_zero, int sms, cudaStream_t st)
+  {
+    pre_kernel<<<stream_grid(end > begin ? end - begin : 0, sms), 256, 0, st>>>(
+      begin, end, h, x, r, p, prec, alpha, beta, alpha_old, beta_old, acc_to_zero);
     return cudaGetLastError();
   }
 
-  cudaError_t launch_post(uint64_t n, const double *r, const double *d, const double *h,
-                          const double *prec, double *acc, int sms, cudaStream_t st)
+  cudaError_t launch_post(uint64_t begin, uint64_t end, const double *r, const double *d,
+                          const double *h, const double *prec, double *acc, int sms, cudaStream_t st)
   {
-    if (n == 0)
+    if (end <= begin)
       return cudaSuccess;
-    post_kernel<<<stream_grid(n, sms), 256, 0, st>>>(n, r, d, h, prec, acc);
+    post_kernel<<<stream_grid(end - begin, sms), 256, 0, st>>>(begin, end, r, d, h, prec, acc);
     return cudaGetLastError();
   }
 

@@ -11,21 +11,15 @@ namespace bp4
 {
   cudaError_t launch_init_degree(int degree, std::vector<uint32_t> &walk);
   int         cells_per_block(int degree);
-  cudaError_t launch_cell_plain(int degree, const CellArgs &a, int sms, cudaStream_t st);
-  cudaError_t launch_cell_trio(int degree, const CellArgs &a, int sms, cudaStream_t st);
-  cudaError_t launch_cell_pf(int degree, const CellArgs &a, int sms, cudaStream_t st);
-  cudaError_t launch_cell_tma(int degree, const TmaArgs &a, int sms, cudaStream_t st);
-  cudaError_t launch_stage_tables(int degree, std::vector<uint16_t> &out);
-  // warp-specialised kernel: pass exactly one of m (merged) / p (plain)
-  cudaError_t launch_cell_ws(int degree, const MergedArgs *m, const CellArgs *p, int sms, cudaStream_t st);
-  cudaError_t launch_cell_merged(int degree, const MergedArgs &a, int sms, cudaStream_t st);
-  cudaError_t launch_build_meta(uint64_t n_cells, uint64_t n_nodes, const uint32_t *entity_index,
-                                uint32_t *touch, uint32_t *owner, uint8_t *meta, cudaStream_t st);
-  cudaError_t launch_pre(uint64_t n, double *h, double *x, double *r, double *p, const double *prec,
-                         double alpha, double beta, double alpha_old, double beta_old, int sms,
-                         cudaStream_t st);
-  cudaError_t launch_post(uint64_t n, const double *r, const double *d, const double *h,
-                          const double *prec, double *acc, int sms, cudaStream_t st);
+  int         blocks_per_sm(int degree);
+  // plain: a.n_cells cells from a.entity_index on; fused: a.n_units units of a.unit_batch
+  cudaError_t launch_cell(int degree, bool fused, const CellArgs &a, int sms, cudaStream_t st);
+  // do_cg_update4b / do_cg_update3b on the DoF interval [begin, end) (the DoFs no range owns)
+  cudaError_t launch_pre(uint64_t begin, uint64_t end, double *h, double *x, double *r, double *p,
+                         const double *prec, double alpha, double beta, double alpha_old,
+                         double beta_old, double *acc_to_zero, int sms, cudaStream_t st);
+  cudaError_t launch_post(uint64_t begin, uint64_t end, const double *r, const double *d,
+                          const double *h, const double *prec, double *acc, int sms, cudaStream_t st);
   cudaError_t launch_fixup(uint64_t n, const uint32_t *con, double *dst, const double *src,
                            cudaStream_t st);
   cudaError_t launch_sadd(uint64_t n, double *dst, double s, double a, const double *src, int sms,

@@ -80,6 +80,16 @@ class Problem:
         self._chk(self.l.bp4h_get_vertices(self.h, _p(out)))
         return out
 
+    def ranges(self):
+        """(range_cell_offset, range_private_offset) as handed to bp4_ctx_create"""
+        n = C.c_uint64()
+        self._chk(self.l.bp4h_get_ranges(self.h, C.byref(n), None, None))
+        rc = np.zeros(n.value, dtype=np.uint64)
+        rp = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            self._chk(self.l.bp4h_get_ranges(self.h, C.byref(n), _p(rc), _p(rp)))
+        return rc, rp
+
     def constrained(self):
         out = np.empty(self.n_constrained, dtype=np.uint32)
         self._chk(self.l.bp4h_get_constrained(self.h, _p(out)))

@@ -35,18 +35,23 @@ namespace dealii
 
         // n_local entries are owned, the vector additionally carries n_ghost ghost slots
         void reinit(bp4_ctx *ctx_, std::uint64_t n_local_, std::uint64_t n_ghost_ = 0,
-                    std::uint64_t n_global_ = 0)
+                    std::uint64_t n_global_ = 0, const bool omit_zeroing_entries = false)
         {
           release();
           ctx      = ctx_;
           n_local  = n_local_;
           n_ghost  = n_ghost_;
           n_global = n_global_ ? n_global_ : n_local_;
-          bp4_check(bp4_vec_alloc(ctx, n_local + n_ghost, &h));
+          if (omit_zeroing_entries)
+            bp4_check(bp4_vec_alloc_uninitialized(ctx, n_local + n_ghost, &h));
+          else
+            bp4_check(bp4_vec_alloc(ctx, n_local + n_ghost, &h));
         }
-        void reinit(const Vector &other, bool /*omit_zeroing_entries*/ = false)
+        // omit_zeroing_entries = true leaves the entries undefined, as in deal.II (the solvers
+        // take their temporaries this way, solver_cg_optimized.h:215-217)
+        void reinit(const Vector &other, const bool omit_zeroing_entries = false)
         {
-          reinit(other.ctx, other.n_local, other.n_ghost, other.n_global);
+          reinit(other.ctx, other.n_local, other.n_ghost, other.n_global, omit_zeroing_entries);
         }
         Vector &operator=(const Number s)
         {

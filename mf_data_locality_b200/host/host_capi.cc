@@ -25,6 +25,8 @@ namespace
     virtual const DoFHandler &dh()                                      = 0;
     virtual const std::vector<unsigned int> &entity()                   = 0;
     virtual const std::vector<double>       &vertices()                 = 0;
+    virtual const std::vector<std::uint64_t> &range_cells()             = 0;
+    virtual const std::vector<std::uint64_t> &range_private()           = 0;
     virtual LinearAlgebra::distributed::Vector<double> &input()         = 0;
     virtual LinearAlgebra::distributed::Vector<double> &output()        = 0;
     virtual LinearAlgebra::distributed::Vector<double> &diagonal()      = 0;
@@ -42,6 +44,8 @@ namespace
     const DoFHandler &dh() override { return prob.dof_handler; }
     const std::vector<unsigned int> &entity() override { return prob.laplace_operator.get_compressed_dof_indices(); }
     const std::vector<double>       &vertices() override { return prob.laplace_operator.get_cell_vertices(); }
+    const std::vector<std::uint64_t> &range_cells() override { return prob.laplace_operator.get_range_cell_offset(); }
+    const std::vector<std::uint64_t> &range_private() override { return prob.laplace_operator.get_range_private_offset(); }
     LinearAlgebra::distributed::Vector<double> &input() override { return prob.input; }
     LinearAlgebra::distributed::Vector<double> &output() override { return prob.output; }
     LinearAlgebra::distributed::Vector<double> &diagonal() override { return prob.diag_mat.diagonal; }
@@ -143,6 +147,20 @@ int bp4h_get_vertices(void *h, double *out)
   return guarded([&] {
     const auto &v = static_cast<ProblemBase *>(h)->vertices();
     std::memcpy(out, v.data(), v.size() * sizeof(double));
+  });
+}
+// cell-batch ranges + private DoF runs handed to the device (bp4_desc::n_ranges): *n = number of
+// table entries (n_ranges + 1, 0 when the numbering has no contiguous private runs); the
+// tables are copied when the pointers are non-null
+int bp4h_get_ranges(void *h, std::uint64_t *n, std::uint64_t *cell_offset, std::uint64_t *private_offset)
+{
+  return guarded([&] {
+    ProblemBase *p = static_cast<ProblemBase *>(h);
+    *n             = p->range_cells().size();
+    if (cell_offset)
+      std::copy(p->range_cells().begin(), p->range_cells().end(), cell_offset);
+    if (private_offset)
+      std::copy(p->range_private().begin(), p->range_private().end(), private_offset);
   });
 }
 int bp4h_get_constrained(void *h, std::uint32_t *out)

@@ -79,7 +79,12 @@ namespace Poisson
               }
           }
 
+      compute_private_ranges(dh, constraints, part);
+
       bp4_desc desc{};
+      desc.n_ranges             = range_cell_offset.empty() ? 0 : range_cell_offset.size() - 1;
+      desc.range_cell_offset    = range_cell_offset.data();
+      desc.range_private_offset = range_private_offset.data();
       desc.degree        = fe_degree;
       desc.device        = device;
       desc.n_cells       = n_cells;
@@ -142,12 +147,82 @@ namespace Poisson
       bp4_check(bp4_inverse_diagonal(ctx, per_node.handle()));
     }
 
+    // cell-batch ranges of the loop and the owned DoFs private to each (bp4_desc::n_ranges)
+    const std::vector<std::uint64_t> &get_range_cell_offset() const { return range_cell_offset; }
+    const std::vector<std::uint64_t> &get_range_private_offset() const { return range_private_offset; }
+
     bp4_ctx                          *context() const { return ctx; }
     const std::vector<unsigned int>  &get_compressed_dof_indices() const { return compressed_dof_indices; }
     const std::vector<double>        &get_cell_vertices() const { return cell_vertices; }
     const MatrixFree                 &get_matrix_free() const { return *data; }
 
   private:
+    // The DoF ranges MatrixFree::cell_loop hands to the pre/post hooks of vmult_with_merged_sums
+    // right around a cell-batch range's own cells (poisson_operator.h:339-364) are the DoFs no
+    // other range touches.  Renumber(*, *, 2) numbers exactly those first and range by range
+    // (touch_count_cellbatch_range + touch_count_grouping, renumber_dofs_for_mf.h:556-590,
+    // :622-671); here they are re-derived from the cell loop (same walk as the renumbering) and
+    // handed to the device as one contiguous run per range.  If the numbering in use does not
+    // deliver contiguous runs starting at DoF 0 (e.g. renumbering switched off), the tables stay
+    // empty and the device streams the vector updates over the whole vector instead.
+    void compute_private_ranges(const DoFHandler &dh, const AffineConstraints &constraints,
+                                const Utilities::MPI::Partitioner &part)
+    {
+      range_cell_offset.clear();
+      range_private_offset.clear();
+      const auto         &ti      = data->get_task_info();
+      const unsigned int  rank    = data->get_rank();
+      const std::uint64_t first   = part.owned.first / n_components;
+      const std::uint64_t n_nodes = part.locally_owned_size() / n_components;
+      const unsigned int  n_ranges = (unsigned int)ti.cell_partition_data.size() - 1;
+      if (n_ranges == 0)
+        return;
+      std::vector<std::uint32_t> last_range(n_nodes, numbers::invalid_unsigned_int);
+      std::vector<unsigned char> count(n_nodes, 0);
+      for (unsigned int r = 0; r < n_ranges; ++r)
+        for (unsigned int b = ti.cell_partition_data[r]; b < ti.cell_partition_data[r + 1]; ++b)
+          for (unsigned int l = 0; l < data->n_active_entries_per_cell_batch(b); ++l)
+            dh.for_each_cell_node(data->get_cell(b, l), [&](const std::uint64_t node, int, int, int) {
+              if (dh.owner[node] != rank)
+                return;
+              const std::uint64_t i = dh.node_number[node] - first;
+              if (last_range[i] != r)
+                {
+                  last_range[i] = r;
+                  if (count[i] < 255)
+                    ++count[i];
+                }
+            });
+      // private = one range, not shared with another rank, not Dirichlet
+      std::vector<std::uint64_t> n_private(n_ranges, 0), lo(n_ranges, ~std::uint64_t(0)), hi(n_ranges, 0);
+      std::vector<unsigned char> is_private(n_nodes, 0);
+      for (std::uint64_t n = 0; n < dh.n_nodes; ++n)
+        if (dh.owner[n] == rank && !dh.shared[n] && !constraints.node_is_constrained(n))
+          {
+            const std::uint64_t i = dh.node_number[n] - first;
+            if (count[i] != 1)
+              continue;
+            const std::uint32_t r = last_range[i];
+            ++n_private[r];
+            lo[r] = std::min(lo[r], i);
+            hi[r] = std::max(hi[r], i + 1);
+          }
+      std::vector<std::uint64_t> cell_off(n_ranges + 1, 0), priv_off(n_ranges + 1, 0);
+      bool                       contiguous = true;
+      for (unsigned int r = 0; r < n_ranges; ++r)
+        {
+          cell_off[r + 1] = data->batch_start[ti.cell_partition_data[r + 1]];
+          priv_off[r + 1] = priv_off[r] + n_components * n_private[r];
+          if (n_private[r] && (n_components * lo[r] != priv_off[r] || n_components * hi[r] != priv_off[r + 1]))
+            contiguous = false;
+        }
+      if (!contiguous)
+        return;
+      range_cell_offset.swap(cell_off);
+      range_private_offset.swap(priv_off);
+    }
+
+    std::vector<std::uint64_t>        range_cell_offset, range_private_offset;
     std::shared_ptr<const MatrixFree> data;
     std::vector<unsigned int>         compressed_dof_indices; // [cell][27], one lane per cell
     std::vector<double>               cell_vertices;          // [cell][8][3]

@@ -240,6 +240,12 @@ class RankData:
     ghost_owner: np.ndarray           # [n_ghost/3] owning rank of each ghost node
     ghost_remote_local: np.ndarray    # [n_ghost/3] local node index on the owner
     group_sizes: tuple = (0, 0, 0)    # owned DoFs in (single-range, multi/zero-range, multi-rank)
+    # cell-batch ranges as cell offsets, and the run of owned DoFs private to each range: the
+    # first group of touch_count_grouping (renumber_dofs_for_mf.h:556-590) is ordered by first
+    # touch, hence range by range -- the DoF ranges around which MatrixFree::cell_loop runs the
+    # pre/post hooks of vmult_with_merged_sums (poisson_operator.h:339-364)
+    range_cell_offset: np.ndarray = None
+    range_private_offset: np.ndarray = None
 
 
 def _lattice(p, n):
@@ -349,12 +355,19 @@ def build_problem(degree: int, s: int, n_ranks: int = 1, lanes: int = 8,
         for g in (g1, g2, g3):                           # grouping, :492-535, :556-590
             idx = np.nonzero(g)[0]
             seq.append(idx[np.argsort(ft[idx], kind="stable")])
+        # group-1 nodes per range: the (only) range touching such a node is that of its first touch
+        n_rng = len(range_start) - 1
+        priv_cnt = np.bincount(cell_range[ft[g1] // npc], minlength=n_rng) if n_rng else np.zeros(0, dtype=np.int64)
+        range_private_offset = 3 * np.concatenate(([0], np.cumsum(priv_cnt)))
+        range_cell_offset = batch_start[range_start]
         seq = np.concatenate(seq)
         new_nodes = owned_nodes[seq]                     # lattice node at each new local position
         new_local[new_nodes] = np.arange(len(new_nodes))
         per_rank.append(dict(cells=cells_r, nodes=nodes_r, owned=new_nodes,
                              batch_start=batch_start, range_start=range_start,
                              part_start=part_start, uniq=uniq,
+                             range_cell_offset=range_cell_offset.astype(np.uint64),
+                             range_private_offset=range_private_offset.astype(np.uint64),
                              groups=(3 * int(g1.sum()), 3 * int(g2.sum()), 3 * int(g3.sum()))))
 
     node_offset = np.concatenate(([0], np.cumsum([len(d["owned"]) for d in per_rank])))
@@ -385,7 +398,8 @@ def build_problem(degree: int, s: int, n_ranks: int = 1, lanes: int = 8,
             constrained=constrained.astype(np.uint32), rhs=rhs,
             batch_start=d["batch_start"], range_start=d["range_start"], part_start=d["part_start"],
             ghost_owner=owner[ghosts], ghost_remote_local=new_local[ghosts],
-            group_sizes=d["groups"]))
+            group_sizes=d["groups"], range_cell_offset=d["range_cell_offset"],
+            range_private_offset=d["range_private_offset"]))
     return out
 
 

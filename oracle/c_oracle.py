@@ -95,13 +95,24 @@ class COracle:
         assert e == 0
         return dst
 
-    def cg(self, b, diag, merged: bool, max_steps=100, tol=1e-15, reduce=1e-8):
-        """returns (x, last_step, residual history)"""
+    def cg(self, b, diag, merged: bool, max_steps=100, tol=1e-15, reduce=1e-8, blocked=False):
+        """returns (x, last_step, residual history).  blocked (merged only): the vector updates
+        run per cell-batch range inside the loop, every thread on its own chunk of ranges -- the
+        reference's cache-blocked cell_loop with pre/post hooks; used as the CPU baseline"""
         b = np.ascontiguousarray(b, dtype=np.float64)
         diag = np.ascontiguousarray(diag, dtype=np.float64)
         x = np.zeros(self.n)
         hist = np.zeros(max_steps + 2)
-        if merged:
+        if merged and blocked:
+            assert self.rd.n_ghost == 0
+            rc = np.ascontiguousarray(self.rd.range_cell_offset, dtype=np.int64)
+            rp = np.ascontiguousarray(self.rd.range_private_offset, dtype=np.int64)
+            it = lib().oracle_cg_merged_blocked(C.byref(self.tab), C.c_long(self.rd.n_cells), C.c_long(self.n),
+                                                _p(self.eidx), _p(self.coef), _p(diag), _p(b), _p(x),
+                                                C.c_int(max_steps), C.c_double(tol), C.c_double(reduce),
+                                                _p(hist), C.c_long(len(rc) - 1), _p(rc), _p(rp))
+            assert it >= 0
+        elif merged:
             it = lib().oracle_cg_merged(C.byref(self.tab), C.c_long(self.rd.n_cells), C.c_long(self.n),
                                         _p(self.eidx), _p(self.coef), _p(diag), _p(b), _p(x),
                                         C.c_int(max_steps), C.c_double(tol), C.c_double(reduce), _p(hist))

@@ -23,10 +23,13 @@ def single(p, s):
     return rd, COracle(rd)
 
 
-def make_ctx(rd, device=0):
+def make_ctx(rd, device=0, ranges=True):
+    """ranges=True hands the oracle's cell-batch ranges + private DoF runs to the context, which
+    switches the in-loop (fused) vector updates of vmult_with_merged_sums on"""
     from mf_data_locality_b200 import capi
     return capi.Context(rd.degree, rd.entity_index, rd.vertices, rd.n_owned, rd.n_ghost,
-                        rd.constrained, device=device)
+                        rd.constrained, device=device,
+                        ranges=(rd.range_cell_offset, rd.range_private_offset) if ranges else None)
 
 
 def rel_l2(a, b):

@@ -14,12 +14,10 @@ VMULT_CASES = [(2, 3), (2, 7), (3, 3), (3, 6), (3, 10), (4, 4), (4, 9), (4, 11),
                (6, 8), (7, 4), (7, 6), (8, 3), (8, 7)]
 
 
-@pytest.mark.parametrize("ws", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("p,s", VMULT_CASES)
-def test_vmult_matches_oracle(p, s, ws, bp4_lib, c_oracle_lib):
+def test_vmult_matches_oracle(p, s, bp4_lib, c_oracle_lib):
     rd, co = single(p, s)
     ctx = make_ctx(rd)
-    ctx.set_merged_variant(3 * ws)          # plain cell kernel: TMA / warp-specialised / classic / cp.async prefetch
     rng = np.random.default_rng(100 * p + s)
     v = rng.standard_normal(rd.n_owned)
     src, dst = ctx.vector(data=v), ctx.vector()
@@ -90,17 +88,24 @@ def test_blas1(bp4_lib):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
-@pytest.mark.parametrize("p,s", [(3, 6), (4, 7), (6, 4)])
-def test_merged_sums_match_oracle(p, s, variant, bp4_lib, c_oracle_lib):
-    """one vmult_with_merged_sums call in each of the three do_cg_update4b regimes"""
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("constrained_rhs", [False, True])
+@pytest.mark.parametrize("p,s", [(2, 7), (3, 6), (4, 7), (4, 9), (5, 6), (6, 4), (7, 5), (8, 4)])
+def test_merged_sums_match_oracle(p, s, fused, constrained_rhs, bp4_lib, c_oracle_lib):
+    """one vmult_with_merged_sums call in each of the three do_cg_update4b regimes, with the
+    vector updates inside the cell loop (fused, default) and streamed (unfused).  With
+    constrained_rhs the Dirichlet rows of x, g, d, h are non-zero: do_cg_update4b/3b sweep ALL
+    owned entries (solver_cg_optimized.h:65-161, 12-61), not only those the cells touch."""
     rd, co = single(p, s)
     ctx = make_ctx(rd)
-    ctx.set_merged_variant(variant)
+    _, n_private, n_units = ctx.fused_info()
+    assert n_private == rd.group_sizes[0] and n_units > 0
+    ctx.set_fused(fused)
     n = rd.n_owned
     rng = np.random.default_rng(3)
     free = np.ones(n)
-    free[rd.constrained] = 0.0
+    if not constrained_rhs:
+        free[rd.constrained] = 0.0
     prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
     prec3 = np.repeat(prec, 3)
     vp = ctx.vector(n // 3, data=prec)
@@ -109,7 +114,9 @@ def test_merged_sums_match_oracle(p, s, variant, bp4_lib, c_oracle_lib):
         vx, vg, vd, vh = (ctx.vector(data=a) for a in (x, g, d, h))
         S = ctx.vmult_merged(vx, vg, vd, vh, vp, alpha, beta, alpha_old, beta_old)
         O.cg_update4b(h, x, g, d, prec3, alpha, beta, alpha_old, beta_old)
-        h[:] = co.vmult_cells(d)
+        dd = d.copy()
+        dd[rd.constrained] = 0.0          # constrained entries are never read by the cells
+        h[:] = co.vmult_cells(dd)
         want = O.cg_update3b(g, d, h, prec3)
         np.testing.assert_allclose(S, want, rtol=1e-11)
         for got, ref in ((vx, x), (vg, g), (vd, d), (vh, h)):
@@ -117,12 +124,12 @@ def test_merged_sums_match_oracle(p, s, variant, bp4_lib, c_oracle_lib):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
-@pytest.mark.parametrize("p,s", [(3, 6), (4, 6), (2, 9)])
-def test_cg_merged_parity(p, s, variant, bp4_lib, c_oracle_lib):
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("p,s", [(3, 6), (4, 6), (2, 9), (5, 7), (6, 6)])
+def test_cg_merged_parity(p, s, fused, bp4_lib, c_oracle_lib):
     rd, co = single(p, s)
     ctx = make_ctx(rd)
-    ctx.set_merged_variant(variant)
+    ctx.set_fused(fused)
     prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
     vp = ctx.vector(rd.n_owned // 3, data=prec)
     for reduce in (1e-8, 1e-10):
@@ -185,10 +192,56 @@ def test_empty_and_ragged_inputs(bp4_lib, c_oracle_lib):
     for p, s in [(4, 3), (3, 4), (5, 3)]:          # 8, 16, 8 cells: never a multiple of 7 / 10 / 5
         rd, co = single(p, s)
         ctx = make_ctx(rd)
-        for variant in (0, 3, 6, 9, 12):
-            ctx.set_merged_variant(variant)
-            w = np.random.default_rng(variant).standard_normal(rd.n_owned)
-            a, b = ctx.vector(data=w), ctx.vector()
-            ctx.vmult(b, a)
-            assert rel_l2(b.download(), co.vmult(w)) <= 1e-12
+        w = np.random.default_rng(p).standard_normal(rd.n_owned)
+        a, b = ctx.vector(data=w), ctx.vector()
+        ctx.vmult(b, a)
+        assert rel_l2(b.download(), co.vmult(w)) <= 1e-12
         ctx.close()
+
+
+def test_fused_needs_range_tables(bp4_lib):
+    """without range tables in the descriptor the vector updates are streamed; asking for the
+    in-loop form is a state error, not a silent fallback"""
+    from mf_data_locality_b200 import capi
+    rd, _ = single(3, 5)
+    ctx = make_ctx(rd, ranges=False)
+    assert ctx.fused_info() == (False, 0, 0)
+    with pytest.raises(capi.Bp4Error, match="range tables"):
+        ctx.set_fused(True)
+    ctx.close()
+    bad = rd.range_private_offset.copy()
+    bad[1] += 1                                    # not a multiple of 3
+    with pytest.raises(capi.Bp4Error, match="multiple of 3"):
+        capi.Context(rd.degree, rd.entity_index, rd.vertices, rd.n_owned, rd.n_ghost, rd.constrained,
+                     ranges=(rd.range_cell_offset, bad))
+
+
+# ---- parity at the sizes BASELINE.json quotes (configs[0..2]) ------------------------------
+SCALE_CASES = [pytest.param(3, 15, False, id="config0-Q3-s15-plain"),
+               pytest.param(4, 18, True, id="config1-Q4-s18-merged"),
+               pytest.param(6, 17, True, id="config2-Q6-s17-merged")]
+
+
+@pytest.mark.parametrize("p,s,merged", SCALE_CASES)
+def test_benchmark_scale_parity(p, s, merged, bp4_lib, c_oracle_lib):
+    """BASELINE.json's own sizes (Q6 at s=17, the largest the CPU oracle finishes in a minute):
+    one operator apply (rel-L2 <= 1e-12) and the benchmark's 100-iteration CG through the C++
+    plugin (iteration count +-1, solution <= 1e-6 at the iteration cap) against the C oracle.
+    Exercises 32-bit index arithmetic at 5e7..1.7e8 entries, the persistent grid's tail and
+    the drift of 100 iterations at full size."""
+    from mf_data_locality_b200 import host
+    rd, co = single(p, s)
+    prob = host.Problem(p, s, plugin="merged" if merged else "plain", device=0)
+    assert prob.n_owned == rd.n_owned
+    v = np.random.default_rng(p * 100 + s).standard_normal(rd.n_owned)
+    got = prob.vmult(v)
+    want = co.vmult(v)
+    assert rel_l2(got, want) <= 1e-12
+    assert np.array_equal(got[rd.constrained], v[rd.constrained])
+    del got, want, v
+    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    x, it = prob.run_cg_solver(rd.rhs)
+    xo, ito, _ = co.cg(rd.rhs, prec, merged=merged)
+    assert abs(it - ito) <= 1
+    assert rel_l2(x, xo) <= (1e-8 if ito < 100 else 1e-6)
+    prob.close()

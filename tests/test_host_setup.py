@@ -30,6 +30,10 @@ def test_tables_bit_exact(host, p, s, n_ranks):
         assert np.array_equal(pr.constrained(), rd.constrained)
         assert np.allclose(pr.vertices(), rd.vertices, rtol=0, atol=1e-15)
         assert pr.n_batches == len(rd.batch_start) - 1 and pr.n_ranges == len(rd.range_start) - 1
+        # cell-batch ranges and the DoF runs private to them (the pre/post ranges of the merged loop)
+        rc, rp = pr.ranges()
+        assert np.array_equal(rc, rd.range_cell_offset) and np.array_equal(rp, rd.range_private_offset)
+        assert rp[-1] == rd.group_sizes[0]
         pr.close()
 
 
@@ -40,6 +44,22 @@ def test_batch_model_parameters(host, lanes, bpr):
     pr = host.Problem(3, 7, device=-1, n_lanes=lanes, batches_per_range=bpr)
     assert np.array_equal(pr.node_of_local(), rd.node_of_local.astype(np.uint64))
     assert np.array_equal(pr.entity_index(), rd.entity_index)
+    rc, rp = pr.ranges()
+    assert np.array_equal(rc, rd.range_cell_offset) and np.array_equal(rp, rd.range_private_offset)
+    pr.close()
+
+
+def test_private_runs_follow_the_grouping(host):
+    """only the cellbatch_range grouping (strategy g = 2) makes the DoFs private to a range one
+    contiguous run per range starting at DoF 0; for the other numberings the host hands no
+    range tables to the device (the vector updates are then streamed, never mis-hooked)"""
+    for r in (1, 2):
+        pr = host.Problem(3, 6, device=-1, renumber=(0, r, 2))
+        rc, rp = pr.ranges()
+        assert len(rc) == pr.n_ranges + 1 and rp[0] == 0 and rp[-1] > 0 and np.all(np.diff(rp.astype(np.int64)) >= 0)
+        pr.close()
+    pr = host.Problem(3, 6, device=-1, renumber=(0, 1, 0))
+    assert len(pr.ranges()[0]) == 0
     pr.close()
 
 

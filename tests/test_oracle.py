@@ -142,3 +142,57 @@ def test_renumbering_invariants():
             # constrained DoFs sit in the second group (touch count 0) unless shared between ranks
             g1 = rd.group_sizes[0]
             assert not np.any(rd.constrained < g1)
+
+
+@pytest.mark.parametrize("p,s", [(2, 6), (3, 6), (4, 7), (5, 5), (6, 5), (7, 4), (8, 4)])
+def test_c_kernels_agree(p, s, c_oracle_lib):
+    """the two C restatements of local_apply -- plain dense contractions and the even-odd,
+    z-layer-wise form that follows the reference's evaluation order (poisson_operator.h:442-447,
+    :534-666) -- and the numpy oracle give the same operator"""
+    rd = O.build_problem(p, s)[0]
+    co = COracle(rd)
+    v = np.random.default_rng(p + s).standard_normal(rd.n_owned)
+    c_oracle_lib.oracle_set_fast(0)
+    dense = co.vmult(v)
+    c_oracle_lib.oracle_set_fast(1)
+    fast = co.vmult(v)
+    assert rel_l2(fast, dense) <= 1e-14
+    assert rel_l2(fast, O.vmult(rd, O.make_tables(p), v)) <= 1e-13
+
+
+@pytest.mark.parametrize("p,s", [(3, 6), (4, 9), (2, 9), (6, 6)])
+def test_blocked_merged_cg_equals_sweeps(p, s, c_oracle_lib):
+    """the cache-blocked merged CG (vector updates per cell-batch range inside the loop, on the
+    DoF runs private to the range; the CPU baseline of bench.py) reproduces the full-sweep form:
+    same iteration count, same iterates up to summation order"""
+    rd = O.build_problem(p, s)[0]
+    co = COracle(rd)
+    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    x0, it0, h0 = co.cg(rd.rhs, prec, merged=True)
+    x1, it1, h1 = co.cg(rd.rhs, prec, merged=True, blocked=True)
+    assert it0 == it1
+    assert rel_l2(x1, x0) <= (1e-10 if it0 < 100 else 1e-6)
+    np.testing.assert_allclose(h1[:10], h0[:10], rtol=1e-12)
+
+
+def test_private_runs_are_private():
+    """every DoF of range r's private run is touched by cells of range r only, is not
+    constrained, and the runs tile [0, n_private) in range order (1 and 2 virtual ranks)"""
+    for n_ranks in (1, 2):
+        for rd in O.build_problem(3, 6, n_ranks=n_ranks):
+            m = O.local_dof_map(3, rd.entity_index)          # [cells][nodes] index of component 0 or -1
+            rc, rp = rd.range_cell_offset.astype(np.int64), rd.range_private_offset.astype(np.int64)
+            assert rp[0] == 0 and rp[-1] == rd.group_sizes[0] and np.all(np.diff(rp) >= 0)
+            range_of_cell = np.searchsorted(rc[1:], np.arange(rd.n_cells), side="right")
+            touched_by = {}
+            for c in range(rd.n_cells):
+                for i in m[c][m[c] >= 0]:
+                    touched_by.setdefault(int(i), set()).add(int(range_of_cell[c]))
+            con = set(int(i) for i in rd.constrained)
+            for r in range(len(rc) - 1):
+                assert rp[r] % 3 == 0
+                for i in range(rp[r], rp[r + 1], 3):         # component 0 of every node of the run
+                    assert touched_by[i] == {r} and i not in con
+            # and nothing outside the runs is private to a single range (owned, unconstrained, unshared)
+            n_single = sum(1 for i, rs in touched_by.items() if len(rs) == 1 and i < rd.n_owned and i not in con)
+            assert 3 * n_single >= rp[-1]                     # (rank-shared single-range nodes are excluded)
