@@ -151,6 +151,11 @@ int bp4_all_zero(bp4_ctx *ctx, const bp4_vec *v, int *result);
 #define BP4_NCCL_ID_BYTES 128
 int bp4_comm_unique_id(unsigned char id[BP4_NCCL_ID_BYTES]);                 /* rank 0 */
 int bp4_comm_init(bp4_ctx *ctx, int rank, int n_ranks, const unsigned char id[BP4_NCCL_ID_BYTES]);
+/* n_ranks of the communicator; peer_copies = 1 when the ghost exchange runs as copy-engine peer
+ * copies into IPC-shared buffers with stream-memory-operation flags (no SM involved; the analogue
+ * of the reference's USE_SHMEM path, benchmark.h:35, :105-108), 0 when it runs as NCCL send/recv
+ * (BP4_P2P=0, more than 16 ranks, or IPC / stream memory operations unavailable)             */
+int bp4_comm_info(bp4_ctx *ctx, int *n_ranks, int *peer_copies);
 int bp4_update_ghost_values(bp4_ctx *ctx, bp4_vec *v);   /* owners -> ghost copies            */
 int bp4_compress_add(bp4_ctx *ctx, bp4_vec *v);          /* ghost contributions -> owners, +=  */
 

@@ -2,6 +2,7 @@
 // Owns the device copies of the mesh data LaplaceOperator::initialize builds
 // (poisson_operator.h:101-293), the vectors, the stream and the reduction scratch.
 // There is no CPU fallback: every entry point needs a CUDA device.
+#include <cuda.h>
 #include <nccl.h>
 
 #include <cmath>
@@ -105,6 +106,24 @@ struct bp4_ctx
   std::vector<uint64_t> import_off, export_off;
   uint32_t             *d_export = nullptr;
   double               *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+  // Peer exchange without SMs (the USE_SHMEM analogue of benchmark.h:35, :105-108): every rank
+  // owns one IPC-shared arena [flags | ghost_in[2] | contrib_in[2]]; owners push their exported
+  // values into the peers' ghost_in with copy-engine peer copies, ghost holders push their
+  // contributions into the owners' contrib_in, and arrival / release is signalled with stream
+  // memory operations (cuStreamWriteValue64 / cuStreamWaitValue64) on the flag words -- nothing
+  // of it needs an SM, so it runs next to the persistent cell kernel.
+  struct P2P
+  {
+    bool                 on = false;
+    char                *arena = nullptr;           // my arena (device)
+    uint64_t             off_ghost[2] = {0, 0}, off_contrib[2] = {0, 0};
+    std::vector<char *>  peer_arena;                // [n_peers] mapped base of peer k's arena
+    std::vector<uint64_t> peer_off_ghost[2], peer_off_contrib[2]; // [n_peers] byte offsets there
+    std::vector<uint64_t> peer_imp_off, peer_exp_off; // [n_peers] where MY data goes (doubles)
+    uint64_t             epoch_fwd = 0, epoch_rev = 0;
+    CUresult (*write64)(CUstream, CUdeviceptr, cuuint64_t, unsigned) = nullptr;
+    CUresult (*wait64)(CUstream, CUdeviceptr, cuuint64_t, unsigned)  = nullptr;
+  } p2p;
   // freed vector buffers kept for reuse, keyed by size: plays the role of deal.II's
   // GrowingVectorMemory pool behind SolverCGFullMerge's temporaries (solver_cg_optimized.h:201)
   std::multimap<uint64_t, double *> pool;
@@ -198,6 +217,7 @@ namespace
 } // namespace
 
 extern "C" {
+static void p2p_teardown(bp4_ctx *c);
 
 const char *bp4_last_error(void) { return g_err.c_str(); }
 
@@ -425,6 +445,7 @@ int bp4_ctx_destroy(bp4_ctx *c)
   if (c->stream)
     cudaStreamSynchronize(c->stream);
   drain_events(c);
+  p2p_teardown(c);
   if (c->comm)
     ncclCommDestroy(c->comm);
   for (auto &kv : c->pool)
@@ -643,6 +664,9 @@ static int cell_range(bp4_ctx *c, double *dst, const double *src, int part, cons
 
 static int exchange_ghosts_on(bp4_ctx *c, double *v, cudaStream_t st);
 static int exchange_compress_on(bp4_ctx *c, double *v, cudaStream_t st);
+static const double *contrib_buffer(const bp4_ctx *c);
+static int compress_release(bp4_ctx *c, cudaStream_t st);
+
 
 // MatrixFree::cell_loop (poisson_operator.h:310, :339) on one rank: update_ghost_values(src),
 // cells, compress(add)(dst).  With a partitioned mesh the two exchanges run on a second stream
@@ -692,8 +716,10 @@ static int cell_loop(bp4_ctx *c, double *dst, const double *src, const MergedCal
     Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
     for (size_t k = 0; k < c->peer.size(); ++k) // per peer: an owned entry may be exported to several
       CU(bp4::launch_unpack_add(c->export_off[k + 1] - c->export_off[k], c->d_export + c->export_off[k],
-                                c->d_recvbuf + c->export_off[k], dst, c->stream));
+                                contrib_buffer(c) + c->export_off[k], dst, c->stream));
   }
+  if (int e = compress_release(c, c->stream))
+    return e;
   CU(cudaMemsetAsync(dst + c->n_owned, 0, sizeof(double) * c->n_ghost, c->stream));
   return 0;
 }
@@ -926,6 +952,138 @@ int bp4_comm_unique_id(unsigned char id[BP4_NCCL_ID_BYTES])
   return 0;
 }
 
+// ---- peer exchange over NVLink without SMs -------------------------------------------------
+namespace
+{
+  constexpr int kP2PMaxRanks = 16;
+  struct P2PCard // what every rank publishes about its arena
+  {
+    cudaIpcMemHandle_t handle;
+    uint64_t           off_ghost[2], off_contrib[2];
+    int64_t            imp_off_for[kP2PMaxRanks]; // my import offset (doubles) for owner r, or -1
+    int64_t            exp_off_for[kP2PMaxRanks]; // my export offset (doubles) for ghost holder r, or -1
+  };
+  enum
+  {
+    kFlagDataFwd = 0, // [r] owner r's ghost values of exchange e have landed in my ghost_in[e & 1]
+    kFlagAckFwd  = 1, // [r] ghost holder r has copied exchange e out of its ghost_in
+    kFlagDataRev = 2, // [r] ghost holder r's contributions of exchange e have landed in my contrib_in[e & 1]
+    kFlagAckRev  = 3  // [r] owner r has added exchange e into its vector
+  };
+  inline CUdeviceptr flag_addr(char *arena, int kind, int rank)
+  {
+    return (CUdeviceptr)(arena + sizeof(uint64_t) * (size_t)(kind * kP2PMaxRanks + rank));
+  }
+} // namespace
+
+#define DRV(call)                                                                              \
+  do                                                                                          \
+    {                                                                                         \
+      CUresult r_ = (call);                                                                   \
+      if (r_ != CUDA_SUCCESS)                                                                 \
+        return fail(BP4_ERR_CUDA, "%s:%d %s: driver error %d", __FILE__, __LINE__, #call, (int)r_); \
+    }                                                                                         \
+  while (0)
+
+static int p2p_setup(bp4_ctx *c)
+{
+  if (c->peer.empty() || c->n_ranks > kP2PMaxRanks)
+    return 0;
+  if (const char *e = getenv("BP4_P2P"))
+    if (atoi(e) == 0)
+      return 0; // developer knob: NCCL send/recv exchange
+  auto &p = c->p2p;
+  cudaDriverEntryPointQueryResult qr;
+  void *fw = nullptr, *fq = nullptr;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fw, cudaEnableDefault, &qr) != cudaSuccess || !fw ||
+      cudaGetDriverEntryPoint("cuStreamWaitValue64", &fq, cudaEnableDefault, &qr) != cudaSuccess || !fq)
+    {
+      cudaGetLastError();
+      return 0; // no stream memory operations: stay on NCCL
+    }
+  p.write64 = reinterpret_cast<decltype(p.write64)>(fw);
+  p.wait64  = reinterpret_cast<decltype(p.wait64)>(fq);
+  const uint64_t ne = c->export_off.back(), ni = c->import_off.back();
+  auto           up = [](uint64_t x) { return (x + 255) & ~uint64_t(255); };
+  P2PCard        mine{};
+  uint64_t       off = up(sizeof(uint64_t) * 4 * kP2PMaxRanks);
+  for (int k = 0; k < 2; ++k)
+    {
+      mine.off_ghost[k] = off;
+      off += up(sizeof(double) * (ni ? ni : 1));
+    }
+  for (int k = 0; k < 2; ++k)
+    {
+      mine.off_contrib[k] = off;
+      off += up(sizeof(double) * (ne ? ne : 1));
+    }
+  CU(cudaMalloc(&p.arena, off));
+  CU(cudaMemset(p.arena, 0, off));
+  CU(cudaIpcGetMemHandle(&mine.handle, p.arena));
+  for (int r = 0; r < kP2PMaxRanks; ++r)
+    mine.imp_off_for[r] = mine.exp_off_for[r] = -1;
+  for (size_t k = 0; k < c->peer.size(); ++k)
+    {
+      mine.imp_off_for[c->peer[k]] = (int64_t)c->import_off[k];
+      mine.exp_off_for[c->peer[k]] = (int64_t)c->export_off[k];
+    }
+  for (int k = 0; k < 2; ++k)
+    p.off_ghost[k] = mine.off_ghost[k], p.off_contrib[k] = mine.off_contrib[k];
+  // all-gather the cards through NCCL (device staging buffers)
+  P2PCard *d_mine = nullptr, *d_all = nullptr;
+  CU(cudaMalloc(&d_mine, sizeof(P2PCard)));
+  CU(cudaMalloc(&d_all, sizeof(P2PCard) * c->n_ranks));
+  CU(cudaMemcpy(d_mine, &mine, sizeof(P2PCard), cudaMemcpyHostToDevice));
+  NC(ncclAllGather(d_mine, d_all, sizeof(P2PCard), ncclChar, c->comm, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::vector<P2PCard> all(c->n_ranks);
+  CU(cudaMemcpy(all.data(), d_all, sizeof(P2PCard) * c->n_ranks, cudaMemcpyDeviceToHost));
+  CU(cudaFree(d_mine));
+  CU(cudaFree(d_all));
+  bool ok = true;
+  for (size_t k = 0; k < c->peer.size() && ok; ++k)
+    {
+      const P2PCard &q = all[c->peer[k]];
+      void          *base = nullptr;
+      if (cudaIpcOpenMemHandle(&base, q.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        {
+          cudaGetLastError();
+          ok = false;
+          break;
+        }
+      p.peer_arena.push_back((char *)base);
+      for (int b = 0; b < 2; ++b)
+        {
+          p.peer_off_ghost[b].push_back(q.off_ghost[b]);
+          p.peer_off_contrib[b].push_back(q.off_contrib[b]);
+        }
+      // my exports land in the peer's ghost block for me; my ghost contributions for that owner
+      // land in its contribution block for me
+      p.peer_imp_off.push_back((uint64_t)std::max<int64_t>(q.imp_off_for[c->rank], 0));
+      p.peer_exp_off.push_back((uint64_t)std::max<int64_t>(q.exp_off_for[c->rank], 0));
+    }
+  // every rank must take the same path: agree on the outcome
+  int *d_ok = nullptr, h_ok = ok ? 1 : 0;
+  CU(cudaMalloc(&d_ok, sizeof(int)));
+  CU(cudaMemcpy(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice));
+  NC(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  CU(cudaFree(d_ok));
+  p.on = h_ok == 1;
+  return 0;
+}
+
+static void p2p_teardown(bp4_ctx *c)
+{
+  for (char *b : c->p2p.peer_arena)
+    cudaIpcCloseMemHandle(b);
+  c->p2p.peer_arena.clear();
+  cudaFree(c->p2p.arena);
+  c->p2p.arena = nullptr;
+  c->p2p.on    = false;
+}
+
 int bp4_comm_init(bp4_ctx *c, int rank, int n_ranks, const unsigned char id[BP4_NCCL_ID_BYTES])
 {
   if (!c || !id)
@@ -936,13 +1094,55 @@ int bp4_comm_init(bp4_ctx *c, int rank, int n_ranks, const unsigned char id[BP4_
   NC(ncclCommInitRank(&c->comm, n_ranks, u, rank));
   c->rank    = rank;
   c->n_ranks = n_ranks;
+  return p2p_setup(c);
+}
+
+int bp4_comm_info(bp4_ctx *c, int *n_ranks, int *peer_copies)
+{
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  if (n_ranks)
+    *n_ranks = c->n_ranks;
+  if (peer_copies)
+    *peer_copies = c->p2p.on ? 1 : 0;
   return 0;
 }
 
-// NCCL part of update_ghost_values: the packed exports go out, ghosts come straight into the
-// (contiguous, per-owner) ghost blocks of v
+// update_ghost_values on stream st: the packed exports (d_sendbuf) go to the peers' ghost blocks.
+// NCCL form: send/recv straight into the (contiguous, per-owner) ghost blocks of v.
+// Peer-copy form: copy engine -> the peers' ghost_in[e & 1], flag; wait for my own ghosts, copy
+// them from ghost_in into v, release the buffer to the owners.
 static int exchange_ghosts_on(bp4_ctx *c, double *v, cudaStream_t st)
 {
+  auto &p = c->p2p;
+  if (p.on)
+    {
+      const uint64_t e = ++p.epoch_fwd;
+      const int      b = (int)(e & 1);
+      for (size_t k = 0; k < c->peer.size(); ++k)
+        {
+          const uint64_t ns = c->export_off[k + 1] - c->export_off[k];
+          if (!ns)
+            continue;
+          if (e > 2) // the peer has emptied this half of its ghost_in (exchange e - 2)
+            DRV(p.wait64((CUstream)st, flag_addr(p.arena, kFlagAckFwd, c->peer[k]), e - 2, CU_STREAM_WAIT_VALUE_GEQ));
+          CU(cudaMemcpyAsync(p.peer_arena[k] + p.peer_off_ghost[b][k] + sizeof(double) * p.peer_imp_off[k],
+                             c->d_sendbuf + c->export_off[k], sizeof(double) * ns, cudaMemcpyDeviceToDevice, st));
+          DRV(p.write64((CUstream)st, flag_addr(p.peer_arena[k], kFlagDataFwd, c->rank), e, CU_STREAM_WRITE_VALUE_DEFAULT));
+        }
+      for (size_t k = 0; k < c->peer.size(); ++k)
+        {
+          const uint64_t nr = c->import_off[k + 1] - c->import_off[k];
+          if (!nr)
+            continue;
+          DRV(p.wait64((CUstream)st, flag_addr(p.arena, kFlagDataFwd, c->peer[k]), e, CU_STREAM_WAIT_VALUE_GEQ));
+          CU(cudaMemcpyAsync(v + c->n_owned + c->import_off[k],
+                             p.arena + p.off_ghost[b] + sizeof(double) * c->import_off[k], sizeof(double) * nr,
+                             cudaMemcpyDeviceToDevice, st));
+          DRV(p.write64((CUstream)st, flag_addr(p.peer_arena[k], kFlagAckFwd, c->rank), e, CU_STREAM_WRITE_VALUE_DEFAULT));
+        }
+      return 0;
+    }
   NC(ncclGroupStart());
   for (size_t k = 0; k < c->peer.size(); ++k)
     {
@@ -956,9 +1156,31 @@ static int exchange_ghosts_on(bp4_ctx *c, double *v, cudaStream_t st)
   return 0;
 }
 
-// NCCL part of compress(add): ghost contributions go to their owners' receive buffer
+// compress(add) on stream st: the ghost slots of v travel to their owners; the owner side ends
+// with the contributions in contrib_buffer(c) ready for unpack_add (compress_release afterwards)
 static int exchange_compress_on(bp4_ctx *c, double *v, cudaStream_t st)
 {
+  auto &p = c->p2p;
+  if (p.on)
+    {
+      const uint64_t e = ++p.epoch_rev;
+      const int      b = (int)(e & 1);
+      for (size_t k = 0; k < c->peer.size(); ++k)
+        {
+          const uint64_t ns = c->import_off[k + 1] - c->import_off[k];
+          if (!ns)
+            continue;
+          if (e > 2)
+            DRV(p.wait64((CUstream)st, flag_addr(p.arena, kFlagAckRev, c->peer[k]), e - 2, CU_STREAM_WAIT_VALUE_GEQ));
+          CU(cudaMemcpyAsync(p.peer_arena[k] + p.peer_off_contrib[b][k] + sizeof(double) * p.peer_exp_off[k],
+                             v + c->n_owned + c->import_off[k], sizeof(double) * ns, cudaMemcpyDeviceToDevice, st));
+          DRV(p.write64((CUstream)st, flag_addr(p.peer_arena[k], kFlagDataRev, c->rank), e, CU_STREAM_WRITE_VALUE_DEFAULT));
+        }
+      for (size_t k = 0; k < c->peer.size(); ++k)
+        if (c->export_off[k + 1] > c->export_off[k])
+          DRV(p.wait64((CUstream)st, flag_addr(p.arena, kFlagDataRev, c->peer[k]), e, CU_STREAM_WAIT_VALUE_GEQ));
+      return 0;
+    }
   NC(ncclGroupStart());
   for (size_t k = 0; k < c->peer.size(); ++k)
     {
@@ -969,6 +1191,25 @@ static int exchange_compress_on(bp4_ctx *c, double *v, cudaStream_t st)
         NC(ncclRecv(c->d_recvbuf + c->export_off[k], nr, ncclDouble, c->peer[k], c->comm, st));
     }
   NC(ncclGroupEnd());
+  return 0;
+}
+
+// where the contributions of the last compress exchange wait for unpack_add
+static const double *contrib_buffer(const bp4_ctx *c)
+{
+  return c->p2p.on ? reinterpret_cast<const double *>(c->p2p.arena + c->p2p.off_contrib[c->p2p.epoch_rev & 1])
+                   : c->d_recvbuf;
+}
+
+// after unpack_add on stream st: hand this half of contrib_in back to the ghost holders
+static int compress_release(bp4_ctx *c, cudaStream_t st)
+{
+  auto &p = c->p2p;
+  if (p.on)
+    for (size_t k = 0; k < c->peer.size(); ++k)
+      if (c->export_off[k + 1] > c->export_off[k])
+        DRV(p.write64((CUstream)st, flag_addr(p.peer_arena[k], kFlagAckRev, c->rank), p.epoch_rev,
+                      CU_STREAM_WRITE_VALUE_DEFAULT));
   return 0;
 }
 
@@ -1003,8 +1244,10 @@ int bp4_compress_add(bp4_ctx *c, bp4_vec *v)
     Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
     for (size_t k = 0; k < c->peer.size(); ++k) // per peer: an owned entry may be exported to several
       CU(bp4::launch_unpack_add(c->export_off[k + 1] - c->export_off[k], c->d_export + c->export_off[k],
-                                c->d_recvbuf + c->export_off[k], v->p(), c->stream));
+                                contrib_buffer(c) + c->export_off[k], v->p(), c->stream));
   }
+  if (int e = compress_release(c, c->stream))
+    return e;
   CU(cudaMemsetAsync(v->p() + c->n_owned, 0, sizeof(double) * c->n_ghost, c->stream));
   return 0;
 }

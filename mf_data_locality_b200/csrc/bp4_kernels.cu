@@ -24,7 +24,10 @@
 #  define BP4_KU 4 // DoFs per thread and sweep of the in-loop do_cg_update4b / 3b
 #endif
 #ifndef BP4_DYNAMIC
-#  define BP4_DYNAMIC 1 // batches / units are claimed from an atomic counter instead of strided
+// batches / units are claimed from an atomic counter instead of strided.  Measured on B200 (operator
+// apply at ~50-100 M DoFs): Q2 +13 %, Q3 +5 %, Q4 +8 %, Q5 +11 %; Q6 -6 %, Q7 -11 %, Q8 -10 % (the
+// claim bookkeeping makes the register-starved high-degree kernels spill), hence P <= 5.
+#  define BP4_DYNAMIC(P) ((P) <= 5)
 #endif
 #ifndef BP4_L2_PREFETCH
 #  define BP4_L2_PREFETCH 1 // bulk L2 prefetch of the next-but-one batch's private DoFs
@@ -179,7 +182,7 @@ namespace bp4
       bool     valid;
     };
     const uint32_t n_units = FUSED ? a.n_units : (uint32_t)((a.n_cells + CPB - 1) / CPB);
-    const bool     dynamic = BP4_DYNAMIC && a.sched != nullptr;
+    const bool     dynamic = BP4_DYNAMIC(P) && a.sched != nullptr;
     auto           unit_at = [&](const uint32_t j) {
       return dynamic ? sm.units[j & 7u] : blockIdx.x + j * gridDim.x;
     };
