@@ -295,6 +295,10 @@ def main():
     L.bp4_fused_info(ctx, C.byref(fused_flag), C.byref(n_priv), C.byref(n_units))
     merged = args.solver == "merged"
     fused = merged and bool(fused_flag.value)
+    nr_, pc_ = C.c_int(), C.c_int()
+    L.bp4_comm_info(ctx, C.byref(nr_), C.byref(pc_))
+    exchange = None if world == 1 else ("copy-engine peer copies into IPC-shared buffers, stream-memory-op flags"
+                                        if pc_.value else "NCCL send/recv")
 
     def barrier():
         if world > 1:
@@ -426,7 +430,7 @@ def main():
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(prob.n_owned * 8),
                    "d2h_bytes_per_step": int(prob.n_owned * 8)},
            "gpu_launches": int(launches.value), "clocks": clocks, "roofline": roofline,
-           "cpu_baseline": cpu, "setup_seconds": setup_seconds, "sweep": sweep}
+           "cpu_baseline": cpu, "setup_seconds": setup_seconds, "ghost_exchange": exchange, "sweep": sweep}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

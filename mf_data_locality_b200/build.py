@@ -80,7 +80,7 @@ def build_host(force=False):
     deps = _sources(HOST, (".cc", ".h")) + [os.path.join(inc, "bp4.h"),
                                             os.path.join(HERE, "benchmark_precond", "bench.cc"),
                                             os.path.join(HERE, "benchmark_precond_merged", "bench.cc")]
-    common = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-I", inc]
+    common = ["/usr/bin/g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-Wall", "-I", inc]
     link = ["-L", HERE, "-lbp4", "-Wl,-rpath,$ORIGIN"]
     outs = []
     jobs = []

@@ -40,7 +40,7 @@ EXPORTS = [
     "bp4_last_error", "bp4_device_count", "bp4_ctx_create", "bp4_ctx_destroy", "bp4_ctx_synchronize",
     "bp4_ctx_stream", "bp4_vec_alloc", "bp4_vec_free", "bp4_vec_size", "bp4_vec_set_zero",
     "bp4_vec_upload", "bp4_vec_download", "bp4_vec_device_ptr", "bp4_vmult", "bp4_vmult_merged",
-    "bp4_vec_alloc_uninitialized", "bp4_debug_set_fused", "bp4_fused_info", "bp4_inverse_diagonal", "bp4_jacobi_vmult", "bp4_x_finalize_even",
+    "bp4_vec_alloc_uninitialized", "bp4_debug_set_fused", "bp4_fused_info", "bp4_inverse_diagonal", "bp4_inverse_diagonal_vector", "bp4_extract_component", "bp4_jacobi_vmult", "bp4_x_finalize_even",
     "bp4_equ", "bp4_add", "bp4_sadd", "bp4_dot", "bp4_add_and_dot", "bp4_l2_norm", "bp4_all_zero",
     "bp4_comm_unique_id", "bp4_comm_init", "bp4_comm_info", "bp4_update_ghost_values", "bp4_compress_add",
     "bp4_profile_enable", "bp4_profile_reset", "bp4_profile_get", "bp4_launch_count",

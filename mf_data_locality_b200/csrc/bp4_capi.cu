@@ -827,6 +827,44 @@ int bp4_inverse_diagonal(bp4_ctx *c, bp4_vec *out)
   return bp4_vec_free(c, tmp);
 }
 
+// the reference's own layout of the result (poisson_operator.h:392-426): a DoF vector whose
+// component-0 entries hold 1/diag of the scalar operator and every other entry is 1 (0 -> 1)
+int bp4_inverse_diagonal_vector(bp4_ctx *c, bp4_vec *out)
+{
+  if (!c)
+    return fail(BP4_ERR_ARG, "null ctx");
+  if (int e = check_len(c, out, "out"))
+    return e;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(out->p(), 0, sizeof(double) * (c->n_owned + c->n_ghost), c->stream));
+  {
+    Timed t(c, BP4_K_BLAS1, 2);
+    CU(bp4::launch_diag_assemble(c->degree, c->n_cells, c->d_entity, c->d_coef, c->d_gll, out->p(), 3,
+                                 c->stream));
+  }
+  if (!c->peer.empty())
+    if (int e = bp4_compress_add(c, out))
+      return e;
+  CU(bp4::launch_diag_invert(c->n_owned, out->p(), c->stream));
+  return 0;
+}
+
+// dst[i] = src[n_components * i + component]: the extraction loop of benchmark.h:141-147
+int bp4_extract_component(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src, int n_components, int component)
+{
+  if (!c || !dst || !src)
+    return fail(BP4_ERR_ARG, "null argument");
+  if (n_components != 3 || component < 0 || component > 2)
+    return fail(BP4_ERR_ARG, "three components per node");
+  if (src->n < c->n_owned || dst->n < c->n_owned / 3)
+    return fail(BP4_ERR_ARG, "Dimension mismatch %llu vs 3 x %llu", (unsigned long long)src->n,
+                (unsigned long long)dst->n);
+  CU(cudaSetDevice(c->device));
+  Timed t(c, BP4_K_BLAS1);
+  CU(bp4::launch_stride3(c->n_owned / 3, src->p() + component, dst->p(), c->stream));
+  return 0;
+}
+
 int bp4_jacobi_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src, const bp4_vec *diag)
 {
   if (!c || !dst || !src || !diag)

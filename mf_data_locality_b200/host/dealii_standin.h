@@ -21,6 +21,7 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #define AssertThrow(cond, msg)         \
@@ -33,6 +34,34 @@
 
 namespace dealii
 {
+  // f(begin, end) on disjoint chunks of [0, n), one host thread per chunk (set-up loops over cells)
+  template <typename F>
+  inline void parallel_chunks(const std::uint64_t n, F &&f)
+  {
+    const unsigned int nt = (unsigned int)std::max<std::uint64_t>(
+      1, std::min<std::uint64_t>({(std::uint64_t)std::thread::hardware_concurrency(), 16, n / 4096 + 1}));
+    std::vector<std::string> errors(nt);
+    std::vector<std::thread> workers;
+    auto                     run = [&](const unsigned int t) {
+      try
+        {
+          f(n * t / nt, n * (t + 1) / nt);
+        }
+      catch (const std::exception &e)
+        {
+          errors[t] = e.what();
+        }
+    };
+    for (unsigned int t = 1; t < nt; ++t)
+      workers.emplace_back(run, t);
+    run(0);
+    for (auto &w : workers)
+      w.join();
+    for (const auto &e : errors)
+      if (!e.empty())
+        throw std::runtime_error(e);
+  }
+
   namespace types
   {
     using global_dof_index = std::uint64_t;

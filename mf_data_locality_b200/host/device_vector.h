@@ -7,6 +7,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace dealii
@@ -31,7 +32,21 @@ namespace dealii
         Vector() = default;
         Vector(const Vector &) = delete;
         Vector &operator=(const Vector &) = delete;
+        Vector(Vector &&o) noexcept { swap(o); }
+        Vector &operator=(Vector &&o) noexcept
+        {
+          swap(o);
+          return *this;
+        }
         ~Vector() { release(); }
+        void swap(Vector &o) noexcept
+        {
+          std::swap(ctx, o.ctx);
+          std::swap(h, o.h);
+          std::swap(n_local, o.n_local);
+          std::swap(n_ghost, o.n_ghost);
+          std::swap(n_global, o.n_global);
+        }
 
         // n_local entries are owned, the vector additionally carries n_ghost ghost slots
         void reinit(bp4_ctx *ctx_, std::uint64_t n_local_, std::uint64_t n_ghost_ = 0,
@@ -89,6 +104,12 @@ namespace dealii
           int r;
           bp4_check(bp4_all_zero(ctx, h, &r));
           return r != 0;
+        }
+        // this[i] = v[n_components * i + component] on the device: the element loop of
+        // benchmark.h:141-147 (local_element(i) = vector.local_element(i * n_components))
+        void extract_component(const Vector &v, const unsigned int n_components, const unsigned int component)
+        {
+          bp4_check(bp4_extract_component(ctx, h, v.h, (int)n_components, (int)component));
         }
         void upload(const Number *host, std::uint64_t n) { bp4_check(bp4_vec_upload(ctx, h, host, n)); }
         void download(Number *host, std::uint64_t n) const { bp4_check(bp4_vec_download(ctx, h, host, n)); }

@@ -19,8 +19,11 @@ namespace Poisson
 {
   using namespace dealii;
 
+  // VectorizedArrayType is the reference's seventh parameter (poisson_operator.h:67-74): the SIMD
+  // type of its CPU kernels.  Accepted and ignored so that reference call sites compile unchanged.
   template <int dim, int fe_degree, int n_q_points_1d = fe_degree + 1, int n_components_ = 1,
-            typename Number = double, typename VectorType = LinearAlgebra::distributed::Vector<Number>>
+            typename Number = double, typename VectorType = LinearAlgebra::distributed::Vector<Number>,
+            typename VectorizedArrayType = void>
   class LaplaceOperator
   {
   public:
@@ -50,10 +53,11 @@ namespace Poisson
       cell_vertices.resize(std::size_t(24) * n_cells);
       constexpr unsigned int p = fe_degree;
       const unsigned int lo[3] = {0, 1, p}, hi[3] = {1, p, p + 1};
-      for (unsigned int b = 0, cell_no = 0; b < data->n_cell_batches(); ++b)
-        for (unsigned int l = 0; l < data->n_active_entries_per_cell_batch(b); ++l, ++cell_no)
+      // cells in loop order (batch by batch, lane by lane); the per-cell work is independent
+      parallel_chunks(n_cells, [&](const std::uint64_t c0, const std::uint64_t c1) {
+        for (std::uint64_t cell_no = c0; cell_no < c1; ++cell_no)
           {
-            const std::uint64_t cell = data->get_cell(b, l);
+            const std::uint64_t cell = data->cell_order[cell_no];
             for (unsigned int v = 0; v < 8; ++v)
               {
                 const Point3 x = dh.get_triangulation().vertex(cell, v);
@@ -78,6 +82,7 @@ namespace Poisson
                 compressed_dof_indices[27 * std::size_t(cell_no) + a] = part.global_to_local(g0);
               }
           }
+      });
 
       compute_private_ranges(dh, constraints, part);
 
@@ -135,16 +140,16 @@ namespace Poisson
     }
 
     // Inverse diagonal of the scalar Laplacian under the quadrature this operator was set up
-    // with (the reference instantiates it with GLL(p+1), benchmark.h:128-140), 1 where the
-    // diagonal is 0.  The reference returns a DoF-sized vector whose every third entry is
-    // then copied into the blocked diagonal (poisson_operator.h:392-426, benchmark.h:141-147);
-    // here the per-node values are produced directly in that final layout.
-    void compute_inverse_diagonal(VectorType &per_node) const
+    // with (the reference instantiates it with GLL(p+1), benchmark.h:128-140), returned the way
+    // the reference returns it (poisson_operator.h:392-426): a DoF vector with 1/diag on the
+    // first component of every node and 1 wherever the assembled value is 0.  The caller keeps
+    // every n_components-th entry (benchmark.h:141-147).
+    VectorType compute_inverse_diagonal() const
     {
-      const Utilities::MPI::Partitioner &part = *data->get_dof_info().vector_partitioner;
-      per_node.reinit(ctx, part.locally_owned_size() / n_components, 0,
-                      data->get_dof_handler().n_dofs() / n_components);
-      bp4_check(bp4_inverse_diagonal(ctx, per_node.handle()));
+      VectorType diag;
+      initialize_dof_vector(diag);
+      bp4_check(bp4_inverse_diagonal_vector(ctx, diag.handle()));
+      return diag;
     }
 
     // cell-batch ranges of the loop and the owned DoFs private to each (bp4_desc::n_ranges)

@@ -19,6 +19,7 @@
 //    poisson_operator.h:198); it is listed as "next"  and throws here.
 #pragma once
 #include <sstream>
+#include <thread>
 
 #include "matrix_free_standin.h"
 
@@ -40,8 +41,8 @@ public:
     AssertThrow(renumber_strat <= 2 && grouping_strat <= 2, "unknown renumbering strategy");
     const unsigned int         n_ranks = dof_handler.get_triangulation().n_ranks;
     std::vector<std::uint32_t> new_node_number(dof_handler.n_nodes);
-    for (unsigned int rank = 0; rank < n_ranks; ++rank)
-      {
+    // the ranks' numberings are independent of each other: one host thread per rank
+    auto renumber_rank = [&](const unsigned int rank) {
         dealii::MatrixFree matrix_free;
         matrix_free.reinit(dof_handler, constraints, dof_handler.get_fe().degree + 1, mf_data, (int)rank);
         const std::uint64_t first = dof_handler.rank_offset[rank],
@@ -59,7 +60,32 @@ public:
         for (std::uint64_t n = 0; n < dof_handler.n_nodes; ++n)
           if (dof_handler.owner[n] == rank)
             new_node_number[n] = new_of_old[dof_handler.node_number[n] - first];
+    };
+    std::vector<std::string> errors(n_ranks);
+    std::vector<std::thread> workers;
+    for (unsigned int rank = 1; rank < n_ranks; ++rank)
+      workers.emplace_back([&, rank] {
+        try
+          {
+            renumber_rank(rank);
+          }
+        catch (const std::exception &e)
+          {
+            errors[rank] = e.what();
+          }
+      });
+    try
+      {
+        renumber_rank(0);
       }
+    catch (const std::exception &e)
+      {
+        errors[0] = e.what();
+      }
+    for (auto &w : workers)
+      w.join();
+    for (const auto &e : errors)
+      AssertThrow(e.empty(), e);
     dof_handler.node_number.swap(new_node_number);
   }
 
@@ -171,10 +197,17 @@ private:
     for (std::uint64_t n = 0; n < dh.n_nodes; ++n)
       if (dh.owner[n] == rank && dh.shared[n])
         group[dh.node_number[n] - first] = 2;
-    // stable order by key inside each group
+    // order by key inside each group.  First-touch keys are a permutation of 0 .. n_own-1: one
+    // scatter instead of a sort; last-touch keys have gaps (every touch draws a new number)
     std::vector<std::uint32_t> by_key(n_own);
-    std::iota(by_key.begin(), by_key.end(), 0u);
-    std::sort(by_key.begin(), by_key.end(), [&](std::uint32_t a, std::uint32_t b) { return key[a] < key[b]; });
+    if (renumber_strat == 1)
+      for (std::uint64_t i = 0; i < n_own; ++i)
+        by_key[key[i]] = (std::uint32_t)i;
+    else
+      {
+        std::iota(by_key.begin(), by_key.end(), 0u);
+        std::sort(by_key.begin(), by_key.end(), [&](std::uint32_t a, std::uint32_t b) { return key[a] < key[b]; });
+      }
     std::vector<std::uint32_t> out;
     out.reserve(n_own);
     for (unsigned char g = 0; g < 3; ++g)

@@ -52,8 +52,8 @@ public:
                                                 it % 2 == 1 ? alpha_old : number(0.), beta_old);
         alpha_old = alpha;
         beta_old  = beta;
-        if (s[0] == 0.)
-          throw std::runtime_error("SolverCGFullMerge: division by zero");
+        // s[0] == 0 is a debug-only Assert in the reference (:249); a release build lets the
+        // NaN travel into the residual, which the control reports as failure -> NoConvergence
         alpha    = s[6] / s[0];                                              // r.Pr / d.Ad
         res_norm = std::sqrt(s[3] + 2 * alpha * s[2] + alpha * alpha * s[1]); // |r + alpha h|
         conv     = this->iteration_status(it, res_norm, x);

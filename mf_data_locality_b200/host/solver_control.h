@@ -4,6 +4,7 @@
 // through the vector stand-in.
 #pragma once
 #include <cmath>
+#include <limits>
 #include <stdexcept>
 
 namespace dealii
@@ -58,7 +59,7 @@ namespace dealii
           initial_val = check_value;
           reduced_tol = check_value * reduce;
         }
-      if (check_value <= reduced_tol)
+      if (check_value < reduced_tol) // strict, as in deal.II's ReductionControl::check
         {
           lstep  = step;
           lvalue = check_value;
@@ -118,10 +119,8 @@ namespace dealii
         {
           it++;
           A.vmult(h, d);
-          double alpha = d * h;
-          if (alpha == 0.)
-            throw std::runtime_error("SolverCG: division by zero");
-          alpha = gh / alpha;
+          double alpha = d * h; // deal.II asserts alpha != 0 in debug builds only
+          alpha        = gh / alpha;
           x.add(alpha, d);
           res  = std::sqrt(std::abs(g.add_and_dot(alpha, h, g)));
           conv = this->iteration_status(it, res, x);

@@ -187,7 +187,7 @@ static int check(int step, double v, int max_steps, double tol, double reduce, d
 {
   if (step == 0)
     *reduced_tol = v * reduce;
-  if (v <= *reduced_tol || v <= tol)
+  if (v < *reduced_tol || v <= tol) /* strict for the reduced tolerance, as in deal.II */
     return 1;
   if (step >= max_steps || isnan(v))
     return 2;

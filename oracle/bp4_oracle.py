@@ -592,7 +592,7 @@ class ReductionControl:
             self.reduced_tol = value * self.reduce
         self.last_step, self.last_value = step, value
         self.history.append(value)
-        if value <= self.reduced_tol or value <= self.tol:
+        if value < self.reduced_tol or value <= self.tol:      # strict for the reduced tolerance (deal.II)
             return "success"
         if step >= self.max_steps or math.isnan(value):
             return "failure"
