@@ -79,6 +79,7 @@ struct BenchmarkOptions
   // multi-GPU: the 128-byte ncclUniqueId all ranks share (created by rank 0 with
   // bp4_comm_unique_id and distributed by the launcher); plays the role of MPI_COMM_WORLD
   const unsigned char *nccl_id = nullptr;
+  bool numbering_only = false; // stop after Renumber + MatrixFree::reinit (inspection of numberings)
 };
 
 class Timer
@@ -141,6 +142,8 @@ struct BenchmarkProblem
     // the device routine evaluates exactly that quadrature
     matrix_free->reinit(dof_handler, constraints, n_q_points, mf_data);
     tick("matrix_free.reinit");
+    if (opt.numbering_only)
+      return;
     laplace_operator.initialize(matrix_free, constraints, opt.device);
     tick("operator.initialize");
     if (opt.device < 0)

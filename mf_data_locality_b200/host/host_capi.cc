@@ -80,7 +80,8 @@ const char *bp4h_plugin(void)
 #endif
 }
 
-// options: [n_ranks, rank, device, n_lanes, batches_per_range, renumber_a, renumber_r, renumber_g]
+// options: [n_ranks, rank, device, n_lanes, batches_per_range, renumber_a, renumber_r, renumber_g,
+//           numbering_only]
 int bp4h_create(int degree, int s, const int *options, const unsigned char *nccl_id, void **out)
 {
   return guarded([&] {
@@ -91,6 +92,7 @@ int bp4h_create(int degree, int s, const int *options, const unsigned char *nccl
         opt.n_ranks = options[0], opt.rank = options[1], opt.device = options[2];
         opt.n_lanes = options[3], opt.batches_per_range = options[4];
         opt.renumber_a = options[5], opt.renumber_r = options[6], opt.renumber_g = options[7];
+        opt.numbering_only = options[8] != 0;
       }
     Timer        t;
     ProblemBase *p = nullptr;

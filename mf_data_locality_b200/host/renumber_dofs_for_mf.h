@@ -14,9 +14,12 @@
 //  * Every process computes the numbering of ALL ranks (the mesh is structured and cheap to
 //    re-derive), which replaces the ghost-number exchange inside
 //    DoFHandler::renumber_dofs (renumber_dofs_for_mf.h:144).
-//  * assembly strategy 1 (cellbatch_assembly, :363-459) interleaves components of different
-//    nodes, which the compressed operator rejects ("Expected contiguous numbering",
-//    poisson_operator.h:198); it is listed as "next"  and throws here.
+//  * assembly strategy 1 (cellbatch_assembly, :363-459) numbers batch by batch, FE_Q slot by
+//    slot, lane by lane.  The reference walks the (p+1)^3 slots of a scalar element there; on
+//    lattice nodes that is exactly this walk.  It interleaves the nodes of one entity over the
+//    cells of a batch, so for p >= 3 LaplaceOperator::initialize rejects the result ("Expected
+//    contiguous numbering", poisson_operator.h:198) -- in the reference as here; for p = 2
+//    (one node per entity) it is a valid input of the operator.
 #pragma once
 #include <sstream>
 #include <thread>
@@ -37,8 +40,8 @@ public:
     static_assert(dim == 3, "the BP4 path is three-dimensional");
     if (renumber_strat == 0) // "base": keep the numbering (renumber_dofs_for_mf.h:111-113)
       return;
-    AssertThrow(assembly_strat == 0, "cellbatch assembly is not supported by the compressed operator");
-    AssertThrow(renumber_strat <= 2 && grouping_strat <= 2, "unknown renumbering strategy");
+    AssertThrow(assembly_strat <= 1 && renumber_strat <= 2 && grouping_strat <= 2,
+                "unknown renumbering strategy");
     const unsigned int         n_ranks = dof_handler.get_triangulation().n_ranks;
     std::vector<std::uint32_t> new_node_number(dof_handler.n_nodes);
     // the ranks' numberings are independent of each other: one host thread per rank
@@ -117,7 +120,48 @@ private:
       }
   }
 
-  // cell_assembly with first_touch_renumber / last_touch_renumber (:247-361, :461-490)
+  // cell-local nodes (i, j, k) in deal.II's FE_Q<3>(p) numbering: 8 vertices, 12 lines, 6 quads
+  // (local coordinates (y,z), (z,x), (x,y), first one fastest), interior -- the order `cf` runs
+  // through in cellbatch_assembly (renumber_dofs_for_mf.h:394-456)
+  static std::vector<std::array<unsigned int, 3>> fe_q_walk(const unsigned int p)
+  {
+    std::vector<std::array<unsigned int, 3>> w;
+    for (unsigned int v = 0; v < 8; ++v)
+      w.push_back({{(v & 1) * p, ((v >> 1) & 1) * p, ((v >> 2) & 1) * p}});
+    for (unsigned int z : {0u, p})
+      {
+        for (unsigned int x : {0u, p})
+          for (unsigned int t = 1; t < p; ++t)
+            w.push_back({{x, t, z}});
+        for (unsigned int y : {0u, p})
+          for (unsigned int t = 1; t < p; ++t)
+            w.push_back({{t, y, z}});
+      }
+    for (unsigned int y : {0u, p})
+      for (unsigned int x : {0u, p})
+        for (unsigned int t = 1; t < p; ++t)
+          w.push_back({{x, y, t}});
+    for (unsigned int x : {0u, p})
+      for (unsigned int b = 1; b < p; ++b)
+        for (unsigned int a = 1; a < p; ++a)
+          w.push_back({{x, a, b}});
+    for (unsigned int y : {0u, p})
+      for (unsigned int a = 1; a < p; ++a)
+        for (unsigned int b = 1; b < p; ++b)
+          w.push_back({{a, y, b}});
+    for (unsigned int z : {0u, p})
+      for (unsigned int b = 1; b < p; ++b)
+        for (unsigned int a = 1; a < p; ++a)
+          w.push_back({{a, b, z}});
+    for (unsigned int k = 1; k < p; ++k)
+      for (unsigned int j = 1; j < p; ++j)
+        for (unsigned int i = 1; i < p; ++i)
+          w.push_back({{i, j, k}});
+    return w;
+  }
+
+  // cell_assembly / cellbatch_assembly with first_touch_renumber / last_touch_renumber
+  // (:247-361, :363-459, :461-490)
   std::vector<std::uint64_t> cell_assembly(const dealii::MatrixFree &mf) const
   {
     const dealii::DoFHandler &dh    = mf.get_dof_handler();
@@ -126,20 +170,30 @@ private:
     constexpr std::uint64_t   unset = ~std::uint64_t(0);
     std::vector<std::uint64_t> key(n_own, unset);
     std::uint64_t              counter = 0;
-    for (unsigned int b = 0; b < mf.n_cell_batches(); ++b)
-      for (unsigned int l = 0; l < mf.n_active_entries_per_cell_batch(b); ++l)
-        walk_cell_objects(dh, mf.get_cell(b, l), [&](const std::uint64_t node, unsigned int) {
-          if (dh.owner[node] != rank)
-            return;
-          std::uint64_t &k = key[dh.node_number[node] - first];
-          if (renumber_strat == 1)
-            {
-              if (k == unset)
-                k = counter++;
-            }
-          else // last touch: the by-value set copy at :481 makes every touch renumber
+    auto touch = [&](const std::uint64_t node) {
+      if (dh.owner[node] != rank)
+        return;
+      std::uint64_t &k = key[dh.node_number[node] - first];
+      if (renumber_strat == 1)
+        {
+          if (k == unset)
             k = counter++;
-        });
+        }
+      else // last touch: the by-value set copy at :481 makes every touch renumber
+        k = counter++;
+    };
+    if (assembly_strat == 0)
+      for (unsigned int b = 0; b < mf.n_cell_batches(); ++b)
+        for (unsigned int l = 0; l < mf.n_active_entries_per_cell_batch(b); ++l)
+          walk_cell_objects(dh, mf.get_cell(b, l), [&](const std::uint64_t node, unsigned int) { touch(node); });
+    else
+      {
+        const auto slots = fe_q_walk(dh.get_fe().degree);
+        for (unsigned int b = 0; b < mf.n_cell_batches(); ++b)
+          for (const auto &ijk : slots)
+            for (unsigned int l = 0; l < mf.n_active_entries_per_cell_batch(b); ++l)
+              touch(dh.cell_node(mf.get_cell(b, l), ijk[0], ijk[1], ijk[2]));
+      }
     for (const std::uint64_t k : key)
       AssertThrow(k != unset, "owned node never touched by a local cell");
     return key;

@@ -252,8 +252,31 @@ def _lattice(p, n):
     return [n[d] * p + 1 for d in range(3)]
 
 
+def fe_q_walk(p: int) -> np.ndarray:
+    """Cell-local nodes (i,j,k) in deal.II's FE_Q<3>(p) numbering -- 8 vertices (x + 2y + 4z),
+    12 lines (0-3 bottom: x=0, x=1 along y, y=0, y=1 along x; 4-7 the same on top; 8-11 vertical at
+    (0,0), (1,0), (0,1), (1,1)), 6 quads (x=0, x=1, y=0, y=1, z=0, z=1; local coordinates (y,z),
+    (z,x), (x,y), first one fastest), interior lexicographic -- the order `cf` runs through in
+    Renumber::cellbatch_assembly (renumber_dofs_for_mf.h:394-456)."""
+    r = range(1, p)
+    w = [((v & 1) * p, ((v >> 1) & 1) * p, ((v >> 2) & 1) * p) for v in range(8)]
+    for z in (0, p):
+        w += [(0, t, z) for t in r] + [(p, t, z) for t in r] + [(t, 0, z) for t in r] + [(t, p, z) for t in r]
+    for (x, y) in ((0, 0), (p, 0), (0, p), (p, p)):
+        w += [(x, y, t) for t in r]
+    for x in (0, p):
+        w += [(x, a, b) for b in r for a in r]            # y fastest, z slow
+    for y in (0, p):
+        w += [(a, y, b) for a in r for b in r]            # z fastest, x slow
+    for z in (0, p):
+        w += [(a, b, z) for b in r for a in r]            # x fastest, y slow
+    w += [(i, j, k) for k in r for j in r for i in r]
+    assert len(w) == (p + 1) ** 3 and len(set(w)) == len(w)
+    return np.array(w, dtype=np.int64)
+
+
 def build_problem(degree: int, s: int, n_ranks: int = 1, lanes: int = 8,
-                  batches_per_range: int = 1) -> list[RankData]:
+                  batches_per_range: int = 1, renumber=(0, 1, 2)) -> list[RankData]:
     """Problem definition of run_templated (benchmark.h:66-176) for `n_ranks` virtual
     MPI ranks: mesh, Q_p^3 DoFs, Dirichlet set, Renumber(0,1,2) numbering,
     LaplaceOperator::initialize data (poisson_operator.h:161-267) and the RHS.
@@ -261,8 +284,18 @@ def build_problem(degree: int, s: int, n_ranks: int = 1, lanes: int = 8,
     deal.II behaviours that are not in the reference tree are explicit parameters
     (SURVEY App. B1/B4): `lanes` = VectorizedArray<double>::size(), `batches_per_range`
     = cell batches per cell_partition_data range.  Ranks own equal contiguous chunks
-    of the active-cell order (p4est), an interface node belongs to the lowest rank."""
+    of the active-cell order (p4est), an interface node belongs to the lowest rank.
+
+    renumber = (assembly, renumber, grouping) strategy triple of Renumber's constructor
+    (renumber_dofs_for_mf.h:17-21): assembly 0 cell / 1 cellbatch (:247-361 / :363-459), renumber
+    1 first touch / 2 last touch (:461-490; the by-value set copy at :481 makes EVERY touch draw
+    a new number, i.e. the order of last touches), grouping 0 base / 1 cellbatch / 2
+    cellbatch_range (:537-671).  The benchmark uses (0, 1, 2) (benchmark.h:112).  The entity
+    indices are only meaningful for numberings that keep every entity contiguous; for the others
+    `contiguous` is False (LaplaceOperator::initialize would throw, poisson_operator.h:198)."""
     p = degree
+    assembly_strat, renumber_strat, grouping_strat = renumber
+    assert assembly_strat in (0, 1) and renumber_strat in (1, 2) and grouping_strat in (0, 1, 2)
     _, _, n = mesh_dims(s)
     NI, NJ, NK = _lattice(p, n)
     n_nodes = NI * NJ * NK
@@ -332,24 +365,49 @@ def build_problem(degree: int, s: int, n_ranks: int = 1, lanes: int = 8,
         range_start = np.array(range_start)
         part_start = np.array(part_start)
 
-        # first touch (cell_assembly + first_touch_renumber, :320-358, :461-474)
+        # traversal of the numbering pass: cell by cell in entity-walk order (cell_assembly,
+        # :320-358), or batch by batch, FE_Q slot by slot, lane by lane (cellbatch_assembly, :378-456)
         flat = nodes_r.ravel()
+        if assembly_strat == 1:
+            fw = fe_q_walk(p)
+            fe_nodes = ((cells_r[:, 2:3] * p + fw[None, :, 2]) * NJ + cells_r[:, 1:2] * p + fw[None, :, 1]) * NI \
+                + cells_r[:, 0:1] * p + fw[None, :, 0]
+            trav = np.concatenate([fe_nodes[batch_start[b]:batch_start[b + 1]].T.ravel()
+                                   for b in range(len(batch_start) - 1)]) if len(cells_r) else flat
+        else:
+            trav = flat
+        # first touch (first_touch_renumber, :461-474) / last touch (:476-490) key per owned node
+        if renumber_strat == 1:
+            uniq_t, pos_t = np.unique(trav, return_index=True)
+        else:
+            uniq_t, pos_r = np.unique(trav[::-1], return_index=True)
+            pos_t = len(trav) - 1 - pos_r
         uniq, first_pos = np.unique(flat, return_index=True)
+        assert np.array_equal(uniq, uniq_t)
         owned_mask = owner[uniq] == r
         owned_nodes = uniq[owned_mask]
-        ft = first_pos[owned_mask]                       # first-touch key (unique)
+        ft = pos_t[owned_mask]                           # ordering key (unique)
+        first_cell = first_pos[owned_mask] // npc        # first cell touching the node (loop order)
         # touch count over cell-batch ranges (touch_count_cellbatch_range, :622-671);
         # constrained DoFs are not in MatrixFree's index lists -> count 0
-        cell_range = np.searchsorted(range_start[1:], np.searchsorted(batch_start[1:], np.arange(len(cells_r)), side="right"), side="right")
-        pair = np.unique(flat.astype(np.int64) * (len(range_start)) + np.repeat(cell_range, npc))
-        cnt_nodes, cnt = np.unique(pair // len(range_start), return_counts=True)
+        cell_batch = np.searchsorted(batch_start[1:], np.arange(len(cells_r)), side="right")
+        cell_range = np.searchsorted(range_start[1:], cell_batch, side="right")
+        # grouping 1 counts cell batches (touch_count_cellbatch, :592-620), 2 counts ranges
+        cell_group = cell_batch if grouping_strat == 1 else cell_range
+        n_grp = len(batch_start) if grouping_strat == 1 else len(range_start)
+        pair = np.unique(flat.astype(np.int64) * n_grp + np.repeat(cell_group, npc))
+        cnt_nodes, cnt = np.unique(pair // n_grp, return_counts=True)
         tc = np.zeros(n_nodes, dtype=np.int64)
         tc[cnt_nodes] = cnt
         tc[on_bnd] = 0
         tco = tc[owned_nodes]
         mo = multi[owned_nodes]
-        g1 = (~mo) & (tco == 1)
-        g2 = (~mo) & (tco != 1)
+        if grouping_strat == 0:                          # base_grouping, :537-554
+            g1 = ~mo
+            g2 = np.zeros_like(mo)
+        else:
+            g1 = (~mo) & (tco == 1)
+            g2 = (~mo) & (tco != 1)
         g3 = mo
         seq = []
         for g in (g1, g2, g3):                           # grouping, :492-535, :556-590
@@ -357,9 +415,13 @@ def build_problem(degree: int, s: int, n_ranks: int = 1, lanes: int = 8,
             seq.append(idx[np.argsort(ft[idx], kind="stable")])
         # group-1 nodes per range: the (only) range touching such a node is that of its first touch
         n_rng = len(range_start) - 1
-        priv_cnt = np.bincount(cell_range[ft[g1] // npc], minlength=n_rng) if n_rng else np.zeros(0, dtype=np.int64)
-        range_private_offset = 3 * np.concatenate(([0], np.cumsum(priv_cnt)))
-        range_cell_offset = batch_start[range_start]
+        # (only the cellbatch_range grouping of cell-wise numberings makes these runs contiguous)
+        if renumber == (0, 1, 2) or renumber == (0, 2, 2):
+            priv_cnt = np.bincount(cell_range[first_cell[g1]], minlength=n_rng) if n_rng else np.zeros(0, dtype=np.int64)
+            range_private_offset = 3 * np.concatenate(([0], np.cumsum(priv_cnt)))
+            range_cell_offset = batch_start[range_start]
+        else:
+            range_private_offset = range_cell_offset = np.zeros(0, dtype=np.int64)
         seq = np.concatenate(seq)
         new_nodes = owned_nodes[seq]                     # lattice node at each new local position
         new_local[new_nodes] = np.arange(len(new_nodes))

@@ -63,14 +63,35 @@ def test_private_runs_follow_the_grouping(host):
     pr.close()
 
 
+STRATEGIES = [(a, r, g) for a in (0, 1) for r in (1, 2) for g in (0, 1, 2)]
+
+
+@pytest.mark.parametrize("strategy", STRATEGIES)
+@pytest.mark.parametrize("p,s,n_ranks", [(3, 6, 1), (2, 7, 2), (4, 6, 4)])
+def test_all_renumber_strategies_bit_exact(host, strategy, p, s, n_ranks):
+    """every (assembly, renumber, grouping) triple of Renumber's constructor
+    (renumber_dofs_for_mf.h:17-21) gives the same permutation and ghost sets in the C++ host
+    mirror and in the numpy oracle"""
+    rds = O.build_problem(p, s, n_ranks=n_ranks, renumber=strategy)
+    for r, rd in enumerate(rds):
+        pr = host.Problem(p, s, device=-1, n_ranks=n_ranks, rank=r, renumber=strategy, numbering_only=True)
+        assert np.array_equal(pr.node_of_local(), rd.node_of_local.astype(np.uint64))
+        pr.close()
+
+
 def test_renumber_strategies(host):
     """base numbering is rejected by the compressed operator, like the reference's AssertThrow
-    "Expected contiguous numbering" (poisson_operator.h:198); first/last touch and the three
-    groupings all deliver contiguous entities"""
+    "Expected contiguous numbering" (poisson_operator.h:198), and so is the cellbatch assembly
+    for p >= 3 (it interleaves an entity's nodes over the cells of a batch); for p = 2 every
+    entity is a single node and the cellbatch numbering is a valid operator input.  First/last
+    touch and the three groupings all deliver contiguous entities."""
     with pytest.raises(host.HostError, match="contiguous"):
         host.Problem(3, 5, device=-1, renumber=(0, 0, 0))
-    with pytest.raises(host.HostError, match="cellbatch assembly"):
+    with pytest.raises(host.HostError, match="contiguous"):
         host.Problem(3, 5, device=-1, renumber=(1, 1, 2))
+    pr = host.Problem(2, 6, device=-1, renumber=(1, 1, 2))
+    assert pr.n_owned == O.n_dofs_total(2, 6)
+    pr.close()
     seen = set()
     for r in (1, 2):
         for g in (0, 1, 2):
