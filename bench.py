@@ -244,7 +244,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--degree", type=int, default=4)
-    ap.add_argument("--s", type=int, default=18)
+    ap.add_argument("--s", "--size", dest="s", type=int, default=18,
+                    help="mesh size: 2^s cells (use --size under torchrun, whose own options shadow --s)")
     ap.add_argument("--mode", default="weak", choices=["weak", "strong"],
                     help="weak: s + log2(N) on N GPUs (fixed DoFs per GPU); strong: s on any N")
     ap.add_argument("--cpu-s", type=int, default=18, help="largest mesh of the CPU sample")
@@ -351,6 +352,13 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = n_dofs * e2e_iters / float(dt.item()) * 1e-9
 
+    per_rank = None
+    if world > 1:   # every rank's share of the iteration (the slowest one sets the pace)
+        mine = {"rank": rank, "n_owned": prob.n_owned, "n_ghost": prob.n_ghost,
+                "ms_per_iteration": {k: v["ms_total"] / max(iters, 1) for k, v in parts.items()},
+                "launches_per_iteration": {k: v["launches"] / max(iters, 1) for k, v in parts.items()}}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -430,7 +438,8 @@ def main():
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(prob.n_owned * 8),
                    "d2h_bytes_per_step": int(prob.n_owned * 8)},
            "gpu_launches": int(launches.value), "clocks": clocks, "roofline": roofline,
-           "cpu_baseline": cpu, "setup_seconds": setup_seconds, "ghost_exchange": exchange, "sweep": sweep}
+           "cpu_baseline": cpu, "setup_seconds": setup_seconds, "ghost_exchange": exchange, "per_rank": per_rank,
+           "sweep": sweep}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -713,10 +713,8 @@ static int cell_loop(bp4_ctx *c, double *dst, const double *src, const MergedCal
       return e;
   CU(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
   {
-    Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
-    for (size_t k = 0; k < c->peer.size(); ++k) // per peer: an owned entry may be exported to several
-      CU(bp4::launch_unpack_add(c->export_off[k + 1] - c->export_off[k], c->d_export + c->export_off[k],
-                                contrib_buffer(c) + c->export_off[k], dst, c->stream));
+    Timed t(c, BP4_K_BLAS1); // one launch for all peers: an owned entry may be exported to several (atomics)
+    CU(bp4::launch_unpack_add(c->export_off.back(), c->d_export, contrib_buffer(c), dst, c->stream));
   }
   if (int e = compress_release(c, c->stream))
     return e;
@@ -1279,10 +1277,8 @@ int bp4_compress_add(bp4_ctx *c, bp4_vec *v)
   if (int e = exchange_compress_on(c, v->p(), c->stream))
     return e;
   {
-    Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
-    for (size_t k = 0; k < c->peer.size(); ++k) // per peer: an owned entry may be exported to several
-      CU(bp4::launch_unpack_add(c->export_off[k + 1] - c->export_off[k], c->d_export + c->export_off[k],
-                                contrib_buffer(c) + c->export_off[k], v->p(), c->stream));
+    Timed t(c, BP4_K_BLAS1); // one launch for all peers: an owned entry may be exported to several (atomics)
+    CU(bp4::launch_unpack_add(c->export_off.back(), c->d_export, contrib_buffer(c), v->p(), c->stream));
   }
   if (int e = compress_release(c, c->stream))
     return e;

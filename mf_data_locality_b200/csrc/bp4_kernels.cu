@@ -801,7 +801,7 @@ namespace bp4
   {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
-      v[idx[i]] += buf[i]; // export lists of different peers may repeat an index: launched per peer
+      atomicAdd(v + idx[i], buf[i]); // export lists of different peers may repeat an index
   }
   // out[i] = in[3 i]
   __global__ void __launch_bounds__(256) stride3_kernel(const uint64_t n, const double *__restrict__ in,
