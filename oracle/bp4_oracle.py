@@ -186,6 +186,36 @@ def trilinear_coefficients(verts: np.ndarray) -> np.ndarray:
     return c
 
 
+def cell_points27(s: int, cells: np.ndarray) -> np.ndarray:
+    """[n_cells][27][3] geometry nodes of genuinely quadratic cells: push_forward of the lattice
+    points (i, j, k)/2 of every cell, index i + 3j + 9k -- what a MappingQ(2) would place on the
+    manifold (the TODO at benchmark.h:75-77)."""
+    n_refine, _, _ = mesh_dims(s)
+    h = 1.0 / (1 << n_refine)
+    off = np.array([[i, j, k] for k in range(3) for j in range(3) for i in range(3)], dtype=np.float64) * 0.5
+    lat = (cells[:, None, :].astype(np.float64) + off[None, :, :]) * h
+    return push_forward(lat)
+
+
+def quadratic_coefficients(points27: np.ndarray) -> np.ndarray:
+    """[n_cells][27][3] monomial coefficients v_m, m = a + 3b + 9c, of the tri-quadratic
+    interpolant X(xi) = sum_m v_m xi^a eta^b zeta^c through the 27 nodes (all entries of
+    cell_quadratic_coefficients, poisson_operator.h:690).  1-D: f(t) through t = 0, 1/2, 1 is
+    f0 + (-3 f0 + 4 f1 - f2) t + (2 f0 - 4 f1 + 2 f2) t^2."""
+    T = np.array([[1.0, 0.0, 0.0], [-3.0, 4.0, -1.0], [2.0, -4.0, 2.0]])     # [power][node]
+    pts = points27.reshape(-1, 3, 3, 3, 3)                                     # [n][k][j][i][d]
+    c = np.einsum("ck,bj,ai,nkjid->ncbad", T, T, T, pts, optimize=True)
+    return c.reshape(-1, 27, 3)
+
+
+def cell_coefficients(rd) -> np.ndarray:
+    """geometry coefficients of a rank's cells: all 27 vectors when the problem was built with
+    quadratic cells, else the eight tri-linear ones"""
+    if rd.coefficients is not None:
+        return rd.coefficients
+    return trilinear_coefficients(rd.vertices)
+
+
 # --------------------------------------------------------------------------- #
 # DoF lattice, entity walk, renumbering (renumber_dofs_for_mf.h, strategy 0,1,2)
 # --------------------------------------------------------------------------- #
@@ -246,6 +276,10 @@ class RankData:
     # pre/post hooks of vmult_with_merged_sums (poisson_operator.h:339-364)
     range_cell_offset: np.ndarray = None
     range_private_offset: np.ndarray = None
+    # genuinely quadratic cells (build_problem(quadratic=True)): the 27 geometry nodes and all 27
+    # coefficient vectors of the form local_apply evaluates (poisson_operator.h:577-602)
+    points27: np.ndarray = None
+    coefficients: np.ndarray = None
 
 
 def _lattice(p, n):
@@ -276,7 +310,7 @@ def fe_q_walk(p: int) -> np.ndarray:
 
 
 def build_problem(degree: int, s: int, n_ranks: int = 1, lanes: int = 8,
-                  batches_per_range: int = 1, renumber=(0, 1, 2)) -> list[RankData]:
+                  batches_per_range: int = 1, renumber=(0, 1, 2), quadratic: bool = False) -> list[RankData]:
     """Problem definition of run_templated (benchmark.h:66-176) for `n_ranks` virtual
     MPI ranks: mesh, Q_p^3 DoFs, Dirichlet set, Renumber(0,1,2) numbering,
     LaplaceOperator::initialize data (poisson_operator.h:161-267) and the RHS.
@@ -462,6 +496,9 @@ def build_problem(degree: int, s: int, n_ranks: int = 1, lanes: int = 8,
             ghost_owner=owner[ghosts], ghost_remote_local=new_local[ghosts],
             group_sizes=d["groups"], range_cell_offset=d["range_cell_offset"],
             range_private_offset=d["range_private_offset"]))
+        if quadratic:
+            out[-1].points27 = cell_points27(s, d["cells"])
+            out[-1].coefficients = quadratic_coefficients(out[-1].points27)
     return out
 
 
@@ -530,6 +567,17 @@ def jacobians(coef: np.ndarray, x1d: np.ndarray) -> np.ndarray:
     """jac[cell][qz][qy][qx][row][d], rows = dX/dxi, dX/deta, dX/dzeta evaluated from
     the tri-linear coefficients exactly as poisson_operator.h:577-602 (the 19
     quadratic coefficients are identically zero, :161-178)."""
+    if coef.shape[1] == 27:
+        # all 27 coefficients: d/dxi_e of sum_m v_m x^a y^b z^c (poisson_operator.h:577-602)
+        P = np.stack([np.ones_like(x1d), x1d, x1d * x1d])                     # [power][q]
+        dP = np.stack([np.zeros_like(x1d), np.ones_like(x1d), 2.0 * x1d])
+        v = coef.reshape(-1, 3, 3, 3, 3)                                       # [n][c][b][a][d]
+        nq = len(x1d)
+        jac = np.empty((coef.shape[0], nq, nq, nq, 3, 3))
+        jac[..., 0, :] = np.einsum("ncbad,ax,by,cz->nzyxd", v, dP, P, P, optimize=True)
+        jac[..., 1, :] = np.einsum("ncbad,ax,by,cz->nzyxd", v, P, dP, P, optimize=True)
+        jac[..., 2, :] = np.einsum("ncbad,ax,by,cz->nzyxd", v, P, P, dP, optimize=True)
+        return jac
     v1, v3, v4, v9, v10, v12, v13 = (coef[:, i] for i in (1, 2, 3, 4, 5, 6, 7))
     x = x1d[None, None, None, :, None]
     y = x1d[None, None, :, None, None]
@@ -572,7 +620,7 @@ def vmult_cells(rd: RankData, t: Tables, src: np.ndarray, chunk: int = 4096) -> 
     p = rd.degree
     n1 = p + 1
     dmap = local_dof_map(p, rd.entity_index)
-    coef = trilinear_coefficients(rd.vertices)
+    coef = cell_coefficients(rd)
     dst = np.zeros(rd.n_owned + rd.n_ghost)
     for c0 in range(0, rd.n_cells, chunk):
         m = dmap[c0:c0 + chunk]
@@ -603,7 +651,7 @@ def inverse_diagonal(rd: RankData) -> np.ndarray:
     multi-rank partition until contributions are exchanged (see virtual ranks)."""
     p = rd.degree
     t = make_tables(p, p + 1, quad="gll")
-    coef = trilinear_coefficients(rd.vertices)
+    coef = cell_coefficients(rd)
     jinv, det = do_invert(jacobians(coef, t.xq))
     w = t.wq[:, None, None] * t.wq[None, :, None] * t.wq[None, None, :]
     G = np.einsum("nzyxde,nzyxdf->nzyxef", jinv, jinv) * (det * w[None])[..., None, None]
@@ -854,6 +902,7 @@ def dense_matrix(rd: RankData, t: Tables) -> np.ndarray:
     dmap = local_dof_map(p, rd.entity_index)
     for c in range(rd.n_cells):
         X = rd.vertices[c]
+        X27 = rd.points27[c] if rd.points27 is not None else None
         # reference gradients of all (p+1)^3 basis functions at all q^3 points
         gr = np.zeros((n1, n1, n1, nq, nq, nq, 3))
         for k in range(n1):
@@ -871,7 +920,19 @@ def dense_matrix(rd: RankData, t: Tables) -> np.ndarray:
                     xi = np.array([t.xq[qx], t.xq[qy], t.xq[qz]])
                     # dX/dxi_e from the trilinear vertex interpolation
                     J = np.zeros((3, 3))      # J[d][e] = dX_d / dxi_e
-                    for v in range(8):
+                    if X27 is not None:
+                        # tri-quadratic Lagrange interpolation of the 27 geometry nodes (nodes 0, 1/2, 1)
+                        nodes = np.array([0.0, 0.5, 1.0])
+                        L = [lagrange_values(nodes, np.array([xi[e]]))[:, 0] for e in range(3)]
+                        dL = [lagrange_derivs(nodes, np.array([xi[e]]))[:, 0] for e in range(3)]
+                        for k2 in range(3):
+                            for j2 in range(3):
+                                for i2 in range(3):
+                                    Xn = X27[i2 + 3 * j2 + 9 * k2]
+                                    J[:, 0] += Xn * dL[0][i2] * L[1][j2] * L[2][k2]
+                                    J[:, 1] += Xn * L[0][i2] * dL[1][j2] * L[2][k2]
+                                    J[:, 2] += Xn * L[0][i2] * L[1][j2] * dL[2][k2]
+                    for v in (range(8) if X27 is None else ()):
                         b = [(v >> e) & 1 for e in range(3)]
                         for e in range(3):
                             f = 1.0

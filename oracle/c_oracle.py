@@ -74,6 +74,7 @@ class COracle:
         self._keep += [np.ascontiguousarray(start), np.ascontiguousarray(order)]
         self.tab = _Tables(p, *[_p(a) for a in self._keep[:6]], 8, _p(self._keep[6]), _p(self._keep[7]))
         self.eidx = np.ascontiguousarray(rd.entity_index, dtype=np.uint32)
+        assert rd.coefficients is None, "the C restatement evaluates tri-linear cells only (use the numpy oracle)"
         self.coef = np.ascontiguousarray(O.trilinear_coefficients(rd.vertices))
         self.con = np.ascontiguousarray(rd.constrained, dtype=np.uint32)
         self.n = rd.n_owned + rd.n_ghost

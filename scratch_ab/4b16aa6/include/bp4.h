@@ -91,13 +91,6 @@ typedef struct bp4_desc
   uint64_t        n_ranges;
   const uint64_t *range_cell_offset;    /* [n_ranges + 1] */
   const uint64_t *range_private_offset; /* [n_ranges + 1] local DoF indices, multiples of 3 */
-  /* optional: [n_cells][27][3] ALL coefficient vectors of the cell geometry
-   * X(xi) = sum_m v_m xi^a eta^b zeta^c, m = a + 3b + 9c, a,b,c in {0,1,2} -- the array
-   * cell_quadratic_coefficients that local_apply evaluates (poisson_operator.h:577-602, :690).
-   * The reference itself only fills the 8 tri-linear ones from the vertices (:161-178, "for now
-   * use only constant and linear term"); with this field a caller can hand genuinely quadratic
-   * cells (the MappingQCache(2) TODO of benchmark.h:75-77).  When given, `vertices` is ignored.  */
-  const double *coefficients;
 } bp4_desc;
 
 const char *bp4_last_error(void);
@@ -137,12 +130,6 @@ int bp4_vmult_merged(bp4_ctx *ctx, bp4_vec *x, bp4_vec *g, bp4_vec *d, bp4_vec *
  * LaplaceOperator::compute_inverse_diagonal + extraction (poisson_operator.h:392-426,
  * benchmark.h:141-147).  out holds n_owned/3 entries.                                       */
 int bp4_inverse_diagonal(bp4_ctx *ctx, bp4_vec *out);
-/* the same in the reference's own result layout (poisson_operator.h:392-426): a DoF vector
- * (n_owned + n_ghost entries) with 1/diag on component 0 of every node and 1 elsewhere ...     */
-int bp4_inverse_diagonal_vector(bp4_ctx *ctx, bp4_vec *out);
-/* ... and the extraction loop of benchmark.h:141-147: dst[i] = src[n_components * i + component] */
-int bp4_extract_component(bp4_ctx *ctx, bp4_vec *dst, const bp4_vec *src, int n_components,
-                          int component);
 /* dst[3i+c] = diag[i] * src[3i+c]: DiagonalMatrixBlocked::vmult, diagonal_matrix_blocked.h:13 */
 int bp4_jacobi_vmult(bp4_ctx *ctx, bp4_vec *dst, const bp4_vec *src, const bp4_vec *diag);
 /* x += c1 * d + c2 * P g: final x update on even iterations, solver_cg_optimized.h:260-288  */

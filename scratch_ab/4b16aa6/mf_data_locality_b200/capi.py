@@ -31,7 +31,7 @@ class _Desc(C.Structure):
                 ("export_offset", C.c_void_p), ("export_index", C.c_void_p),
                 ("n_cells_before_comm", C.c_uint64), ("n_cells_comm", C.c_uint64),
                 ("n_ranges", C.c_uint64), ("range_cell_offset", C.c_void_p),
-                ("range_private_offset", C.c_void_p), ("coefficients", C.c_void_p)]
+                ("range_private_offset", C.c_void_p)]
 
 
 _lib = None
@@ -40,7 +40,7 @@ EXPORTS = [
     "bp4_last_error", "bp4_device_count", "bp4_ctx_create", "bp4_ctx_destroy", "bp4_ctx_synchronize",
     "bp4_ctx_stream", "bp4_vec_alloc", "bp4_vec_free", "bp4_vec_size", "bp4_vec_set_zero",
     "bp4_vec_upload", "bp4_vec_download", "bp4_vec_device_ptr", "bp4_vmult", "bp4_vmult_merged",
-    "bp4_vec_alloc_uninitialized", "bp4_debug_set_fused", "bp4_fused_info", "bp4_inverse_diagonal", "bp4_inverse_diagonal_vector", "bp4_extract_component", "bp4_jacobi_vmult", "bp4_x_finalize_even",
+    "bp4_vec_alloc_uninitialized", "bp4_debug_set_fused", "bp4_fused_info", "bp4_inverse_diagonal", "bp4_jacobi_vmult", "bp4_x_finalize_even",
     "bp4_equ", "bp4_add", "bp4_sadd", "bp4_dot", "bp4_add_and_dot", "bp4_l2_norm", "bp4_all_zero",
     "bp4_comm_unique_id", "bp4_comm_init", "bp4_comm_info", "bp4_update_ghost_values", "bp4_compress_add",
     "bp4_profile_enable", "bp4_profile_reset", "bp4_profile_get", "bp4_launch_count",
@@ -124,7 +124,7 @@ class Context:
     (poisson_operator.h:101-293)."""
 
     def __init__(self, degree, entity_index, vertices, n_owned, n_ghost=0, constrained=None,
-                 device=0, peers=None, ranges=None, partitions=None, coefficients=None):
+                 device=0, peers=None, ranges=None, partitions=None):
         """ranges = (range_cell_offset, range_private_offset): cell-batch ranges of the loop and
         the DoF runs private to them (bp4_desc::n_ranges); partitions = (n_cells_before_comm,
         n_cells_comm) of the overlapped ghost exchange"""
@@ -152,11 +152,6 @@ class Context:
             assert len(rc) == len(rp)
             d.n_ranges, d.range_cell_offset, d.range_private_offset = len(rc) - 1, _ptr(rc), _ptr(rp)
             keep += [rc, rp]
-        if coefficients is not None:            # [n_cells][27][3]: genuinely quadratic cells
-            cq = np.ascontiguousarray(coefficients, dtype=np.float64).reshape(-1, 27, 3)
-            assert len(cq) == len(ei)
-            d.coefficients = _ptr(cq)
-            keep += [cq]
         if partitions is not None:
             d.n_cells_before_comm, d.n_cells_comm = int(partitions[0]), int(partitions[1])
         self.h = C.c_void_p()

@@ -78,7 +78,6 @@ struct ProfEvent
 struct bp4_ctx
 {
   int          degree = 0, device = 0, sms = 0;
-  int          n_coef = 24; // geometry coefficients per cell: 24 (tri-linear) or 81 (all 27 vectors)
   uint64_t     n_cells = 0, n_owned = 0, n_ghost = 0, n_constrained = 0;
   uint64_t     n_before = 0, n_comm = 0; // cell partitions for the overlapped exchange
   cudaStream_t comm_stream = nullptr;
@@ -301,15 +300,12 @@ static int ctx_create_impl(const bp4_desc *d, bp4_ctx *c)
   CU(cudaMemcpy(c->d_walk, walk.data(), sizeof(uint32_t) * walk.size(), cudaMemcpyHostToDevice));
 
   const size_t nc = d->n_cells ? d->n_cells : 1;
-  c->n_coef       = d->coefficients ? 81 : 24;
   CU(cudaMalloc(&c->d_entity, sizeof(uint32_t) * 27 * nc));
-  CU(cudaMalloc(&c->d_coef, sizeof(double) * c->n_coef * nc));
+  CU(cudaMalloc(&c->d_coef, sizeof(double) * 24 * nc));
   if (d->n_cells)
-    CU(cudaMemcpy(c->d_entity, d->entity_index, sizeof(uint32_t) * 27 * d->n_cells, cudaMemcpyHostToDevice));
-  if (d->n_cells && d->coefficients) // all 27 coefficient vectors of the reference's kernel, as given
-    CU(cudaMemcpy(c->d_coef, d->coefficients, sizeof(double) * 81 * d->n_cells, cudaMemcpyHostToDevice));
-  else if (d->n_cells)
     {
+      CU(cudaMemcpy(c->d_entity, d->entity_index, sizeof(uint32_t) * 27 * d->n_cells,
+                    cudaMemcpyHostToDevice));
       // tri-linear coefficients from the 8 vertices, poisson_operator.h:161-178
       std::vector<double> cf(24 * d->n_cells);
       for (uint64_t i = 0; i < d->n_cells; ++i)
@@ -390,7 +386,7 @@ static int ctx_create_impl(const bp4_desc *d, bp4_ctx *c)
       CU(cudaMemcpy(c->d_batch, batches.data(), sizeof(bp4::BatchDesc) * batches.size(), cudaMemcpyHostToDevice));
       CU(cudaMemcpy(c->d_unit_batch, unit_batch.data(), sizeof(uint32_t) * unit_batch.size(),
                     cudaMemcpyHostToDevice));
-      c->n_private = c->n_coef == 24 ? rp[d->n_ranges] : 0; // in-loop updates: tri-linear kernel only
+      c->n_private = rp[d->n_ranges];
       c->fused     = BP4_FUSED_DEFAULT && c->n_private > 0;
       if (const char *e = getenv("BP4_FUSED")) // developer knob: 0 = pre kernel + cells + post kernel
         c->fused = c->n_private > 0 && atoi(e) != 0;
@@ -422,7 +418,7 @@ int bp4_ctx_create(const bp4_desc *d, bp4_ctx **out)
     return fail(BP4_ERR_ARG, "n_owned/n_ghost must be multiples of 3");
   if (d->n_owned + d->n_ghost >= 0xFFFFFFFFull)
     return fail(BP4_ERR_ARG, "local vector exceeds 32-bit local indices (poisson_operator.h:693)");
-  if (d->n_cells && (!d->entity_index || (!d->vertices && !d->coefficients)))
+  if (d->n_cells && (!d->entity_index || !d->vertices))
     return fail(BP4_ERR_ARG, "entity_index/vertices missing");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
@@ -653,15 +649,15 @@ static int cell_range(bp4_ctx *c, double *dst, const double *src, int part, cons
       a.c2           = a.update_x ? m->alpha_old / m->beta_old : 0.;
       a.acc          = c->d_acc;
       Timed t(c, BP4_K_MERGED);
-      CU(bp4::launch_cell(c->degree, true, false, a, c->sms, c->stream));
+      CU(bp4::launch_cell(c->degree, true, a, c->sms, c->stream));
     }
   else
     {
       a.entity_index = c->d_entity + 27 * begin;
-      a.coef         = c->d_coef + (uint64_t)c->n_coef * begin;
+      a.coef         = c->d_coef + 24 * begin;
       a.n_cells      = end - begin;
       Timed t(c, BP4_K_VMULT);
-      CU(bp4::launch_cell(c->degree, false, c->n_coef == 81, a, c->sms, c->stream));
+      CU(bp4::launch_cell(c->degree, false, a, c->sms, c->stream));
     }
   return 0;
 }
@@ -717,8 +713,10 @@ static int cell_loop(bp4_ctx *c, double *dst, const double *src, const MergedCal
       return e;
   CU(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
   {
-    Timed t(c, BP4_K_BLAS1); // one launch for all peers: an owned entry may be exported to several (atomics)
-    CU(bp4::launch_unpack_add(c->export_off.back(), c->d_export, contrib_buffer(c), dst, c->stream));
+    Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
+    for (size_t k = 0; k < c->peer.size(); ++k) // per peer: an owned entry may be exported to several
+      CU(bp4::launch_unpack_add(c->export_off[k + 1] - c->export_off[k], c->d_export + c->export_off[k],
+                                contrib_buffer(c) + c->export_off[k], dst, c->stream));
   }
   if (int e = compress_release(c, c->stream))
     return e;
@@ -818,7 +816,7 @@ int bp4_inverse_diagonal(bp4_ctx *c, bp4_vec *out)
     return e;
   {
     Timed t(c, BP4_K_BLAS1, 3);
-    CU(bp4::launch_diag_assemble(c->degree, c->n_cells, c->d_entity, c->d_coef, c->n_coef, c->d_gll, tmp->p(), 3,
+    CU(bp4::launch_diag_assemble(c->degree, c->n_cells, c->d_entity, c->d_coef, c->d_gll, tmp->p(), 3,
                                  c->stream));
   }
   if (!c->peer.empty())
@@ -827,44 +825,6 @@ int bp4_inverse_diagonal(bp4_ctx *c, bp4_vec *out)
   CU(bp4::launch_stride3(c->n_owned / 3, tmp->p(), out->p(), c->stream));
   CU(bp4::launch_diag_invert(c->n_owned / 3, out->p(), c->stream));
   return bp4_vec_free(c, tmp);
-}
-
-// the reference's own layout of the result (poisson_operator.h:392-426): a DoF vector whose
-// component-0 entries hold 1/diag of the scalar operator and every other entry is 1 (0 -> 1)
-int bp4_inverse_diagonal_vector(bp4_ctx *c, bp4_vec *out)
-{
-  if (!c)
-    return fail(BP4_ERR_ARG, "null ctx");
-  if (int e = check_len(c, out, "out"))
-    return e;
-  CU(cudaSetDevice(c->device));
-  CU(cudaMemsetAsync(out->p(), 0, sizeof(double) * (c->n_owned + c->n_ghost), c->stream));
-  {
-    Timed t(c, BP4_K_BLAS1, 2);
-    CU(bp4::launch_diag_assemble(c->degree, c->n_cells, c->d_entity, c->d_coef, c->n_coef, c->d_gll, out->p(), 3,
-                                 c->stream));
-  }
-  if (!c->peer.empty())
-    if (int e = bp4_compress_add(c, out))
-      return e;
-  CU(bp4::launch_diag_invert(c->n_owned, out->p(), c->stream));
-  return 0;
-}
-
-// dst[i] = src[n_components * i + component]: the extraction loop of benchmark.h:141-147
-int bp4_extract_component(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src, int n_components, int component)
-{
-  if (!c || !dst || !src)
-    return fail(BP4_ERR_ARG, "null argument");
-  if (n_components != 3 || component < 0 || component > 2)
-    return fail(BP4_ERR_ARG, "three components per node");
-  if (src->n < c->n_owned || dst->n < c->n_owned / 3)
-    return fail(BP4_ERR_ARG, "Dimension mismatch %llu vs 3 x %llu", (unsigned long long)src->n,
-                (unsigned long long)dst->n);
-  CU(cudaSetDevice(c->device));
-  Timed t(c, BP4_K_BLAS1);
-  CU(bp4::launch_stride3(c->n_owned / 3, src->p() + component, dst->p(), c->stream));
-  return 0;
 }
 
 int bp4_jacobi_vmult(bp4_ctx *c, bp4_vec *dst, const bp4_vec *src, const bp4_vec *diag)
@@ -1281,8 +1241,10 @@ int bp4_compress_add(bp4_ctx *c, bp4_vec *v)
   if (int e = exchange_compress_on(c, v->p(), c->stream))
     return e;
   {
-    Timed t(c, BP4_K_BLAS1); // one launch for all peers: an owned entry may be exported to several (atomics)
-    CU(bp4::launch_unpack_add(c->export_off.back(), c->d_export, contrib_buffer(c), v->p(), c->stream));
+    Timed t(c, BP4_K_BLAS1, (int)c->peer.size());
+    for (size_t k = 0; k < c->peer.size(); ++k) // per peer: an owned entry may be exported to several
+      CU(bp4::launch_unpack_add(c->export_off[k + 1] - c->export_off[k], c->d_export + c->export_off[k],
+                                contrib_buffer(c) + c->export_off[k], v->p(), c->stream));
   }
   if (int e = compress_release(c, c->stream))
     return e;

@@ -490,96 +490,57 @@ namespace bp4
 
   // ---------------------------------------------------------------------------------------
   // phase 2: item = (qx, qz), all three components, one y-line of quadrature points.
-  // QUAD = false: cf = tri-linear coefficients [8][3] in the order v0,v1,v3,v4,v9,v10,v12,v13
-  // (the ones LaplaceOperator::initialize fills, poisson_operator.h:165-177);
-  // QUAD = true : cf = all 27 coefficients [27][3] of X = sum v_{a+3b+9c} xi^a eta^b zeta^c, the
-  // form local_apply evaluates (poisson_operator.h:577-602).
-  // x = xq[qx], z = xq[qz], wxz = wq[qx]*wq[qz].
+  // cf = tri-linear coefficients [8][3] in the order v0,v1,v3,v4,v9,v10,v12,v13
+  // (poisson_operator.h:165-177); x = xq[qx], z = xq[qz], wxz = wq[qx]*wq[qz].
   // ---------------------------------------------------------------------------------------
-  template <int P, bool QUAD = false>
+  template <int P>
   BP4_HD void phase2(const Tab<P> &tb, const double *cf, double *work, const int qx, const int qz,
                      const double x, const double z, const double wxz)
   {
     using G         = Geom<P>;
     constexpr int N = G::N, Q = G::Q;
     // --- geometry of the whole y-line first: G = (w / det) K^T K, six entries per point.
-    // rows of dX/dxi_e; along the line they are polynomials in y whose coefficients are
-    // collapsed in zeta and xi once per line:
-    //   tri-linear: r0 = dX/dxi   = (v1 + z v10) + y (v4 + z v13)
-    //               r1 = dX/deta  = (v3 + z v12) + x (v4 + z v13)      (constant along the line)
-    //               r2 = dX/dzeta = (v9 + x v10) + y (v12 + x v13)
-    //   quadratic : r0, r2 quadratic and r1 linear in y (same collapse order as the reference:
-    //               xi_i = v_i + z (v_{9+i} + z v_{18+i}), di_i = v_{9+i} + 2 z v_{18+i})
+    // rows of dX/dxi_e (poisson_operator.h:577-602):
+    //   r0 = dX/dxi   = (v1 + z v10) + y (v4 + z v13)
+    //   r1 = dX/deta  = (v3 + z v12) + x (v4 + z v13)      (constant along the line)
+    //   r2 = dX/dzeta = (v9 + x v10) + y (v12 + x v13)
     double g00[Q], g01[Q], g02[Q], g11[Q], g12[Q], g22[Q];
     {
-      constexpr int NB = QUAD ? 3 : 2; // coefficients in y of r0 and r2
-      double        A[NB][3], Cc[NB][3], R1[2][3];
+      double A[3], B[3], R1[3], Cc[3], Dd[3];
       BP4_UNROLL
       for (int d = 0; d < 3; ++d)
         {
-          if constexpr (!QUAD)
-            {
-              const double v1 = cf[3 + d], v3 = cf[6 + d], v4 = cf[9 + d], v9 = cf[12 + d],
-                           v10 = cf[15 + d], v12 = cf[18 + d], v13 = cf[21 + d];
-              A[0][d]  = v1 + z * v10;
-              A[1][d]  = v4 + z * v13;
-              R1[0][d] = (v3 + z * v12) + x * A[1][d];
-              R1[1][d] = 0.;
-              Cc[0][d] = v9 + x * v10;
-              Cc[1][d] = v12 + x * v13;
-            }
-          else
-            {
-              double xi[9], di[9];
-              BP4_UNROLL
-              for (int i = 0; i < 9; ++i)
-                {
-                  xi[i] = cf[3 * i + d] + z * (cf[3 * (9 + i) + d] + z * cf[3 * (18 + i) + d]);
-                  di[i] = cf[3 * (9 + i) + d] + (z + z) * cf[3 * (18 + i) + d];
-                }
-              BP4_UNROLL
-              for (int b = 0; b < 3; ++b)
-                {
-                  A[b][d]  = xi[1 + 3 * b] + (x + x) * xi[2 + 3 * b];
-                  Cc[b][d] = di[3 * b] + x * (di[3 * b + 1] + x * di[3 * b + 2]);
-                }
-              R1[0][d] = xi[3] + x * (xi[4] + x * xi[5]);
-              R1[1][d] = xi[6] + x * (xi[7] + x * xi[8]);
-            }
+          const double v1 = cf[3 + d], v3 = cf[6 + d], v4 = cf[9 + d], v9 = cf[12 + d],
+                       v10 = cf[15 + d], v12 = cf[18 + d], v13 = cf[21 + d];
+          A[d]  = v1 + z * v10;
+          B[d]  = v4 + z * v13;
+          R1[d] = (v3 + z * v12) + x * B[d];
+          Cc[d] = v9 + x * v10;
+          Dd[d] = v12 + x * v13;
         }
       BP4_UNROLL
       for (int q = 0; q < Q; ++q)
         {
           const double y = tb.xq[q];
-          double       r0[3], r1[3], r2[3];
+          double       r0[3], r2[3];
           BP4_UNROLL
           for (int d = 0; d < 3; ++d)
             {
-              if constexpr (!QUAD)
-                {
-                  r0[d] = A[0][d] + y * A[1][d];
-                  r1[d] = R1[0][d];
-                  r2[d] = Cc[0][d] + y * Cc[1][d];
-                }
-              else
-                {
-                  r0[d] = A[0][d] + y * (A[1][d] + y * A[NB - 1][d]);
-                  r1[d] = R1[0][d] + (y + y) * R1[1][d];
-                  r2[d] = Cc[0][d] + y * (Cc[1][d] + y * Cc[NB - 1][d]);
-                }
+              r0[d] = A[d] + y * B[d];
+              r2[d] = Cc[d] + y * Dd[d];
             }
           // columns of adj: k0 = r1 x r2, k1 = r2 x r0, k2 = r0 x r1;  det = r0 . k0
           // (the cofactor inverse of poisson_operator.h:41-63 without the division)
           double k0[3], k1[3], k2[3];
-          k0[0] = r1[1] * r2[2] - r1[2] * r2[1];
-          k0[1] = r1[2] * r2[0] - r1[0] * r2[2];
-          k0[2] = r1[0] * r2[1] - r1[1] * r2[0];
+          k0[0] = R1[1] * r2[2] - R1[2] * r2[1];
+          k0[1] = R1[2] * r2[0] - R1[0] * r2[2];
+          k0[2] = R1[0] * r2[1] - R1[1] * r2[0];
           k1[0] = r2[1] * r0[2] - r2[2] * r0[1];
           k1[1] = r2[2] * r0[0] - r2[0] * r0[2];
           k1[2] = r2[0] * r0[1] - r2[1] * r0[0];
-          k2[0] = r0[1] * r1[2] - r0[2] * r1[1];
-          k2[1] = r0[2] * r1[0] - r0[0] * r1[2];
-          k2[2] = r0[0] * r1[1] - r0[1] * r1[0];
+          k2[0] = r0[1] * R1[2] - r0[2] * R1[1];
+          k2[1] = r0[2] * R1[0] - r0[0] * R1[2];
+          k2[2] = r0[0] * R1[1] - r0[1] * R1[0];
           const double det = r0[0] * k0[0] + r0[1] * k0[1] + r0[2] * k0[2];
           // == det * w * J^-1 J^-T  (poisson_operator.h:604-625)
           const double sc = (wxz * tb.wq[q]) * rcp_nobranch(det);

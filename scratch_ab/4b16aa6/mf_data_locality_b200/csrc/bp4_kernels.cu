@@ -40,8 +40,8 @@ namespace bp4
   template <int P>
   __constant__ Tab<P> c_tab;
 
-  template <int P, int CPB, int NC>
-  __device__ __forceinline__ void load_tables(CellSmem<P, CPB, NC> &sm, const uint32_t *dtab)
+  template <int P, int CPB>
+  __device__ __forceinline__ void load_tables(CellSmem<P, CPB> &sm, const uint32_t *dtab)
   {
     for (int i = threadIdx.x; i < Geom<P>::DOF; i += kThreads)
       sm.dtab[i] = dtab[i];
@@ -90,12 +90,12 @@ namespace bp4
   // Phase 2 as a real call for the high degrees: its ~100 live doubles get a register allocation
   // of their own instead of competing with whatever the gather/scatter code around it keeps
   // alive (the inlined form spilled 2.6x more after an unrelated change to the gather).
-  template <int P, bool QUAD>
+  template <int P>
   __device__ __noinline__ void phase2_call(const uint32_t cf_off, const uint32_t work_off, const int qx,
                                            const int qz, const double x, const double z, const double wxz)
   {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    phase2<P, QUAD>(c_tab<P>, reinterpret_cast<const double *>(smem_raw + cf_off),
+    phase2<P>(c_tab<P>, reinterpret_cast<const double *>(smem_raw + cf_off),
               reinterpret_cast<double *>(smem_raw + work_off), qx, qz, x, z, wxz);
   }
 
@@ -156,19 +156,18 @@ namespace bp4
   // (and between ranks, and the Dirichlet ones) are the tail [n_private, n_owned) of the vector:
   // pre_kernel / post_kernel stream them before / after this kernel.
   // ---------------------------------------------------------------------------------------
-  template <int P, int CPB, bool FUSED, bool QUAD>
+  template <int P, int CPB, bool FUSED>
   __global__ void __launch_bounds__(kThreads, Cfg<P>::BLOCKS) cell_kernel(const CellArgs a)
   {
-    constexpr int NC = Cfg<P, QUAD>::NCOEF;
     using G         = Geom<P>;
     constexpr int Q = G::Q;
     // high degrees: phases 1 and 3 as one sweep per 1-D contraction (see phase1a)
     constexpr bool kFine = P >= BP4_FINE_FROM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CellSmem<P, CPB, NC> &sm  = *reinterpret_cast<CellSmem<P, CPB, NC> *>(smem_raw);
-    const int             tid = threadIdx.x;
-    const Tab<P>         &tb  = c_tab<P>;
-    load_tables<P, CPB, NC>(sm, a.dtab);
+    CellSmem<P, CPB> &sm  = *reinterpret_cast<CellSmem<P, CPB> *>(smem_raw);
+    const int         tid = threadIdx.x;
+    const Tab<P>     &tb  = c_tab<P>;
+    load_tables<P, CPB>(sm, a.dtab);
     BP4_TICK_INIT
 
     // ---- work list of this block: a unit is one batch (plain) or the batches
@@ -189,7 +188,7 @@ namespace bp4
     };
     auto claim_ahead = [&](const uint32_t j_cur) { // thread 0 only; visible after the next barrier
       if (dynamic)
-        while (sm.n_claimed < j_cur + (FUSED ? 5u : 3u))
+        while (sm.n_claimed < j_cur + 5u)
           {
             sm.units[sm.n_claimed & 7u] = gridDim.x + atomicAdd(a.sched, 1u);
             ++sm.n_claimed;
@@ -241,7 +240,7 @@ namespace bp4
     };
 
     // metadata items of a batch handled by this thread: at most ME indices and MC coefficients
-    constexpr int ME = (CPB * 27 + kThreads - 1) / kThreads, MC = (CPB * NC + kThreads - 1) / kThreads;
+    constexpr int ME = (CPB * 27 + kThreads - 1) / kThreads, MC = (CPB * 24 + kThreads - 1) / kThreads;
     uint32_t      me[ME];
     double        mc[MC];
     auto          fetch_meta = [&](const Batch &d) {
@@ -255,7 +254,7 @@ namespace bp4
       for (int u = 0; u < MC; ++u)
         {
           const int k = tid + u * kThreads;
-          mc[u]       = k < d.nc * NC ? __ldg(a.coef + (uint64_t)d.cell0 * NC + k) : 0.;
+          mc[u]       = k < d.nc * 24 ? __ldg(a.coef + (uint64_t)d.cell0 * 24 + k) : 0.;
         }
     };
     auto park_meta = [&](const int bf) {
@@ -270,8 +269,8 @@ namespace bp4
       for (int u = 0; u < MC; ++u)
         {
           const int k = tid + u * kThreads;
-          if (k < CPB * NC)
-            sm.coef[bf][k / NC][k % NC] = mc[u];
+          if (k < CPB * 24)
+            sm.coef[bf][k / 24][k % 24] = mc[u];
         }
     };
 
@@ -454,13 +453,10 @@ namespace bp4
         nn_it  = nxt_it;
         if (nxt_it.valid)
           {
-            nxt = describe(nxt_it);
-            if constexpr (FUSED) // the plain kernel looks one batch ahead only
-              {
-                nn_it = advance(nxt_it);
-                if (nn_it.valid)
-                  nn = describe(nn_it);
-              }
+            nxt   = describe(nxt_it);
+            nn_it = advance(nxt_it);
+            if (nn_it.valid)
+              nn = describe(nn_it);
           }
         if (FUSED)
           {
@@ -527,12 +523,12 @@ namespace bp4
             const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
             const int qz = r / Q, qx = r % Q;
             if constexpr (P >= BP4_P2_CALL_FROM)
-              phase2_call<P, QUAD>((uint32_t)((const unsigned char *)sm.coef[bf][cell] - smem_raw),
+              phase2_call<P>((uint32_t)((const unsigned char *)sm.coef[bf][cell] - smem_raw),
                              (uint32_t)((const unsigned char *)(sm.work + cell * G::WORK) - smem_raw), qx, qz,
                              sm.xq[qx], sm.xq[qz], sm.wq[qx] * sm.wq[qz]);
             else
-              phase2<P, QUAD>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
-                              sm.wq[qx] * sm.wq[qz]);
+              phase2<P>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
+                        sm.wq[qx] * sm.wq[qz]);
           }
         BP4_TICK(4)
         __syncthreads();
@@ -610,15 +606,10 @@ namespace bp4
         }
         BP4_TICK(6)
         BP4_TRACE(i, 2)
-        It    n3_it = nn_it;
-        Batch n3{};
-        if constexpr (FUSED)
-          {
-            if (nn_it.valid)
-              n3_it = advance(nn_it);
-            if (n3_it.valid)
-              n3 = describe(n3_it);
-          }
+        const It n3_it = nn_it.valid ? advance(nn_it) : nn_it;
+        Batch    n3{};
+        if (n3_it.valid)
+          n3 = describe(n3_it);
         if (FUSED)
           {
             post_finish(wpost, done_b, done_e, do_post);
@@ -643,18 +634,8 @@ namespace bp4
             done_b = cur.post_b, done_e = cur.post_e;
           }
         cur_it = nxt_it, cur = nxt;
-        if constexpr (FUSED)
-          {
-            nxt_it = nn_it, nxt = nn;
-            nn_it = n3_it, nn = n3;
-          }
-        else
-          {
-            if (nxt_it.valid)
-              nxt_it = advance(nxt_it);
-            if (nxt_it.valid)
-              nxt = describe(nxt_it);
-          }
+        nxt_it = nn_it, nxt = nn;
+        nn_it = n3_it, nn = n3;
       }
     if (FUSED)
       {
@@ -820,7 +801,7 @@ namespace bp4
   {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
-      atomicAdd(v + idx[i], buf[i]); // export lists of different peers may repeat an index
+      v[idx[i]] += buf[i]; // export lists of different peers may repeat an index: launched per peer
   }
   // out[i] = in[3 i]
   __global__ void __launch_bounds__(256) stride3_kernel(const uint64_t n, const double *__restrict__ in,
@@ -856,41 +837,19 @@ namespace bp4
   // inverse diagonal of the scalar GLL(p+1) Laplacian (poisson_operator.h:392-426): one
   // thread per (cell, node); collocation makes the unit-vector gradient non-zero only on
   // the three grid lines through the node.  gll holds x[N], w[N], Dg[N][N] (Dg[i][q]=l_i'(x_q)).
-  __device__ __forceinline__ void metric_at(const double *cf, const int n_coef, double x, double y, double z,
-                                            double w, double &g00, double &g01, double &g02, double &g11,
+  __device__ __forceinline__ void metric_at(const double *cf, double x, double y, double z, double w,
+                                            double &g00, double &g01, double &g02, double &g11,
                                             double &g12, double &g22)
   {
     double r0[3], r1[3], r2[3];
-    if (n_coef == 24)
-      {
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
-          {
-            const double v1 = cf[3 + d], v3 = cf[6 + d], v4 = cf[9 + d], v9 = cf[12 + d],
-                         v10 = cf[15 + d], v12 = cf[18 + d], v13 = cf[21 + d];
-            r0[d] = (v1 + z * v10) + y * (v4 + z * v13);
-            r1[d] = (v3 + z * v12) + x * (v4 + z * v13);
-            r2[d] = (v9 + y * v12) + x * (v10 + y * v13);
-          }
-      }
-    else // all 27 coefficients of X = sum v_{a+3b+9c} x^a y^b z^c (poisson_operator.h:577-602)
+    for (int d = 0; d < 3; ++d)
       {
-        const double px[3] = {1., x, x * x}, py[3] = {1., y, y * y}, pz[3] = {1., z, z * z};
-        const double dx[3] = {0., 1., x + x}, dy[3] = {0., 1., y + y}, dz[3] = {0., 1., z + z};
-        for (int d = 0; d < 3; ++d)
-          {
-            double s0 = 0., s1 = 0., s2 = 0.;
-            for (int c = 0; c < 3; ++c)
-              for (int b = 0; b < 3; ++b)
-                for (int a = 0; a < 3; ++a)
-                  {
-                    const double v = cf[3 * (a + 3 * b + 9 * c) + d];
-                    s0 += v * dx[a] * py[b] * pz[c];
-                    s1 += v * px[a] * dy[b] * pz[c];
-                    s2 += v * px[a] * py[b] * dz[c];
-                  }
-            r0[d] = s0, r1[d] = s1, r2[d] = s2;
-          }
+        const double v1 = cf[3 + d], v3 = cf[6 + d], v4 = cf[9 + d], v9 = cf[12 + d],
+                     v10 = cf[15 + d], v12 = cf[18 + d], v13 = cf[21 + d];
+        r0[d] = (v1 + z * v10) + y * (v4 + z * v13);
+        r1[d] = (v3 + z * v12) + x * (v4 + z * v13);
+        r2[d] = (v9 + y * v12) + x * (v10 + y * v13);
       }
     double k0[3], k1[3], k2[3];
     k0[0] = r1[1] * r2[2] - r1[2] * r2[1];
@@ -914,7 +873,7 @@ namespace bp4
 
   __global__ void __launch_bounds__(128) diag_kernel(const int p, const uint64_t n_cells,
                                                      const uint32_t *__restrict__ entity_index,
-                                                     const double *__restrict__ coef, const int n_coef,
+                                                     const double *__restrict__ coef,
                                                      const double *__restrict__ gll, double *diag,
                                                      const int stride)
   {
@@ -933,19 +892,19 @@ namespace bp4
     const int sx = ex == 1 ? p - 1 : 1, sy = ey == 1 ? p - 1 : 1;
     const int pos = oi + sx * (oj + sy * ok);
     const double *x = gll, *w = gll + N, *Dg = gll + 2 * N;
-    const double *cf = coef + cell * n_coef;
+    const double *cf = coef + cell * 24;
     double        s = 0., g00, g01, g02, g11, g12, g22;
     for (int q = 0; q < N; ++q)
       {
         const double dx = Dg[i * N + q], dy = Dg[j * N + q], dz = Dg[k * N + q];
-        metric_at(cf, n_coef, x[q], x[j], x[k], w[q] * w[j] * w[k], g00, g01, g02, g11, g12, g22);
+        metric_at(cf, x[q], x[j], x[k], w[q] * w[j] * w[k], g00, g01, g02, g11, g12, g22);
         s += dx * dx * g00;
-        metric_at(cf, n_coef, x[i], x[q], x[k], w[i] * w[q] * w[k], g00, g01, g02, g11, g12, g22);
+        metric_at(cf, x[i], x[q], x[k], w[i] * w[q] * w[k], g00, g01, g02, g11, g12, g22);
         s += dy * dy * g11;
-        metric_at(cf, n_coef, x[i], x[j], x[q], w[i] * w[j] * w[q], g00, g01, g02, g11, g12, g22);
+        metric_at(cf, x[i], x[j], x[q], w[i] * w[j] * w[q], g00, g01, g02, g11, g12, g22);
         s += dz * dz * g22;
       }
-    metric_at(cf, n_coef, x[i], x[j], x[k], w[i] * w[j] * w[k], g00, g01, g02, g11, g12, g22);
+    metric_at(cf, x[i], x[j], x[k], w[i] * w[j] * w[k], g00, g01, g02, g11, g12, g22);
     const double di = Dg[i * N + i], dj = Dg[j * N + j], dk = Dg[k * N + k];
     s += 2. * (di * dj * g01 + di * dk * g02 + dj * dk * g12);
     atomicAdd(diag + ((size_t)base / 3 + pos) * stride, s);
@@ -979,26 +938,20 @@ namespace bp4
     cudaError_t e = cudaMemcpyToSymbol(c_tab<P>, &tb, sizeof(tb));
     if (e != cudaSuccess)
       return e;
-    constexpr int CPB = Cfg<P>::CPB, CPBQ = Cfg<P, true>::CPB;
-    e = cudaFuncSetAttribute(cell_kernel<P, CPB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(CellSmem<P, CPB, 24>));
+    constexpr int CPB = Cfg<P>::CPB;
+    e = cudaFuncSetAttribute(cell_kernel<P, CPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CellSmem<P, CPB>));
     if (e != cudaSuccess)
       return e;
-    e = cudaFuncSetAttribute(cell_kernel<P, CPBQ, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(CellSmem<P, CPBQ, 81>));
-    if (e != cudaSuccess)
-      return e;
-    return cudaFuncSetAttribute(cell_kernel<P, CPB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(CellSmem<P, CPB, 24>));
+    return cudaFuncSetAttribute(cell_kernel<P, CPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(CellSmem<P, CPB>));
   }
 
   template <int P>
-  static cudaError_t run_cell(const bool fused, const bool quad, const CellArgs &a, int sms, cudaStream_t st)
+  static cudaError_t run_cell(const bool fused, const CellArgs &a, int sms, cudaStream_t st)
   {
-    constexpr int  CPB = Cfg<P>::CPB, CPBQ = Cfg<P, true>::CPB;
-    if (fused && quad)
-      return cudaErrorInvalidValue;
-    const uint64_t units = fused ? a.n_units : (a.n_cells + (quad ? CPBQ : CPB) - 1) / (quad ? CPBQ : CPB);
+    constexpr int  CPB   = Cfg<P>::CPB;
+    const uint64_t units = fused ? a.n_units : (a.n_cells + CPB - 1) / CPB;
     const int      grid  = (int)std::min<uint64_t>(units, (uint64_t)sms * Cfg<P>::BLOCKS);
     if (grid == 0)
       return cudaSuccess;
@@ -1013,11 +966,9 @@ namespace bp4
     cudaMemcpyToSymbolAsync(g_trace, &d_trace, sizeof(d_trace), 0, cudaMemcpyHostToDevice, st);
 #endif
     if (fused)
-      cell_kernel<P, CPB, true, false><<<grid, kThreads, sizeof(CellSmem<P, CPB, 24>), st>>>(a);
-    else if (quad)
-      cell_kernel<P, CPBQ, false, true><<<grid, kThreads, sizeof(CellSmem<P, CPBQ, 81>), st>>>(a);
+      cell_kernel<P, CPB, true><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
     else
-      cell_kernel<P, CPB, false, false><<<grid, kThreads, sizeof(CellSmem<P, CPB, 24>), st>>>(a);
+      cell_kernel<P, CPB, false><<<grid, kThreads, sizeof(CellSmem<P, CPB>), st>>>(a);
 #ifdef BP4_PHASE_TIMING
     if (d_trace)
       {
@@ -1070,24 +1021,24 @@ namespace bp4
 #undef CALL
   }
 
-  cudaError_t launch_cell(int degree, bool fused, bool quad, const CellArgs &a, int sms, cudaStream_t st)
+  cudaError_t launch_cell(int degree, bool fused, const CellArgs &a, int sms, cudaStream_t st)
   {
-#define CALL(P) run_cell<P>(fused, quad, a, sms, st)
+#define CALL(P) run_cell<P>(fused, a, sms, st)
     BP4_DISPATCH(degree, CALL)
 #undef CALL
   }
 
-  int cells_per_block(int degree, bool quad)
+  int cells_per_block(int degree)
   {
     switch (degree)
       {
-        case 2: return quad ? Cfg<2, true>::CPB : Cfg<2>::CPB;
-        case 3: return quad ? Cfg<3, true>::CPB : Cfg<3>::CPB;
-        case 4: return quad ? Cfg<4, true>::CPB : Cfg<4>::CPB;
-        case 5: return quad ? Cfg<5, true>::CPB : Cfg<5>::CPB;
-        case 6: return quad ? Cfg<6, true>::CPB : Cfg<6>::CPB;
-        case 7: return quad ? Cfg<7, true>::CPB : Cfg<7>::CPB;
-        case 8: return quad ? Cfg<8, true>::CPB : Cfg<8>::CPB;
+        case 2: return Cfg<2>::CPB;
+        case 3: return Cfg<3>::CPB;
+        case 4: return Cfg<4>::CPB;
+        case 5: return Cfg<5>::CPB;
+        case 6: return Cfg<6>::CPB;
+        case 7: return Cfg<7>::CPB;
+        case 8: return Cfg<8>::CPB;
       }
     return 0;
   }
@@ -1189,14 +1140,14 @@ namespace bp4
 
   // assemble the scalar GLL diagonal: entry of node i goes to diag[i * stride]
   cudaError_t launch_diag_assemble(int degree, uint64_t n_cells, const uint32_t *entity_index,
-                                   const double *coef, int n_coef, const double *gll, double *diag,
-                                   int stride, cudaStream_t st)
+                                   const double *coef, const double *gll, double *diag, int stride,
+                                   cudaStream_t st)
   {
     const int      N3 = (degree + 1) * (degree + 1) * (degree + 1);
     const uint64_t n  = n_cells * N3;
     if (n > 0)
-      diag_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(degree, n_cells, entity_index, coef, n_coef,
-                                                                gll, diag, stride);
+      diag_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(degree, n_cells, entity_index, coef, gll,
+                                                                diag, stride);
     return cudaGetLastError();
   }
 

@@ -18,31 +18,29 @@ namespace bp4
   constexpr int kThreads     = 128;
   constexpr int kBlocksPerSM = 2;
 
-  // QUAD: all 27 geometry coefficients per cell (81 doubles) instead of the 8 tri-linear ones (24)
-  template <int P, bool QUAD = false>
+  template <int P>
   struct Cfg
   {
     using G = Geom<P>;
-    static constexpr int NCOEF = QUAD ? 81 : 24;
     // resident blocks per SM of the cell kernel: three (<= 168 registers, smaller batches)
     // measured faster at Q2 (+12 %) and Q6 (+13 %), slower or equal elsewhere
     static constexpr int BLOCKS   = (P == 2 || P == 6) ? 3 : kBlocksPerSM;
     static constexpr int budget   = (227 * 1024) / BLOCKS - 512;
-    static constexpr int per_cell = (G::WORK + 2 * NCOEF) * 8 + 2 * 28 * 4;
+    static constexpr int per_cell = (G::WORK + 2 * 24) * 8 + 2 * 28 * 4;
     static constexpr int fit      = (budget - 4 * G::DOF - 16 * G::Q - 256) / per_cell;
     // phase 2 carries ~2/3 of the FP64 work: prefer Q^2*CPB close to a multiple of the block
     static constexpr int want = (2 * kThreads) / (G::Q * G::Q) > 0 ? (2 * kThreads) / (G::Q * G::Q) : 1;
     static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
   };
 
-  template <int P, int CPB, int NCOEF = 24>
+  template <int P, int CPB>
   struct alignas(16) CellSmem
   {
     using G = Geom<P>;
     // the gathered DoFs, the three phases and the result all live in the work rows: gather
     // fills the first N*N slots of each row, phases 1 and 3 run in place
     double   work[CPB * G::WORK];
-    double   coef[2][CPB][NCOEF]; // double-buffered: the next batch's metadata is prefetched
+    double   coef[2][CPB][24]; // double-buffered: the next batch's metadata is prefetched
     double   xq[G::Q];
     double   wq[G::Q];
     double   red[8];           // fused: the block's share of the seven merged sums
@@ -72,7 +70,7 @@ namespace bp4
   struct CellArgs
   {
     const uint32_t *entity_index; // [n_cells][27]
-    const double   *coef;         // [n_cells][24] tri-linear or [n_cells][81] quadratic coefficients
+    const double   *coef;         // [n_cells][24] tri-linear coefficients
     const uint32_t *dtab;         // [3 N^3] gather/scatter table (build_dof_table)
     uint64_t        n_cells;      // plain: cells of this launch, batches are cut on the fly
     const double   *src;          // plain: input vector; fused: the search direction d (= p)

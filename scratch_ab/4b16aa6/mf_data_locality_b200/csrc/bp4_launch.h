@@ -10,11 +10,10 @@
 namespace bp4
 {
   cudaError_t launch_init_degree(int degree, std::vector<uint32_t> &walk);
-  int         cells_per_block(int degree, bool quad = false);
+  int         cells_per_block(int degree);
   int         blocks_per_sm(int degree);
-  // plain: a.n_cells cells from a.entity_index on; fused: a.n_units units of a.unit_batch;
-  // quad: a.coef holds all 27 coefficients per cell (plain kernel only)
-  cudaError_t launch_cell(int degree, bool fused, bool quad, const CellArgs &a, int sms, cudaStream_t st);
+  // plain: a.n_cells cells from a.entity_index on; fused: a.n_units units of a.unit_batch
+  cudaError_t launch_cell(int degree, bool fused, const CellArgs &a, int sms, cudaStream_t st);
   // do_cg_update4b / do_cg_update3b on the DoF interval [begin, end) (the DoFs no range owns)
   cudaError_t launch_pre(uint64_t begin, uint64_t end, double *h, double *x, double *r, double *p,
                          const double *prec, double alpha, double beta, double alpha_old,
@@ -35,8 +34,8 @@ namespace bp4
   cudaError_t launch_xfinal(uint64_t n, double *x, const double *d, const double *g, const double *prec,
                             double c1, double c2, int sms, cudaStream_t st);
   cudaError_t launch_diag_assemble(int degree, uint64_t n_cells, const uint32_t *entity_index,
-                                   const double *coef, int n_coef, const double *gll, double *diag,
-                                   int stride, cudaStream_t st);
+                                   const double *coef, const double *gll, double *diag, int stride,
+                                   cudaStream_t st);
   cudaError_t launch_diag_invert(uint64_t n_nodes, double *diag, cudaStream_t st);
   cudaError_t launch_pack(uint64_t n, const uint32_t *idx, const double *v, double *buf, cudaStream_t st);
   cudaError_t launch_unpack_add(uint64_t n, const uint32_t *idx, const double *buf, double *v, cudaStream_t st);

@@ -42,14 +42,12 @@ class Problem:
     """BenchmarkProblem of host/benchmark.h.  device < 0 builds the tables only (no GPU)."""
 
     def __init__(self, degree, s, plugin="merged", n_ranks=1, rank=0, device=0, n_lanes=8,
-                 batches_per_range=1, renumber=(0, 1, 2), nccl_id: bytes | None = None,
-                 numbering_only=False, mapping_degree=1):
+                 batches_per_range=1, renumber=(0, 1, 2), nccl_id: bytes | None = None):
         """nccl_id: the 128-byte ncclUniqueId shared by all ranks (needed when n_ranks > 1 and a
         device is used; see capi.unique_id())"""
         self.l = lib(plugin)
         self.plugin = plugin
-        opts = (C.c_int * 10)(n_ranks, rank, device, n_lanes, batches_per_range, *renumber,
-                              1 if numbering_only else 0, mapping_degree)
+        opts = (C.c_int * 8)(n_ranks, rank, device, n_lanes, batches_per_range, *renumber)
         idbuf = (C.c_ubyte * 128).from_buffer_copy(nccl_id) if nccl_id else None
         self.h = C.c_void_p()
         self._chk(self.l.bp4h_create(C.c_int(degree), C.c_int(s), opts, idbuf, C.byref(self.h)))
@@ -80,16 +78,6 @@ class Problem:
     def vertices(self):
         out = np.empty((self.n_cells, 8, 3))
         self._chk(self.l.bp4h_get_vertices(self.h, _p(out)))
-        return out
-
-    def coefficients(self):
-        """[n_cells][27][3] geometry coefficients of a quadratic mapping, None for the tri-linear one"""
-        n = C.c_uint64()
-        self._chk(self.l.bp4h_get_coefficients(self.h, C.byref(n), None))
-        if n.value == 0:
-            return None
-        out = np.empty((self.n_cells, 27, 3))
-        self._chk(self.l.bp4h_get_coefficients(self.h, C.byref(n), _p(out)))
         return out
 
     def ranges(self):

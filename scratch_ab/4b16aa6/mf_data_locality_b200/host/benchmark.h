@@ -79,8 +79,6 @@ struct BenchmarkOptions
   // multi-GPU: the 128-byte ncclUniqueId all ranks share (created by rank 0 with
   // bp4_comm_unique_id and distributed by the launcher); plays the role of MPI_COMM_WORLD
   const unsigned char *nccl_id = nullptr;
-  unsigned int mapping_degree = 1; // 2: genuinely quadratic cells (the TODO of benchmark.h:75-77)
-  bool numbering_only = false; // stop after Renumber + MatrixFree::reinit (inspection of numberings)
 };
 
 class Timer
@@ -107,13 +105,6 @@ struct BenchmarkProblem
   BenchmarkProblem(const unsigned int s, const BenchmarkOptions &opt)
     : tria(opt.n_ranks, opt.rank), dof_handler(tria)
   {
-    Timer      lap;
-    const bool show = std::getenv("BP4_SETUP_TIMING") != nullptr;
-    auto       tick = [&](const char *what) {
-      if (show)
-        std::cerr << "  setup[" << opt.rank << "] " << what << ": " << lap.wall_time() << " s" << std::endl;
-      lap.restart();
-    };
     // box [0,2]^r x [0,1]^(3-r), r = s % 3, refined s / 3 times, vertices moved by the chart
     const unsigned int          n_refine = s / 3, remainder = s % 3;
     std::array<unsigned int, 3> subdivisions{{1, 1, 1}};
@@ -122,19 +113,15 @@ struct BenchmarkProblem
     MyManifold<dim> manifold;
     tria.build(subdivisions, n_refine, [manifold](const Point3 &p) { return manifold.push_forward(p); });
 
-    tick("triangulation");
     dof_handler.distribute_dofs(FESystem{fe_degree, n_components});
     VectorTools::interpolate_boundary_values(dof_handler, constraints);
     constraints.close();
-    tick("distribute_dofs");
 
     mf_data.n_lanes           = opt.n_lanes;
     mf_data.batches_per_range = opt.batches_per_range;
-    mf_data.mapping_degree    = opt.mapping_degree;
 
     Renumber<dim, double> renum(opt.renumber_a, opt.renumber_r, opt.renumber_g);
     renum.renumber(dof_handler, constraints, mf_data);
-    tick("renumber");
 
     // Dirichlet constraints are geometric here, so they need no rebuild after renumbering
     // (the reference re-creates them at benchmark.h:115-120)
@@ -143,11 +130,7 @@ struct BenchmarkProblem
     // Jacobi preconditioner from the diagonal under GLL(p+1) quadrature (benchmark.h:124-148);
     // the device routine evaluates exactly that quadrature
     matrix_free->reinit(dof_handler, constraints, n_q_points, mf_data);
-    tick("matrix_free.reinit");
-    if (opt.numbering_only)
-      return;
     laplace_operator.initialize(matrix_free, constraints, opt.device);
-    tick("operator.initialize");
     if (opt.device < 0)
       return; // tables only
     if (opt.n_ranks > 1)
@@ -155,14 +138,7 @@ struct BenchmarkProblem
         AssertThrow(opt.nccl_id != nullptr, "n_ranks > 1 needs BenchmarkOptions::nccl_id");
         bp4_check(bp4_comm_init(laplace_operator.context(), (int)opt.rank, (int)opt.n_ranks, opt.nccl_id));
       }
-    {
-      // benchmark.h:139-147: keep the first component's entry of every node
-      const auto                         vector = laplace_operator.compute_inverse_diagonal();
-      const Utilities::MPI::Partitioner &part   = *matrix_free->get_dof_info().vector_partitioner;
-      diag_mat.diagonal.reinit(laplace_operator.context(), part.locally_owned_size() / n_components, 0,
-                               dof_handler.n_dofs() / n_components);
-      diag_mat.diagonal.extract_component(vector, n_components, 0);
-    }
+    laplace_operator.compute_inverse_diagonal(diag_mat.diagonal);
 
     // right-hand side i % 8 on unconstrained local entries, start vector 0 (benchmark.h:170-176)
     laplace_operator.initialize_dof_vector(input);
@@ -212,7 +188,17 @@ BenchmarkResult run_templated(const unsigned int s, const bool short_output, con
   res.n_dofs     = problem.dof_handler.n_dofs();
   if (!short_output)
     {
-      const double diag_norm = problem.diag_mat.diagonal.l2_norm(); // benchmark.h:149-154
+      // benchmark.h:149-154.  The diagonal holds one value per node; its global l2 norm goes
+      // through the same reduction as every other norm: spread it to component 0 of a DoF vector
+      const std::uint64_t n_nodes = problem.diag_mat.diagonal.local_size();
+      std::vector<double> nodes(n_nodes), spread(problem.input.local_size(), 0.);
+      problem.diag_mat.diagonal.download(nodes.data(), n_nodes);
+      for (std::uint64_t i = 0; i < n_nodes; ++i)
+        spread[n_components * i] = nodes[i];
+      dealii::LinearAlgebra::distributed::Vector<double> tmp;
+      tmp.reinit(problem.input);
+      tmp.upload(spread.data(), spread.size());
+      const double diag_norm = tmp.l2_norm();
       if (opt.rank == 0)
         std::cout << "Norm of diagonal for preconditioner: " << diag_norm << std::endl;
     }
@@ -233,8 +219,8 @@ BenchmarkResult run_templated(const unsigned int s, const bool short_output, con
   for (unsigned int t = 0; t < 2; ++t)
     {
       time.restart();
-      for (unsigned int i = 0; i < 50; ++i) // argument order as in the reference (benchmark.h:209)
-        problem.laplace_operator.vmult(problem.input, problem.output);
+      for (unsigned int i = 0; i < 50; ++i)
+        problem.laplace_operator.vmult(problem.output, problem.input);
       bp4_check(bp4_ctx_synchronize(problem.laplace_operator.context()));
       matvec_time = std::min(time.wall_time() / 50, matvec_time);
     }

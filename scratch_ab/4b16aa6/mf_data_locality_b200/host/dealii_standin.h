@@ -21,7 +21,6 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
-#include <thread>
 #include <vector>
 
 #define AssertThrow(cond, msg)         \
@@ -34,34 +33,6 @@
 
 namespace dealii
 {
-  // f(begin, end) on disjoint chunks of [0, n), one host thread per chunk (set-up loops over cells)
-  template <typename F>
-  inline void parallel_chunks(const std::uint64_t n, F &&f)
-  {
-    const unsigned int nt = (unsigned int)std::max<std::uint64_t>(
-      1, std::min<std::uint64_t>({(std::uint64_t)std::thread::hardware_concurrency(), 16, n / 4096 + 1}));
-    std::vector<std::string> errors(nt);
-    std::vector<std::thread> workers;
-    auto                     run = [&](const unsigned int t) {
-      try
-        {
-          f(n * t / nt, n * (t + 1) / nt);
-        }
-      catch (const std::exception &e)
-        {
-          errors[t] = e.what();
-        }
-    };
-    for (unsigned int t = 1; t < nt; ++t)
-      workers.emplace_back(run, t);
-    run(0);
-    for (auto &w : workers)
-      w.join();
-    for (const auto &e : errors)
-      if (!e.empty())
-        throw std::runtime_error(e);
-  }
-
   namespace types
   {
     using global_dof_index = std::uint64_t;
@@ -148,18 +119,6 @@ namespace dealii
       Point3       p;
       for (int d = 0; d < 3; ++d)
         p[d] = double(cells[cell][d] + ((v >> d) & 1u)) * h;
-      return chart(p);
-    }
-
-    // geometry node (i, j, k) / 2, i, j, k in {0, 1, 2}, of a cell under a quadratic mapping:
-    // the chart evaluated at the lattice half-steps (what MappingQ(2) places on the manifold)
-    Point3 point27(std::uint64_t cell, unsigned int i, unsigned int j, unsigned int k) const
-    {
-      const double       h   = 1.0 / double(1u << refinements);
-      const unsigned int o[3] = {i, j, k};
-      Point3             p;
-      for (int d = 0; d < 3; ++d)
-        p[d] = (double(cells[cell][d]) + 0.5 * double(o[d])) * h;
       return chart(p);
     }
 

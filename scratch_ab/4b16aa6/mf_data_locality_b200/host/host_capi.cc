@@ -25,7 +25,6 @@ namespace
     virtual const DoFHandler &dh()                                      = 0;
     virtual const std::vector<unsigned int> &entity()                   = 0;
     virtual const std::vector<double>       &vertices()                 = 0;
-    virtual const std::vector<double>       &coefficients()             = 0;
     virtual const std::vector<std::uint64_t> &range_cells()             = 0;
     virtual const std::vector<std::uint64_t> &range_private()           = 0;
     virtual LinearAlgebra::distributed::Vector<double> &input()         = 0;
@@ -45,7 +44,6 @@ namespace
     const DoFHandler &dh() override { return prob.dof_handler; }
     const std::vector<unsigned int> &entity() override { return prob.laplace_operator.get_compressed_dof_indices(); }
     const std::vector<double>       &vertices() override { return prob.laplace_operator.get_cell_vertices(); }
-    const std::vector<double>       &coefficients() override { return prob.laplace_operator.get_cell_coefficients(); }
     const std::vector<std::uint64_t> &range_cells() override { return prob.laplace_operator.get_range_cell_offset(); }
     const std::vector<std::uint64_t> &range_private() override { return prob.laplace_operator.get_range_private_offset(); }
     LinearAlgebra::distributed::Vector<double> &input() override { return prob.input; }
@@ -82,8 +80,7 @@ const char *bp4h_plugin(void)
 #endif
 }
 
-// options: [n_ranks, rank, device, n_lanes, batches_per_range, renumber_a, renumber_r, renumber_g,
-//           numbering_only, mapping_degree]
+// options: [n_ranks, rank, device, n_lanes, batches_per_range, renumber_a, renumber_r, renumber_g]
 int bp4h_create(int degree, int s, const int *options, const unsigned char *nccl_id, void **out)
 {
   return guarded([&] {
@@ -94,8 +91,6 @@ int bp4h_create(int degree, int s, const int *options, const unsigned char *nccl
         opt.n_ranks = options[0], opt.rank = options[1], opt.device = options[2];
         opt.n_lanes = options[3], opt.batches_per_range = options[4];
         opt.renumber_a = options[5], opt.renumber_r = options[6], opt.renumber_g = options[7];
-        opt.numbering_only = options[8] != 0;
-        opt.mapping_degree = options[9] > 0 ? options[9] : 1;
       }
     Timer        t;
     ProblemBase *p = nullptr;
@@ -166,16 +161,6 @@ int bp4h_get_ranges(void *h, std::uint64_t *n, std::uint64_t *cell_offset, std::
       std::copy(p->range_cells().begin(), p->range_cells().end(), cell_offset);
     if (private_offset)
       std::copy(p->range_private().begin(), p->range_private().end(), private_offset);
-  });
-}
-// [n_cells][27][3] geometry coefficients of a quadratic mapping (*n = 0 for the tri-linear one)
-int bp4h_get_coefficients(void *h, std::uint64_t *n, double *out)
-{
-  return guarded([&] {
-    const auto &c = static_cast<ProblemBase *>(h)->coefficients();
-    *n            = c.size();
-    if (out)
-      std::memcpy(out, c.data(), c.size() * sizeof(double));
   });
 }
 int bp4h_get_constrained(void *h, std::uint32_t *out)

@@ -13,10 +13,6 @@ namespace dealii
     unsigned int n_lanes            = 8;    // VectorizedArray<double>::size(), AVX-512
     unsigned int batches_per_range  = 1;    // cell batches per cell_partition_data range
     bool         initialize_mapping = true; // unused: geometry is evaluated on the fly
-    // degree of the Mapping handed to MatrixFree::reinit in the reference (MappingQGeneric(1),
-    // benchmark.h:89).  2 = genuinely quadratic cells: LaplaceOperator::initialize then fills all
-    // 27 coefficient vectors (the TODO of benchmark.h:75-77, poisson_operator.h:169 "for now")
-    unsigned int mapping_degree = 1;
   };
 
   class MatrixFree

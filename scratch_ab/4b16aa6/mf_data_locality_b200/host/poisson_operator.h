@@ -19,11 +19,8 @@ namespace Poisson
 {
   using namespace dealii;
 
-  // VectorizedArrayType is the reference's seventh parameter (poisson_operator.h:67-74): the SIMD
-  // type of its CPU kernels.  Accepted and ignored so that reference call sites compile unchanged.
   template <int dim, int fe_degree, int n_q_points_1d = fe_degree + 1, int n_components_ = 1,
-            typename Number = double, typename VectorType = LinearAlgebra::distributed::Vector<Number>,
-            typename VectorizedArrayType = void>
+            typename Number = double, typename VectorType = LinearAlgebra::distributed::Vector<Number>>
   class LaplaceOperator
   {
   public:
@@ -53,11 +50,10 @@ namespace Poisson
       cell_vertices.resize(std::size_t(24) * n_cells);
       constexpr unsigned int p = fe_degree;
       const unsigned int lo[3] = {0, 1, p}, hi[3] = {1, p, p + 1};
-      // cells in loop order (batch by batch, lane by lane); the per-cell work is independent
-      parallel_chunks(n_cells, [&](const std::uint64_t c0, const std::uint64_t c1) {
-        for (std::uint64_t cell_no = c0; cell_no < c1; ++cell_no)
+      for (unsigned int b = 0, cell_no = 0; b < data->n_cell_batches(); ++b)
+        for (unsigned int l = 0; l < data->n_active_entries_per_cell_batch(b); ++l, ++cell_no)
           {
-            const std::uint64_t cell = data->cell_order[cell_no];
+            const std::uint64_t cell = data->get_cell(b, l);
             for (unsigned int v = 0; v < 8; ++v)
               {
                 const Point3 x = dh.get_triangulation().vertex(cell, v);
@@ -82,49 +78,13 @@ namespace Poisson
                 compressed_dof_indices[27 * std::size_t(cell_no) + a] = part.global_to_local(g0);
               }
           }
-      });
 
       compute_private_ranges(dh, constraints, part);
-      // quadratic mapping: all 27 coefficient vectors v_{a+3b+9c} of X = sum v_m xi^a eta^b zeta^c
-      // (cell_quadratic_coefficients, :690) from the 27 geometry nodes; per direction the
-      // interpolant through t = 0, 1/2, 1 is f0 + (-3 f0 + 4 f1 - f2) t + (2 f0 - 4 f1 + 2 f2) t^2
-      cell_coefficients.clear();
-      if (data->get_additional_data().mapping_degree == 2)
-        {
-          cell_coefficients.resize(std::size_t(81) * n_cells);
-          static const double T[3][3] = {{1., 0., 0.}, {-3., 4., -1.}, {2., -4., 2.}};
-          parallel_chunks(n_cells, [&](const std::uint64_t c0, const std::uint64_t c1) {
-            for (std::uint64_t cell_no = c0; cell_no < c1; ++cell_no)
-              {
-                const std::uint64_t cell = data->cell_order[cell_no];
-                Point3              X[27];
-                for (unsigned int k = 0; k < 3; ++k)
-                  for (unsigned int j = 0; j < 3; ++j)
-                    for (unsigned int i = 0; i < 3; ++i)
-                      X[i + 3 * j + 9 * k] = dh.get_triangulation().point27(cell, i, j, k);
-                for (unsigned int c = 0; c < 3; ++c)
-                  for (unsigned int b = 0; b < 3; ++b)
-                    for (unsigned int a = 0; a < 3; ++a)
-                      for (unsigned int d = 0; d < 3; ++d)
-                        {
-                          double v = 0.;
-                          for (unsigned int k = 0; k < 3; ++k)
-                            for (unsigned int j = 0; j < 3; ++j)
-                              for (unsigned int i = 0; i < 3; ++i)
-                                v += T[c][k] * T[b][j] * T[a][i] * X[i + 3 * j + 9 * k][d];
-                          cell_coefficients[81 * std::size_t(cell_no) + 3 * (a + 3 * b + 9 * c) + d] = v;
-                        }
-              }
-          });
-        }
-      else
-        AssertThrow(data->get_additional_data().mapping_degree == 1, "mapping degree 1 or 2");
 
       bp4_desc desc{};
       desc.n_ranges             = range_cell_offset.empty() ? 0 : range_cell_offset.size() - 1;
       desc.range_cell_offset    = range_cell_offset.data();
       desc.range_private_offset = range_private_offset.data();
-      desc.coefficients         = cell_coefficients.empty() ? nullptr : cell_coefficients.data();
       desc.degree        = fe_degree;
       desc.device        = device;
       desc.n_cells       = n_cells;
@@ -175,16 +135,16 @@ namespace Poisson
     }
 
     // Inverse diagonal of the scalar Laplacian under the quadrature this operator was set up
-    // with (the reference instantiates it with GLL(p+1), benchmark.h:128-140), returned the way
-    // the reference returns it (poisson_operator.h:392-426): a DoF vector with 1/diag on the
-    // first component of every node and 1 wherever the assembled value is 0.  The caller keeps
-    // every n_components-th entry (benchmark.h:141-147).
-    VectorType compute_inverse_diagonal() const
+    // with (the reference instantiates it with GLL(p+1), benchmark.h:128-140), 1 where the
+    // diagonal is 0.  The reference returns a DoF-sized vector whose every third entry is
+    // then copied into the blocked diagonal (poisson_operator.h:392-426, benchmark.h:141-147);
+    // here the per-node values are produced directly in that final layout.
+    void compute_inverse_diagonal(VectorType &per_node) const
     {
-      VectorType diag;
-      initialize_dof_vector(diag);
-      bp4_check(bp4_inverse_diagonal_vector(ctx, diag.handle()));
-      return diag;
+      const Utilities::MPI::Partitioner &part = *data->get_dof_info().vector_partitioner;
+      per_node.reinit(ctx, part.locally_owned_size() / n_components, 0,
+                      data->get_dof_handler().n_dofs() / n_components);
+      bp4_check(bp4_inverse_diagonal(ctx, per_node.handle()));
     }
 
     // cell-batch ranges of the loop and the owned DoFs private to each (bp4_desc::n_ranges)
@@ -194,7 +154,6 @@ namespace Poisson
     bp4_ctx                          *context() const { return ctx; }
     const std::vector<unsigned int>  &get_compressed_dof_indices() const { return compressed_dof_indices; }
     const std::vector<double>        &get_cell_vertices() const { return cell_vertices; }
-    const std::vector<double>        &get_cell_coefficients() const { return cell_coefficients; }
     const MatrixFree                 &get_matrix_free() const { return *data; }
 
   private:
@@ -267,7 +226,6 @@ namespace Poisson
     std::shared_ptr<const MatrixFree> data;
     std::vector<unsigned int>         compressed_dof_indices; // [cell][27], one lane per cell
     std::vector<double>               cell_vertices;          // [cell][8][3]
-    std::vector<double>               cell_coefficients;      // [cell][27][3], quadratic mapping only
     bp4_ctx                          *ctx = nullptr;
   };
 } // namespace Poisson

@@ -29,7 +29,8 @@ def make_ctx(rd, device=0, ranges=True):
     from mf_data_locality_b200 import capi
     return capi.Context(rd.degree, rd.entity_index, rd.vertices, rd.n_owned, rd.n_ghost,
                         rd.constrained, device=device,
-                        ranges=(rd.range_cell_offset, rd.range_private_offset) if ranges else None)
+                        ranges=(rd.range_cell_offset, rd.range_private_offset) if ranges else None,
+                        coefficients=rd.coefficients)
 
 
 def rel_l2(a, b):

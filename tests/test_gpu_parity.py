@@ -216,6 +216,64 @@ def test_fused_needs_range_tables(bp4_lib):
                      ranges=(rd.range_cell_offset, bad))
 
 
+@pytest.mark.parametrize("p,s", [(2, 6), (3, 6), (4, 7), (5, 5), (6, 5), (7, 4), (8, 4)])
+def test_quadratic_geometry_matches_oracle(p, s, bp4_lib):
+    """genuinely quadratic cells: all 27 coefficient vectors per cell cross the ABI
+    (bp4_desc::coefficients) and the kernel evaluates the full form of
+    poisson_operator.h:577-602.  Operator apply, GLL inverse diagonal and one merged iteration
+    against the numpy oracle (which is pinned by a dense tri-quadratic assembly)."""
+    from mf_data_locality_b200 import capi
+    rd = O.build_problem(p, s, quadratic=True)[0]
+    t = O.make_tables(p)
+    ctx = make_ctx(rd)
+    v = np.random.default_rng(p).standard_normal(rd.n_owned)
+    src, dst = ctx.vector(data=v), ctx.vector()
+    ctx.vmult(dst, src)
+    got = dst.download()
+    want = O.vmult(rd, t, v)
+    assert rel_l2(got, want) <= 1e-12
+    lin = O.vmult(O.build_problem(p, s)[0], t, v)
+    assert rel_l2(got, lin) > 1e-3                      # not the tri-linear operator
+    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    assert rel_l2(ctx.inverse_diagonal().download(), prec) <= 1e-12
+    # the in-loop vector updates are built for the tri-linear kernel only: asking is an error
+    assert ctx.fused_info()[0] is False
+    with pytest.raises(capi.Bp4Error):
+        ctx.set_fused(True)
+    n = rd.n_owned
+    rng = np.random.default_rng(9)
+    free = np.ones(n)
+    free[rd.constrained] = 0.0
+    prec3 = np.repeat(prec, 3)
+    vp = ctx.vector(n // 3, data=prec)
+    x, g, d, h = (rng.standard_normal(n) * free for _ in range(4))
+    vx, vg, vd, vh = (ctx.vector(data=a) for a in (x, g, d, h))
+    S = ctx.vmult_merged(vx, vg, vd, vh, vp, 0.7, 0.3, 0.4, 0.2)
+    O.cg_update4b(h, x, g, d, prec3, 0.7, 0.3, 0.4, 0.2)
+    h[:] = O.vmult_cells(rd, t, d)
+    np.testing.assert_allclose(S, O.cg_update3b(g, d, h, prec3), rtol=1e-11)
+    ctx.close()
+
+
+def test_quadratic_geometry_through_the_host_mirror(bp4_lib):
+    """mapping_degree = 2 in the C++ mirror: set-up, operator and the merged plugin on quadratic cells"""
+    from mf_data_locality_b200 import host
+    p, s = 4, 7
+    rd = O.build_problem(p, s, quadratic=True)[0]
+    t = O.make_tables(p)
+    prob = host.Problem(p, s, plugin="merged", device=0, mapping_degree=2)
+    v = np.random.default_rng(1).standard_normal(rd.n_owned)
+    assert rel_l2(prob.vmult(v), O.vmult(rd, t, v)) <= 1e-12
+    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    assert rel_l2(prob.diagonal(), prec) <= 1e-12
+    ctl = O.ReductionControl(100, 1e-15, 1e-8)
+    xo = O.solver_cg_merged(lambda w: O.vmult_cells(rd, t, w), np.zeros(rd.n_owned), rd.rhs, prec, ctl)
+    x, it = prob.run_cg_solver(rd.rhs)
+    assert abs(it - ctl.last_step) <= 1
+    assert rel_l2(x, xo) <= (1e-8 if ctl.last_step < 100 else 1e-6)
+    prob.close()
+
+
 # ---- parity at the sizes BASELINE.json quotes (configs[0..2]) ------------------------------
 SCALE_CASES = [pytest.param(3, 15, False, id="config0-Q3-s15-plain"),
                pytest.param(4, 18, True, id="config1-Q4-s18-merged"),

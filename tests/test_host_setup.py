@@ -103,6 +103,22 @@ def test_renumber_strategies(host):
     assert len(seen) >= 4          # the strategies really are different numberings
 
 
+@pytest.mark.parametrize("p,s,n_ranks", [(3, 6, 1), (2, 7, 2), (5, 4, 1)])
+def test_quadratic_mapping_coefficients(host, p, s, n_ranks):
+    """mapping_degree = 2: LaplaceOperator::initialize fills all 27 coefficient vectors of every
+    cell (the array local_apply evaluates, poisson_operator.h:577-602, :690) -- equal to the
+    oracle's to rounding; the tri-linear mapping hands none"""
+    for r, rd in enumerate(O.build_problem(p, s, n_ranks=n_ranks, quadratic=True)):
+        pr = host.Problem(p, s, device=-1, n_ranks=n_ranks, rank=r, mapping_degree=2)
+        c = pr.coefficients()
+        assert c.shape == rd.coefficients.shape and np.allclose(c, rd.coefficients, rtol=0, atol=1e-13)
+        assert np.array_equal(pr.entity_index(), rd.entity_index)
+        pr.close()
+    pr = host.Problem(p, s, device=-1)
+    assert pr.coefficients() is None
+    pr.close()
+
+
 def test_unsupported_degree(host):
     with pytest.raises(host.HostError, match="degrees 2 to 8"):
         host.Problem(9, 3, device=-1)
