@@ -189,7 +189,7 @@ namespace bp4
     };
     auto claim_ahead = [&](const uint32_t j_cur) { // thread 0 only; visible after the next barrier
       if (dynamic)
-        while (sm.n_claimed < j_cur + (FUSED ? 5u : 3u))
+        while (sm.n_claimed < j_cur + 5u)
           {
             sm.units[sm.n_claimed & 7u] = gridDim.x + atomicAdd(a.sched, 1u);
             ++sm.n_claimed;
@@ -454,13 +454,10 @@ namespace bp4
         nn_it  = nxt_it;
         if (nxt_it.valid)
           {
-            nxt = describe(nxt_it);
-            if constexpr (FUSED) // the plain kernel looks one batch ahead only
-              {
-                nn_it = advance(nxt_it);
-                if (nn_it.valid)
-                  nn = describe(nn_it);
-              }
+            nxt   = describe(nxt_it);
+            nn_it = advance(nxt_it);
+            if (nn_it.valid)
+              nn = describe(nn_it);
           }
         if (FUSED)
           {
@@ -610,15 +607,10 @@ namespace bp4
         }
         BP4_TICK(6)
         BP4_TRACE(i, 2)
-        It    n3_it = nn_it;
-        Batch n3{};
-        if constexpr (FUSED)
-          {
-            if (nn_it.valid)
-              n3_it = advance(nn_it);
-            if (n3_it.valid)
-              n3 = describe(n3_it);
-          }
+        const It n3_it = nn_it.valid ? advance(nn_it) : nn_it;
+        Batch    n3{};
+        if (n3_it.valid)
+          n3 = describe(n3_it);
         if (FUSED)
           {
             post_finish(wpost, done_b, done_e, do_post);
@@ -643,18 +635,8 @@ namespace bp4
             done_b = cur.post_b, done_e = cur.post_e;
           }
         cur_it = nxt_it, cur = nxt;
-        if constexpr (FUSED)
-          {
-            nxt_it = nn_it, nxt = nn;
-            nn_it = n3_it, nn = n3;
-          }
-        else
-          {
-            if (nxt_it.valid)
-              nxt_it = advance(nxt_it);
-            if (nxt_it.valid)
-              nxt = describe(nxt_it);
-          }
+        nxt_it = nn_it, nxt = nn;
+        nn_it = n3_it, nn = n3;
       }
     if (FUSED)
       {
