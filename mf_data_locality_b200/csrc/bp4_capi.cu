@@ -91,7 +91,9 @@ struct bp4_ctx
   int         *d_flag = nullptr;
   uint32_t    *d_sched = nullptr; // [4] unit counters of the cell-kernel launches of one loop
   uint32_t     stagger_ns = 0;    // developer knob BP4_STAGGER_NS
-  double      *h_acc  = nullptr; // pinned [8]
+  double      *h_acc  = nullptr; // pinned [8] + sequence word (h_acc[8] reinterpreted), device-mapped
+  unsigned long long pub_seq = 0;
+  int          spin_wait = 1;    // BP4_SPIN_WAIT=0: cudaMemcpyAsync + cudaStreamSynchronize instead
   int         *h_flag = nullptr; // pinned
   // fused merged loop (vmult_with_merged_sums): units of whole cell-batch ranges, their batches
   // and the private DoF runs the vector updates are hooked to (bp4_kernels.cuh, BatchDesc)
@@ -131,6 +133,7 @@ struct bp4_ctx
   // measurement
   bool                   profile = false;
   std::vector<ProfEvent> events;
+  std::vector<cudaEvent_t> event_pool; // recycled timing events (creating one costs microseconds)
   double                 prof_ms[BP4_K_COUNT]  = {0};
   uint64_t               prof_cnt[BP4_K_COUNT] = {0};
   uint64_t               launches               = 0;
@@ -150,8 +153,14 @@ namespace
       c->prof_cnt[id] += 1;
       if (on)
         {
-          cudaEventCreate(&ev.a);
-          cudaEventCreate(&ev.b);
+          for (cudaEvent_t *e : {&ev.a, &ev.b})
+            if (c->event_pool.empty())
+              cudaEventCreate(e);
+            else
+              {
+                *e = c->event_pool.back();
+                c->event_pool.pop_back();
+              }
           ev.id = id;
           cudaEventRecord(ev.a, c->stream);
         }
@@ -178,8 +187,8 @@ namespace
           err = cudaEventElapsedTime(&ms, ev.a, ev.b);
         if (err == cudaSuccess)
           c->prof_ms[ev.id] += ms;
-        cudaEventDestroy(ev.a);
-        cudaEventDestroy(ev.b);
+        c->event_pool.push_back(ev.a);
+        c->event_pool.push_back(ev.b);
       }
     c->events.clear();
     CU(err);
@@ -209,8 +218,30 @@ namespace
   {
     if (c->comm)
       NC(ncclAllReduce(c->d_acc, c->d_acc, k, ncclDouble, ncclSum, c->comm, c->stream));
-    CU(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    if (c->spin_wait)
+      {
+        // the last kernel of the chain writes the values and then a sequence number into mapped
+        // pinned memory; the host polls that word (and the stream, for errors, now and then)
+        volatile unsigned long long *seq_word = reinterpret_cast<volatile unsigned long long *>(c->h_acc + 8);
+        const unsigned long long     seq      = ++c->pub_seq;
+        CU(bp4::launch_publish(c->d_acc, k, c->h_acc, const_cast<unsigned long long *>(seq_word), seq, c->stream));
+        c->launches += 1;
+        int idle = 0;
+        for (unsigned long long spins = 1; *seq_word != seq; ++spins)
+          if ((spins & 0xFFFF) == 0)
+            {
+              const cudaError_t q = cudaStreamQuery(c->stream);
+              if (q != cudaSuccess && q != cudaErrorNotReady)
+                CU(q);
+              if (q == cudaSuccess && ++idle > 8) // stream drained, nothing published: cannot happen
+                return fail(BP4_ERR_CUDA, "reduction result was not published");
+            }
+      }
+    else
+      {
+        CU(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+      }
     for (int i = 0; i < k; ++i)
       out[i] = c->h_acc[i];
     return 0;
@@ -342,7 +373,10 @@ static int ctx_create_impl(const bp4_desc *d, bp4_ctx *c)
   CU(cudaMemset(c->d_acc, 0, sizeof(double) * 8));
   CU(cudaMalloc(&c->d_flag, sizeof(int)));
   CU(cudaMalloc(&c->d_sched, sizeof(uint32_t) * 4));
-  CU(cudaMallocHost(&c->h_acc, sizeof(double) * 8));
+  CU(cudaMallocHost(&c->h_acc, sizeof(double) * 16)); // UVA: the pointer is valid on the device too
+  memset(c->h_acc, 0, sizeof(double) * 16);
+  if (const char *e = getenv("BP4_SPIN_WAIT"))
+    c->spin_wait = atoi(e) != 0;
   CU(cudaMallocHost(&c->h_flag, sizeof(int)));
 
   // cell-batch ranges and their private DoF runs -> units and batches of the fused merged loop
@@ -449,6 +483,9 @@ int bp4_ctx_destroy(bp4_ctx *c)
   if (c->stream)
     cudaStreamSynchronize(c->stream);
   drain_events(c);
+  for (cudaEvent_t e : c->event_pool)
+    cudaEventDestroy(e);
+  c->event_pool.clear();
   p2p_teardown(c);
   if (c->comm)
     ncclCommDestroy(c->comm);

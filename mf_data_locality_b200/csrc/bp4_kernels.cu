@@ -789,6 +789,21 @@ namespace bp4
       atomicOr(flag, 1);
   }
 
+  // hand k reduced values to the host through mapped pinned memory: values first, then a system
+  // fence, then the sequence number the host is spinning on (a few microseconds less per host
+  // round trip than a device-to-host copy plus stream synchronisation)
+  __global__ void publish_kernel(const double *__restrict__ acc, const int k, volatile double *host_vals,
+                                 volatile unsigned long long *host_seq, const unsigned long long seq)
+  {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+      {
+        for (int i = 0; i < k; ++i)
+          host_vals[i] = acc[i];
+        __threadfence_system();
+        *host_seq = seq;
+      }
+  }
+
   // ghost exchange helpers: buf[k] = v[idx[k]] and v[idx[k]] += buf[k]
   __global__ void __launch_bounds__(256) pack_kernel(const uint64_t n, const uint32_t *__restrict__ idx,
                                                      const double *__restrict__ v, double *__restrict__ buf)
@@ -1186,6 +1201,13 @@ namespace bp4
   {
     if (n_nodes > 0)
       invert_diag_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, st>>>(n_nodes, diag);
+    return cudaGetLastError();
+  }
+
+  cudaError_t launch_publish(const double *acc, int k, double *host_vals, unsigned long long *host_seq,
+                             unsigned long long seq, cudaStream_t st)
+  {
+    publish_kernel<<<1, 32, 0, st>>>(acc, k, host_vals, host_seq, seq);
     return cudaGetLastError();
   }
 
