@@ -307,10 +307,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------
+    L.bp4_profile_enable(ctx, 1)        # on during the warm-up too: the timing events get created there
     for _ in range(args.warmup):
         prob.run_cg_solver(None, want_x=False)
     L.bp4_profile_reset(ctx)
-    L.bp4_profile_enable(ctx, 1)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_local, iters = timed_solves(prob, stream, args.steps, barrier)
