@@ -971,7 +971,8 @@ int bp4_dot(bp4_ctx *c, const bp4_vec *a, const bp4_vec *b, double *result)
   if (!c || !a || !b || !result)
     return fail(BP4_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
-  CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
+  if (!c->spin_wait) // the publish kernel leaves the accumulators cleared
+    CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
   {
     Timed t(c, BP4_K_BLAS1);
     CU(bp4::launch_dot(sweep_len(c, {a, b}), a->p(), b->p(), c->d_acc, c->sms, c->stream));
@@ -984,7 +985,8 @@ int bp4_add_and_dot(bp4_ctx *c, bp4_vec *g, double a, const bp4_vec *h, const bp
   if (!c || !g || !h || !w || !result)
     return fail(BP4_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
-  CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
+  if (!c->spin_wait) // the publish kernel leaves the accumulators cleared
+    CU(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
   {
     Timed t(c, BP4_K_BLAS1);
     CU(bp4::launch_add_and_dot(sweep_len(c, {g, h, w}), g->p(), a, h->p(), w->p(), c->d_acc, c->sms, c->stream));

@@ -792,13 +792,17 @@ namespace bp4
   // hand k reduced values to the host through mapped pinned memory: values first, then a system
   // fence, then the sequence number the host is spinning on (a few microseconds less per host
   // round trip than a device-to-host copy plus stream synchronisation)
-  __global__ void publish_kernel(const double *__restrict__ acc, const int k, volatile double *host_vals,
+  // The accumulators are cleared on the way out: the next reduction needs no memset.
+  __global__ void publish_kernel(double *acc, const int k, volatile double *host_vals,
                                  volatile unsigned long long *host_seq, const unsigned long long seq)
   {
     if (threadIdx.x == 0 && blockIdx.x == 0)
       {
         for (int i = 0; i < k; ++i)
-          host_vals[i] = acc[i];
+          {
+            host_vals[i] = acc[i];
+            acc[i]       = 0.;
+          }
         __threadfence_system();
         *host_seq = seq;
       }
@@ -1204,7 +1208,7 @@ namespace bp4
     return cudaGetLastError();
   }
 
-  cudaError_t launch_publish(const double *acc, int k, double *host_vals, unsigned long long *host_seq,
+  cudaError_t launch_publish(double *acc, int k, double *host_vals, unsigned long long *host_seq,
                              unsigned long long seq, cudaStream_t st)
   {
     publish_kernel<<<1, 32, 0, st>>>(acc, k, host_vals, host_seq, seq);

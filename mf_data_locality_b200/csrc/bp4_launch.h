@@ -38,7 +38,7 @@ namespace bp4
                                    const double *coef, int n_coef, const double *gll, double *diag,
                                    int stride, cudaStream_t st);
   cudaError_t launch_diag_invert(uint64_t n_nodes, double *diag, cudaStream_t st);
-  cudaError_t launch_publish(const double *acc, int k, double *host_vals, unsigned long long *host_seq,
+  cudaError_t launch_publish(double *acc, int k, double *host_vals, unsigned long long *host_seq,
                              unsigned long long seq, cudaStream_t st);
   cudaError_t launch_pack(uint64_t n, const uint32_t *idx, const double *v, double *buf, cudaStream_t st);
   cudaError_t launch_unpack_add(uint64_t n, const uint32_t *idx, const double *buf, double *v, cudaStream_t st);
