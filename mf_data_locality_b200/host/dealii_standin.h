@@ -34,12 +34,19 @@
 
 namespace dealii
 {
+  // threads one parallel_chunks call may use; callers that already run several workers lower it
+  inline unsigned int &parallel_cap()
+  {
+    thread_local unsigned int cap = 16;
+    return cap;
+  }
+
   // f(begin, end) on disjoint chunks of [0, n), one host thread per chunk (set-up loops over cells)
   template <typename F>
   inline void parallel_chunks(const std::uint64_t n, F &&f)
   {
     const unsigned int nt = (unsigned int)std::max<std::uint64_t>(
-      1, std::min<std::uint64_t>({(std::uint64_t)std::thread::hardware_concurrency(), 16, n / 4096 + 1}));
+      1, std::min<std::uint64_t>({(std::uint64_t)std::thread::hardware_concurrency(), parallel_cap(), n / 4096 + 1}));
     std::vector<std::string> errors(nt);
     std::vector<std::thread> workers;
     auto                     run = [&](const unsigned int t) {
@@ -130,16 +137,30 @@ namespace dealii
       const std::uint64_t chunk = cells_per_rank();
       return (unsigned int)std::min<std::uint64_t>(cell / (chunk ? chunk : 1), n_ranks - 1);
     }
+    // bits of a 21-bit number moved to every third position (Morton interleave, one dimension)
+    static std::uint64_t spread3(std::uint64_t x)
+    {
+      x &= 0x1fffff;
+      x = (x | x << 32) & 0x1f00000000ffffULL;
+      x = (x | x << 16) & 0x1f0000ff0000ffULL;
+      x = (x | x << 8) & 0x100f00f00f00f00fULL;
+      x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+      x = (x | x << 2) & 0x1249249249249249ULL;
+      return x;
+    }
+    // contribution of coordinate c of direction d to the active-cell index: the Morton bits of
+    // its position inside the coarse cell plus the coarse cell's share of the linear index
+    std::uint64_t index_part(const int d, const std::uint32_t c) const
+    {
+      const std::uint32_t side = 1u << refinements;
+      const std::uint64_t k    = c >> refinements;
+      const std::uint64_t coarse = d == 0 ? k : (d == 1 ? k * sub[0] : k * sub[0] * sub[1]);
+      return (coarse << (3 * refinements)) + (spread3(c & (side - 1)) << d);
+    }
     // active-cell index of the cell at lattice position c (inverse of the traversal order)
     std::uint64_t cell_index(const std::array<std::uint32_t, 3> &c) const
     {
-      const std::uint32_t side = 1u << refinements;
-      const std::uint32_t k[3] = {c[0] >> refinements, c[1] >> refinements, c[2] >> refinements};
-      std::uint64_t       m    = 0;
-      for (unsigned int b = 0; b < refinements; ++b)
-        for (int d = 0; d < 3; ++d)
-          m |= std::uint64_t(((c[d] & (side - 1)) >> b) & 1u) << (3 * b + d);
-      return ((std::uint64_t(k[2]) * sub[1] + k[1]) * sub[0] + k[0]) * (std::uint64_t(1) << (3 * refinements)) + m;
+      return index_part(0, c[0]) + index_part(1, c[1]) + index_part(2, c[2]);
     }
     // vertex v = x + 2y + 4z of a cell (poisson_operator.h:153-160)
     Point3 vertex(std::uint64_t cell, unsigned int v) const
@@ -203,21 +224,24 @@ namespace dealii
       owner.assign(n_nodes, (unsigned char)255);
       shared.assign(n_nodes, 0);
       AssertThrow(tria->n_ranks <= 255, "at most 255 ranks");
-      const std::uint64_t n_cells = tria->n_global_active_cells();
-      // owner = min rank over touching cells; shared = touched by more than one rank
-      for (std::uint64_t c = 0; c < n_cells; ++c)
-        {
-          const unsigned char r = (unsigned char)tria->subdomain_id(c);
-          for_each_cell_node(c, [&](std::uint64_t node, int, int, int) {
-            if (owner[node] == 255)
-              owner[node] = r;
-            else if (owner[node] != r)
+      // owner = min rank over the (up to 8) cells touching a node; shared = more than one rank.
+      // Node by node from the lattice, in parallel.
+      parallel_chunks(n_nodes, [&](const std::uint64_t n0, const std::uint64_t n1) {
+        std::uint64_t cells[8];
+        for (std::uint64_t n = n0; n < n1; ++n)
+          {
+            const unsigned int nc = incident_cells(n, cells);
+            unsigned char      lo = 255, hi = 0;
+            for (unsigned int k = 0; k < nc; ++k)
               {
-                shared[node] = 1;
-                owner[node]  = std::min(owner[node], r);
+                const unsigned char r = (unsigned char)tria->subdomain_id(cells[k]);
+                lo = std::min(lo, r);
+                hi = std::max(hi, r);
               }
-          });
-        }
+            owner[n]  = lo;
+            shared[n] = lo != hi;
+          }
+      });
       rank_offset.assign(tria->n_ranks + 1, 0);
       for (std::uint64_t n = 0; n < n_nodes; ++n)
         ++rank_offset[owner[n] + 1];
@@ -237,6 +261,33 @@ namespace dealii
       return IndexSet{3 * rank_offset[rank], 3 * rank_offset[rank + 1]};
     }
     IndexSet locally_owned_dofs() const { return locally_owned_dofs(tria->this_rank); }
+
+    // active-cell indices of the cells a lattice node belongs to (1, 2, 4 or 8 of them)
+    unsigned int incident_cells(const std::uint64_t node, std::uint64_t (&cells)[8]) const
+    {
+      const unsigned int  p      = fe.degree;
+      const std::uint64_t idx[3] = {node % nn[0], (node / nn[0]) % nn[1], node / (nn[0] * nn[1])};
+      std::uint32_t       lo[3], hi[3];
+      for (int d = 0; d < 3; ++d)
+        {
+          const std::uint32_t q = (std::uint32_t)(idx[d] / p);
+          hi[d]                 = std::min<std::uint32_t>(q, tria->n_cells_dir[d] - 1);
+          lo[d]                 = (idx[d] % p == 0 && q > 0) ? q - 1 : hi[d];
+        }
+      // the index is a sum of one term per direction: two candidates per direction at most
+      std::uint64_t part[3][2];
+      for (int d = 0; d < 3; ++d)
+        {
+          part[d][0] = tria->index_part(d, lo[d]);
+          part[d][1] = hi[d] != lo[d] ? tria->index_part(d, hi[d]) : part[d][0];
+        }
+      unsigned int n = 0;
+      for (std::uint32_t z = lo[2]; z <= hi[2]; ++z)
+        for (std::uint32_t y = lo[1]; y <= hi[1]; ++y)
+          for (std::uint32_t x = lo[0]; x <= hi[0]; ++x)
+            cells[n++] = part[0][x - lo[0]] + part[1][y - lo[1]] + part[2][z - lo[2]];
+      return n;
+    }
 
     template <typename F>
     void for_each_cell_node(std::uint64_t cell, F &&f) const

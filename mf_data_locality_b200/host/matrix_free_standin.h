@@ -50,15 +50,20 @@ namespace dealii
       // cells that touch a node owned elsewhere go to the middle partition (they read ghost
       // values / write ghost contributions); the others are split around it
       std::vector<std::uint64_t> inner, comm;
-      for (std::uint64_t c = c0; c < c1; ++c)
-        {
-          bool needs_comm = false;
-          if (tria.n_ranks > 1)
-            dh.for_each_cell_node(c, [&](std::uint64_t node, int, int, int) {
-              needs_comm |= dh.owner[node] != rank;
-            });
-          (needs_comm ? comm : inner).push_back(c);
-        }
+      {
+        std::vector<unsigned char> needs_comm(c1 - c0, 0);
+        if (tria.n_ranks > 1)
+          parallel_chunks(c1 - c0, [&](const std::uint64_t a, const std::uint64_t b) {
+            for (std::uint64_t c = c0 + a; c < c0 + b; ++c)
+              {
+                bool nc = false;
+                dh.for_each_cell_node(c, [&](std::uint64_t node, int, int, int) { nc |= dh.owner[node] != rank; });
+                needs_comm[c - c0] = nc;
+              }
+          });
+        for (std::uint64_t c = c0; c < c1; ++c)
+          (needs_comm[c - c0] ? comm : inner).push_back(c);
+      }
       const unsigned int L = ad.n_lanes;
       cell_order.clear();
       batch_start.assign(1, 0);
@@ -90,6 +95,20 @@ namespace dealii
         add_partition(inner.data(), inner.data() + inner.size());
       // deal.II appends the ghost-face partitions; Renumber loops over size() - 2
       task_info.partition_row_index.push_back(task_info.partition_row_index.back());
+      // inverse maps of the loop order: position, batch and range of every local cell
+      first_cell = c0;
+      cell_pos.assign(c1 - c0, 0);
+      batch_of_pos.assign(cell_order.size(), 0);
+      range_of_pos.assign(cell_order.size(), 0);
+      for (std::uint32_t i = 0; i < cell_order.size(); ++i)
+        cell_pos[cell_order[i] - c0] = i;
+      for (unsigned int b = 0; b + 1 < batch_start.size(); ++b)
+        for (unsigned int i = batch_start[b]; i < batch_start[b + 1]; ++i)
+          batch_of_pos[i] = b;
+      for (unsigned int r = 0; r + 1 < task_info.cell_partition_data.size(); ++r)
+        for (unsigned int b = task_info.cell_partition_data[r]; b < task_info.cell_partition_data[r + 1]; ++b)
+          for (unsigned int i = batch_start[b]; i < batch_start[b + 1]; ++i)
+            range_of_pos[i] = r;
 
       // vector partitioner: owned range + ghost nodes sorted by (current) global number
       auto part   = std::make_shared<Utilities::MPI::Partitioner>();
@@ -119,45 +138,28 @@ namespace dealii
                                                                      (std::uint64_t)g) - dh.rank_offset.begin()) - 1;
               ++imports[o];
             }
-          const unsigned int  p     = dh.get_fe().degree;
           const std::uint64_t first = dh.rank_offset[rank];
-          // my shared owned nodes sit on cells of the comm partition or on inner cells next to
-          // another rank; walk all local cells' nodes once and look at the up-to-8 touching cells
-          std::vector<unsigned char> seen; // per owned node
-          seen.assign(dh.rank_offset[rank + 1] - first, 0);
-          for (std::uint64_t c = c0; c < c1; ++c)
-            dh.for_each_cell_node(c, [&](std::uint64_t node, int, int, int) {
+          // my shared owned nodes and the other ranks among the (up to 8) cells touching them
+          for (std::uint64_t node = 0; node < dh.n_nodes; ++node)
+            {
               if (dh.owner[node] != rank || !dh.shared[node])
-                return;
+                continue;
               const std::uint32_t ln = dh.node_number[node] - (std::uint32_t)first;
-              if (seen[ln])
-                return;
-              seen[ln] = 1;
-              const std::uint64_t I = node % dh.nn[0], J = (node / dh.nn[0]) % dh.nn[1],
-                                  K = node / (dh.nn[0] * dh.nn[1]);
-              const std::uint64_t idx[3] = {I, J, K};
-              std::uint32_t       lo[3], hi[3];
-              for (int d = 0; d < 3; ++d)
+              std::uint64_t       cells[8];
+              const unsigned int  ncell = dh.incident_cells(node, cells);
+              unsigned int        ranks[8], nr = 0;
+              for (unsigned int q = 0; q < ncell; ++q)
                 {
-                  const std::uint32_t q = (std::uint32_t)(idx[d] / p);
-                  hi[d]                 = std::min<std::uint32_t>(q, tria.n_cells_dir[d] - 1);
-                  lo[d]                 = (idx[d] % p == 0 && q > 0) ? q - 1 : hi[d];
+                  const unsigned int r   = tria.subdomain_id(cells[q]);
+                  bool               dup = r == rank;
+                  for (unsigned int k = 0; k < nr; ++k)
+                    dup |= ranks[k] == r;
+                  if (!dup)
+                    ranks[nr++] = r;
                 }
-              unsigned int ranks[8], nr = 0;
-              for (std::uint32_t z = lo[2]; z <= hi[2]; ++z)
-                for (std::uint32_t y = lo[1]; y <= hi[1]; ++y)
-                  for (std::uint32_t x = lo[0]; x <= hi[0]; ++x)
-                    {
-                      const unsigned int r = tria.subdomain_id(tria.cell_index({{x, y, z}}));
-                      bool               dup = r == rank;
-                      for (unsigned int k = 0; k < nr; ++k)
-                        dup |= ranks[k] == r;
-                      if (!dup)
-                        ranks[nr++] = r;
-                    }
               for (unsigned int k = 0; k < nr; ++k)
                 exports[ranks[k]].push_back(ln);
-            });
+            }
           part->import_offset.assign(1, 0);
           part->export_offset.assign(1, 0);
           for (unsigned int r = 0; r < tria.n_ranks; ++r)
@@ -178,13 +180,10 @@ namespace dealii
       constrained_dofs.clear();
       {
         std::vector<std::uint32_t> nodes;
-        for (std::uint64_t c = c0; c < c1; ++c)
-          dh.for_each_cell_node(c, [&](std::uint64_t node, int, int, int) {
-            if (dh.owner[node] == rank && con.node_is_constrained(node))
-              nodes.push_back(dh.node_number[node]);
-          });
+        for (std::uint64_t node = 0; node < dh.n_nodes; ++node)
+          if (dh.owner[node] == rank && con.node_is_constrained(node))
+            nodes.push_back(dh.node_number[node]);
         std::sort(nodes.begin(), nodes.end());
-        nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
         const std::uint64_t first = dh.rank_offset[rank];
         for (const std::uint32_t n : nodes)
           for (unsigned int c = 0; c < 3; ++c)
@@ -208,6 +207,22 @@ namespace dealii
     unsigned int                     get_rank() const { return rank; }
     const AdditionalData            &get_additional_data() const { return data; }
 
+    // the local cells touching a lattice node, as positions in the loop order
+    unsigned int incident_positions(const std::uint64_t node, std::uint32_t (&pos)[8]) const
+    {
+      std::uint64_t      cells[8];
+      const unsigned int nc = dof_handler->incident_cells(node, cells);
+      unsigned int       n  = 0;
+      for (unsigned int k = 0; k < nc; ++k)
+        if (cells[k] >= first_cell && cells[k] - first_cell < cell_pos.size())
+          pos[n++] = cell_pos[cells[k] - first_cell];
+      return n;
+    }
+
+    std::uint64_t              first_cell = 0;
+    std::vector<std::uint32_t> cell_pos;     // loop position of local cell (active index - first_cell)
+    std::vector<std::uint32_t> batch_of_pos; // cell batch of every loop position
+    std::vector<std::uint32_t> range_of_pos; // cell-batch range of every loop position
     std::vector<std::uint64_t> cell_order;  // active-cell index per physical cell, loop order
     std::vector<unsigned int>  batch_start; // first physical cell of every batch (+ sentinel)
     unsigned int               n_q_points_1d = 0;

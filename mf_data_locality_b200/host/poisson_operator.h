@@ -218,32 +218,29 @@ namespace Poisson
       const unsigned int  n_ranges = (unsigned int)ti.cell_partition_data.size() - 1;
       if (n_ranges == 0)
         return;
-      std::vector<std::uint32_t> last_range(n_nodes, numbers::invalid_unsigned_int);
-      std::vector<unsigned char> count(n_nodes, 0);
-      for (unsigned int r = 0; r < n_ranges; ++r)
-        for (unsigned int b = ti.cell_partition_data[r]; b < ti.cell_partition_data[r + 1]; ++b)
-          for (unsigned int l = 0; l < data->n_active_entries_per_cell_batch(b); ++l)
-            dh.for_each_cell_node(data->get_cell(b, l), [&](const std::uint64_t node, int, int, int) {
-              if (dh.owner[node] != rank)
-                return;
-              const std::uint64_t i = dh.node_number[node] - first;
-              if (last_range[i] != r)
-                {
-                  last_range[i] = r;
-                  if (count[i] < 255)
-                    ++count[i];
-                }
-            });
+      // per owned node: the one range around it, or invalid if there are several / it is shared
+      // with another rank / Dirichlet (node by node from the lattice, in parallel)
+      std::vector<std::uint32_t> only_range(n_nodes, numbers::invalid_unsigned_int);
+      parallel_chunks(dh.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+        for (std::uint64_t n = a; n < b; ++n)
+          {
+            if (dh.owner[n] != rank || dh.shared[n] || constraints.node_is_constrained(n))
+              continue;
+            std::uint32_t      ps[8];
+            const unsigned int np = data->incident_positions(n, ps);
+            bool               one = np > 0;
+            for (unsigned int k = 1; k < np; ++k)
+              one &= data->range_of_pos[ps[k]] == data->range_of_pos[ps[0]];
+            if (one)
+              only_range[dh.node_number[n] - first] = data->range_of_pos[ps[0]];
+          }
+      });
       // private = one range, not shared with another rank, not Dirichlet
       std::vector<std::uint64_t> n_private(n_ranges, 0), lo(n_ranges, ~std::uint64_t(0)), hi(n_ranges, 0);
-      std::vector<unsigned char> is_private(n_nodes, 0);
-      for (std::uint64_t n = 0; n < dh.n_nodes; ++n)
-        if (dh.owner[n] == rank && !dh.shared[n] && !constraints.node_is_constrained(n))
+      for (std::uint64_t i = 0; i < n_nodes; ++i)
+        if (only_range[i] != numbers::invalid_unsigned_int)
           {
-            const std::uint64_t i = dh.node_number[n] - first;
-            if (count[i] != 1)
-              continue;
-            const std::uint32_t r = last_range[i];
+            const std::uint32_t r = only_range[i];
             ++n_private[r];
             lo[r] = std::min(lo[r], i);
             hi[r] = std::max(hi[r], i + 1);

@@ -21,6 +21,9 @@
 //    contiguous numbering", poisson_operator.h:198) -- in the reference as here; for p = 2
 //    (one node per entity) it is a valid input of the operator.
 #pragma once
+#include <chrono>
+#include <cstdlib>
+#include <iostream>
 #include <sstream>
 #include <thread>
 
@@ -46,14 +49,25 @@ public:
     std::vector<std::uint32_t> new_node_number(dof_handler.n_nodes);
     // the ranks' numberings are independent of each other: one host thread per rank
     auto renumber_rank = [&](const unsigned int rank) {
+        const bool show = std::getenv("BP4_SETUP_TIMING") != nullptr && rank == 0;
+        auto       t0   = std::chrono::steady_clock::now();
+        auto       lap  = [&](const char *what) {
+          const auto t1 = std::chrono::steady_clock::now();
+          if (show)
+            std::cerr << "    renumber: " << what << " " << std::chrono::duration<double>(t1 - t0).count() << " s\n";
+          t0 = t1;
+        };
         dealii::MatrixFree matrix_free;
         matrix_free.reinit(dof_handler, constraints, dof_handler.get_fe().degree + 1, mf_data, (int)rank);
+        lap("matrix_free.reinit");
         const std::uint64_t first = dof_handler.rank_offset[rank],
                             n_own = dof_handler.rank_offset[rank + 1] - first;
         // key[i] = position of owned node i in the matrix-free traversal
         std::vector<std::uint64_t> key = cell_assembly(matrix_free);
         AssertThrow(key.size() == n_own, "Expected " + std::to_string(n_own) + " nodes");
+        lap("cell_assembly");
         const std::vector<std::uint32_t> new_numbers = grouping(matrix_free, key);
+        lap("grouping");
         AssertThrow(new_numbers.size() == n_own, "Dimension mismatch " + std::to_string(new_numbers.size()) +
                                                    " vs " + std::to_string(n_own));
         // new_numbers[i] = old owned index that moves to position i (:139-144)
@@ -70,6 +84,7 @@ public:
       workers.emplace_back([&, rank] {
         try
           {
+            dealii::parallel_cap() = std::max(1u, 16u / n_ranks); // the rank workers share the cores
             renumber_rank(rank);
           }
         catch (const std::exception &e)
@@ -77,14 +92,17 @@ public:
             errors[rank] = e.what();
           }
       });
+    const unsigned int cap_before = dealii::parallel_cap();
     try
       {
+        dealii::parallel_cap() = std::max(1u, 16u / n_ranks);
         renumber_rank(0);
       }
     catch (const std::exception &e)
       {
         errors[0] = e.what();
       }
+    dealii::parallel_cap() = cap_before;
     for (auto &w : workers)
       w.join();
     for (const auto &e : errors)
@@ -170,6 +188,58 @@ private:
     constexpr std::uint64_t   unset = ~std::uint64_t(0);
     std::vector<std::uint64_t> key(n_own, unset);
     std::uint64_t              counter = 0;
+    if (assembly_strat == 0 && renumber_strat == 1)
+      {
+        // First touch, cell by cell, without the sequential sweep: a node is numbered by the
+        // FIRST cell of the loop that holds it (the smallest loop position among the up to 8
+        // cells around it), and inside that cell in the order of the object walk.  So: cells
+        // count the owned nodes they are first for (parallel), a prefix sum over the loop
+        // order gives every cell its first key, and a second parallel pass hands the keys out.
+        const std::uint32_t        n_cells = mf.n_physical_cells();
+        std::vector<std::uint64_t> first_key(n_cells + 1, 0);
+        std::vector<std::uint32_t> first_pos(n_own, 0xFFFFFFFFu); // loop position of the first cell
+        dealii::parallel_chunks(dh.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t node = a; node < b; ++node)
+            {
+              if (dh.owner[node] != rank)
+                continue;
+              std::uint32_t      ps[8];
+              const unsigned int n  = mf.incident_positions(node, ps);
+              std::uint32_t      lo = 0xFFFFFFFFu;
+              for (unsigned int k = 0; k < n; ++k)
+                lo = std::min(lo, ps[k]);
+              first_pos[dh.node_number[node] - first] = lo;
+            }
+        });
+        auto for_first_nodes = [&](const std::uint32_t pos, auto &&f) {
+          walk_cell_objects(dh, mf.cell_order[pos], [&](const std::uint64_t node, unsigned int) {
+            if (dh.owner[node] == rank && first_pos[dh.node_number[node] - first] == pos)
+              f(node);
+          });
+        };
+        dealii::parallel_chunks(n_cells, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t pos = a; pos < b; ++pos)
+            {
+              std::uint64_t cnt = 0;
+              for_first_nodes((std::uint32_t)pos, [&](std::uint64_t) { ++cnt; });
+              first_key[pos + 1] = cnt;
+            }
+        });
+        for (std::uint32_t pos = 0; pos < n_cells; ++pos)
+          first_key[pos + 1] += first_key[pos];
+        dealii::parallel_chunks(n_cells, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t pos = a; pos < b; ++pos)
+            {
+              std::uint64_t k = first_key[pos];
+              for_first_nodes((std::uint32_t)pos, [&](const std::uint64_t node) {
+                key[dh.node_number[node] - first] = k++;
+              });
+            }
+        });
+        for (const std::uint64_t k : key)
+          AssertThrow(k != unset, "owned node never touched by a local cell");
+        return key;
+      }
     auto touch = [&](const std::uint64_t node) {
       if (dh.owner[node] != rank)
         return;
@@ -206,31 +276,30 @@ private:
     const dealii::DoFHandler &dh    = mf.get_dof_handler();
     const unsigned int        rank  = mf.get_rank();
     const std::uint64_t       first = dh.rank_offset[rank], n_own = dh.rank_offset[rank + 1] - first;
-    std::vector<unsigned char> count(n_own, 0);
-    std::vector<std::uint32_t> last_group(n_own, 0xFFFFFFFFu);
-    const auto                &ti      = mf.get_task_info();
-    std::uint32_t              group   = 0;
-    auto                       visit_batch = [&](const unsigned int b) {
-      for (unsigned int l = 0; l < mf.n_active_entries_per_cell_batch(b); ++l)
-        dh.for_each_cell_node(mf.get_cell(b, l), [&](const std::uint64_t node, int, int, int) {
+    // per node: the distinct groups (cell batches or cell-batch ranges) among the local cells
+    // around it -- the same count the sweep over the loop produces, node by node in parallel
+    std::vector<unsigned char>        count(n_own, 0);
+    const std::vector<std::uint32_t> &group_of_pos = by_range ? mf.range_of_pos : mf.batch_of_pos;
+    dealii::parallel_chunks(dh.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+      for (std::uint64_t node = a; node < b; ++node)
+        {
           if (dh.owner[node] != rank || mf.get_constraints().node_is_constrained(node))
-            return;
-          const std::uint64_t i = dh.node_number[node] - first;
-          if (last_group[i] != group)
+            continue;
+          std::uint32_t      ps[8], seen[8];
+          const unsigned int n = mf.incident_positions(node, ps);
+          unsigned int       c = 0;
+          for (unsigned int k = 0; k < n; ++k)
             {
-              last_group[i] = group;
-              ++count[i];
+              const std::uint32_t g   = group_of_pos[ps[k]];
+              bool                dup = false;
+              for (unsigned int q = 0; q < c; ++q)
+                dup |= seen[q] == g;
+              if (!dup)
+                seen[c++] = g;
             }
-        });
-    };
-    if (by_range)
-      for (unsigned int part = 0; part + 2 < ti.partition_row_index.size(); ++part)
-        for (unsigned int r = ti.partition_row_index[part]; r < ti.partition_row_index[part + 1]; ++r, ++group)
-          for (unsigned int b = ti.cell_partition_data[r]; b < ti.cell_partition_data[r + 1]; ++b)
-            visit_batch(b);
-    else
-      for (unsigned int b = 0; b < mf.n_cell_batches(); ++b, ++group)
-        visit_batch(b);
+          count[dh.node_number[node] - first] = (unsigned char)c;
+        }
+    });
     return count;
   }
 
