@@ -580,6 +580,7 @@ int bp4_vec_set_zero(bp4_ctx *c, bp4_vec *v)
 {
   if (!c || !v)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(v->p(), 0, sizeof(double) * v->n, c->stream));
   return 0;
 }
@@ -588,6 +589,7 @@ int bp4_vec_upload(bp4_ctx *c, bp4_vec *v, const double *host, uint64_t n)
 {
   if (!c || !v || (!host && n))
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   if (n > v->n)
     return fail(BP4_ERR_ARG, "upload of %llu > vector size %llu", (unsigned long long)n,
                 (unsigned long long)v->n);
@@ -599,6 +601,7 @@ int bp4_vec_download(bp4_ctx *c, const bp4_vec *v, double *host, uint64_t n)
 {
   if (!c || !v || (!host && n))
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   if (n > v->n)
     return fail(BP4_ERR_ARG, "download of %llu > vector size %llu", (unsigned long long)n,
                 (unsigned long long)v->n);
@@ -846,6 +849,7 @@ int bp4_inverse_diagonal(bp4_ctx *c, bp4_vec *out)
 {
   if (!c || !out)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   if (out->n < c->n_owned / 3)
     return fail(BP4_ERR_ARG, "diagonal vector needs n_owned/3 entries");
   // assemble DoF-wise into slot 3*node of a local vector so that the ordinary ghost
@@ -1297,6 +1301,7 @@ int bp4_update_ghost_values(bp4_ctx *c, bp4_vec *v)
 {
   if (!c || !v)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   if (c->peer.empty())
     return 0;
   if (!c->comm)
@@ -1313,6 +1318,7 @@ int bp4_compress_add(bp4_ctx *c, bp4_vec *v)
 {
   if (!c || !v)
     return fail(BP4_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
   if (c->peer.empty())
     return 0;
   if (!c->comm)
