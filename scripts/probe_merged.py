@@ -41,8 +41,8 @@ print(f"  vmult : wall {wall*1e3:.3f} ms, cell kernel {ms/cnt:.3f} ms -> {n/(ms/
 ctx.profile_enable(False)
 
 prec = ctx.inverse_diagonal()
-for mode in ([True, False] if fused else [False]):
-    if fused:
+for mode in ([True, False] if n_priv > 0 else [False]):
+    if n_priv > 0:
         ctx.set_fused(mode)
     x, g, d, h = ctx.vector(), ctx.vector(), ctx.vector(), ctx.vector()
     ctx.equ(g, -1.0, src)
