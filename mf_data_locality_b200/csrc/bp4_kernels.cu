@@ -43,7 +43,7 @@ namespace bp4
   template <int P, int CPB, int NC>
   __device__ __forceinline__ void load_tables(CellSmem<P, CPB, NC> &sm, const uint32_t *dtab)
   {
-    for (int i = threadIdx.x; i < Geom<P>::DOF; i += kThreads)
+    for (int i = threadIdx.x; i < Geom<P>::DOF; i += blockDim.x)
       sm.dtab[i] = dtab[i];
     if (threadIdx.x < Geom<P>::Q)
       {
@@ -157,9 +157,10 @@ namespace bp4
   // pre_kernel / post_kernel stream them before / after this kernel.
   // ---------------------------------------------------------------------------------------
   template <int P, int CPB, bool FUSED, bool QUAD>
-  __global__ void __launch_bounds__(kThreads, Cfg<P>::BLOCKS) cell_kernel(const CellArgs a)
+  __global__ void __launch_bounds__(Cfg<P>::THREADS, Cfg<P>::BLOCKS) cell_kernel(const CellArgs a)
   {
     constexpr int NC = Cfg<P, QUAD>::NCOEF;
+    constexpr int kThreads = Cfg<P>::THREADS; // shadows the namespace default inside this kernel
     using G         = Geom<P>;
     constexpr int Q = G::Q;
     // high degrees: phases 1 and 3 as one sweep per 1-D contraction (see phase1a)
@@ -1014,11 +1015,11 @@ namespace bp4
     cudaMemcpyToSymbolAsync(g_trace, &d_trace, sizeof(d_trace), 0, cudaMemcpyHostToDevice, st);
 #endif
     if (fused)
-      cell_kernel<P, CPB, true, false><<<grid, kThreads, sizeof(CellSmem<P, CPB, 24>), st>>>(a);
+      cell_kernel<P, CPB, true, false><<<grid, Cfg<P>::THREADS, sizeof(CellSmem<P, CPB, 24>), st>>>(a);
     else if (quad)
-      cell_kernel<P, CPBQ, false, true><<<grid, kThreads, sizeof(CellSmem<P, CPBQ, 81>), st>>>(a);
+      cell_kernel<P, CPBQ, false, true><<<grid, Cfg<P>::THREADS, sizeof(CellSmem<P, CPBQ, 81>), st>>>(a);
     else
-      cell_kernel<P, CPB, false, false><<<grid, kThreads, sizeof(CellSmem<P, CPB, 24>), st>>>(a);
+      cell_kernel<P, CPB, false, false><<<grid, Cfg<P>::THREADS, sizeof(CellSmem<P, CPB, 24>), st>>>(a);
 #ifdef BP4_PHASE_TIMING
     if (d_trace)
       {
@@ -1045,7 +1046,7 @@ namespace bp4
           tot += double(h[k]);
         fprintf(stderr, "phase clk share: meta %.1f%% gather %.1f%% barrier %.1f%% P1 %.1f%% P2 %.1f%% P3 %.1f%% scatter %.1f%% post %.1f%% | per-warp total %.0f clk\n",
                 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot,
-                100 * h[5] / tot, 100 * h[6] / tot, 100 * h[7] / tot, tot / (grid * (kThreads / 32)));
+                100 * h[5] / tot, 100 * h[6] / tot, 100 * h[7] / tot, tot / (grid * (Cfg<P>::THREADS / 32)));
       }
 #endif
     return cudaGetLastError();

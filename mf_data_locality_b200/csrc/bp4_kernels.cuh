@@ -16,6 +16,9 @@ namespace bp4
   // may use up to 255 registers per thread (phase 2 keeps 9*Q doubles live), and while one
   // block waits on its gather or a barrier the other keeps the FP64 pipe busy.
   constexpr int kThreads     = 128;
+#ifndef BP4_WIDE
+#  define BP4_WIDE(P) false
+#endif
   constexpr int kBlocksPerSM = 2;
 
   // QUAD: all 27 geometry coefficients per cell (81 doubles) instead of the 8 tri-linear ones (24)
@@ -24,15 +27,20 @@ namespace bp4
   {
     using G = Geom<P>;
     static constexpr int NCOEF = QUAD ? 81 : 24;
+    // "wide" configuration: ONE block of 256 threads per SM (255 registers, no spills) whose
+    // batch fills phase 2 exactly (Q6: 4 cells = 256 lines, Q7: 3 cells = 243 lines)
+    static constexpr bool WIDE    = BP4_WIDE(P);
+    static constexpr int  THREADS = WIDE ? 256 : kThreads;
     // resident blocks per SM of the cell kernel: three (<= 168 registers, smaller batches)
     // measured faster at Q2 (+12 %) and Q6 (+13 %), slower or equal elsewhere
-    static constexpr int BLOCKS   = (P == 2 || P == 6) ? 3 : kBlocksPerSM;
+    static constexpr int BLOCKS   = WIDE ? 1 : ((P == 2 || P == 6) ? 3 : kBlocksPerSM);
     static constexpr int budget   = (227 * 1024) / BLOCKS - 512;
     static constexpr int per_cell = (G::WORK + 2 * NCOEF) * 8 + 2 * 28 * 4;
     static constexpr int fit      = (budget - 4 * G::DOF - 16 * G::Q - 256) / per_cell;
     // phase 2 carries ~2/3 of the FP64 work: prefer Q^2*CPB close to a multiple of the block
-    static constexpr int want = (2 * kThreads) / (G::Q * G::Q) > 0 ? (2 * kThreads) / (G::Q * G::Q) : 1;
-    static constexpr int CPB  = fit < 1 ? 1 : (fit < want ? fit : want);
+    static constexpr int rounds = WIDE ? 1 : 2;
+    static constexpr int want   = (rounds * THREADS) / (G::Q * G::Q) > 0 ? (rounds * THREADS) / (G::Q * G::Q) : 1;
+    static constexpr int CPB    = fit < 1 ? 1 : (fit < want ? fit : want);
   };
 
   template <int P, int CPB, int NCOEF = 24>
