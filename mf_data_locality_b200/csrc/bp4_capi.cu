@@ -273,6 +273,8 @@ static void build_units(const std::vector<uint32_t> &range_cell, const std::vect
       size_t re = r + 1;
       while (re < r1 && range_cell[re] - range_cell[r] < target)
         ++re;
+      if (range_cell[r1] - range_cell[re] < target / 2) // a short remainder joins the last unit
+        re = r1;
       unit_batch.push_back((uint32_t)batches.size());
       const uint32_t uc0 = range_cell[r], uc1 = range_cell[re];
       for (uint32_t cb = uc0; cb < uc1; cb += cpb)
@@ -425,6 +427,11 @@ static int ctx_create_impl(const bp4_desc *d, bp4_ctx *c)
       CU(cudaMemcpy(c->d_unit_batch, unit_batch.data(), sizeof(uint32_t) * unit_batch.size(),
                     cudaMemcpyHostToDevice));
       c->n_private = c->n_coef == 24 ? rp[d->n_ranges] : 0; // in-loop updates: tri-linear kernel only
+      // the staged fused loop takes a batch's private run in two jobs of its shared-memory rows
+      const uint32_t limit = bp4::fused_run_limit(d->degree); // 0: no fused kernel at this degree
+      for (const bp4::BatchDesc &b : batches)
+        if (b.pre_end - b.pre_begin > limit || b.post_end - b.post_begin > limit)
+          c->n_private = 0; // the updates of every DoF are streamed then
       c->fused     = BP4_FUSED_DEFAULT && c->n_private > 0;
       if (const char *e = getenv("BP4_FUSED")) // developer knob: 0 = pre kernel + cells + post kernel
         c->fused = c->n_private > 0 && atoi(e) != 0;
@@ -670,7 +677,8 @@ static int cell_range(bp4_ctx *c, double *dst, const double *src, int part, cons
   a.src   = src;
   a.dst   = dst;
   a.sched = c->d_sched + (part < 0 ? 0 : part);
-  a.stagger_ns = c->stagger_ns;
+  a.stagger_ns  = c->stagger_ns;
+  a.claim_depth = 5;
   if (m)
     {
       const uint32_t u0 = part < 0 ? c->unit_part[0] : c->unit_part[part],
@@ -792,7 +800,9 @@ int bp4_debug_set_fused(bp4_ctx *c, int on)
   if (!c)
     return fail(BP4_ERR_ARG, "null ctx");
   if (on && c->n_private == 0)
-    return fail(BP4_ERR_STATE, "no private DoF runs: the context was created without range tables");
+    return fail(BP4_ERR_STATE, "no private DoF runs: the context was created without range tables, with "
+                               "quadratic geometry, at a degree without a fused kernel (> 4), or with runs "
+                               "too long for its staging rows");
   c->fused = on != 0;
   return 0;
 }

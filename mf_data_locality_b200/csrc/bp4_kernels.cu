@@ -20,9 +20,6 @@
 #ifndef BP4_FINE_FROM
 #  define BP4_FINE_FROM 6
 #endif
-#ifndef BP4_KU
-#  define BP4_KU 4 // DoFs per thread and sweep of the in-loop do_cg_update4b / 3b
-#endif
 #ifndef BP4_DYNAMIC
 // batches / units are claimed from an atomic counter instead of strided.  Measured on B200 (operator
 // apply at ~50-100 M DoFs): Q2 +13 %, Q3 +5 %, Q4 +8 %, Q5 +11 %; Q6 -6 %, Q7 -11 %, Q8 -10 % (the
@@ -31,9 +28,6 @@
 #endif
 #ifndef BP4_POST_UNROLL
 #  define BP4_POST_UNROLL 4 // measured: 1 -> 0.233 ms, 4 -> 0.211 ms (6.45 TB/s), 2 and 8 slower (Q4 s=18)
-#endif
-#ifndef BP4_L2_PREFETCH
-#  define BP4_L2_PREFETCH 1 // bulk L2 prefetch of the next-but-one batch's private DoFs
 #endif
 
 namespace bp4
@@ -67,6 +61,9 @@ namespace bp4
   // per-block timeline of the first kTraceBatches batches (BP4_TRACE=<file>): globaltimer at the
   // top of the batch, after phase 3, after the scatter, at the end of the memory window; + SM id
   constexpr int kTraceBatches = 48;
+#  ifndef BP4_TRACE_TID
+#    define BP4_TRACE_TID 0
+#  endif
   __device__ unsigned long long *g_trace;
   __device__ __forceinline__ unsigned long long gtime()
   {
@@ -81,8 +78,8 @@ namespace bp4
     return r;
   }
 #  define BP4_TRACE(i, k)                                                                     \
-    if (g_trace && threadIdx.x == 0 && (i) < kTraceBatches)                                   \
-      g_trace[((size_t)blockIdx.x * kTraceBatches + (i)) * 5 + (k)] = (k) == 4 ? smid() : gtime();
+    if (g_trace && threadIdx.x == BP4_TRACE_TID && (i) < kTraceBatches)                                   \
+      g_trace[((size_t)blockIdx.x * kTraceBatches + (i)) * 20 + (k)] = (k) == 4 ? smid() : gtime();
 #else
 #  define BP4_TICK_INIT
 #  define BP4_TICK(k)
@@ -127,14 +124,35 @@ namespace bp4
   // i / 3 for 32-bit i without an integer division
   __device__ __forceinline__ uint32_t div3(const uint32_t i) { return __umulhi(i, 0xAAAAAAABu) >> 1; }
 
-  // TMA-unit prefetch of [p, p + bytes) into L2; no register, no scoreboard, no completion
-  __device__ __forceinline__ void l2_prefetch_span(const double *v, const uint32_t begin, const uint32_t end)
+  // ---- mbarrier / asynchronous-copy wrappers (PTX ISA: mbarrier, cp.async) ----
+  __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+  __device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count)
   {
-    if (end <= begin)
-      return;
-    const uint64_t lo = (uint64_t)(v + begin) & ~uint64_t(15);
-    const uint32_t bytes = (uint32_t)((((uint64_t)(v + end) + 15) & ~uint64_t(15)) - lo);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"(bytes) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t parity)
+  {
+    asm volatile("{\n\t.reg .pred p;\n"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n\t}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+  }
+  __device__ __forceinline__ void cp_async16(const uint32_t smem_dst, const void *gmem_src)
+  {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+  }
+  __device__ __forceinline__ void cp_async8(const uint32_t smem_dst, const void *gmem_src)
+  {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+  }
+  __device__ __forceinline__ void cp_async4(const uint32_t smem_dst, const void *gmem_src)
+  {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
   }
 
   // ---------------------------------------------------------------------------------------
@@ -174,7 +192,6 @@ namespace bp4
     const Tab<P>         &tb  = c_tab<P>;
     load_tables<P, CPB, NC>(sm, a.dtab);
     BP4_TICK_INIT
-
     // ---- work list of this block: a unit is one batch (plain) or the batches
     // [unit_batch[u], unit_batch[u+1]) of whole ranges (fused).  Units are claimed dynamically
     // (BP4_DYNAMIC): the first one is blockIdx.x, the following ones come from an atomic counter,
@@ -191,9 +208,10 @@ namespace bp4
     auto           unit_at = [&](const uint32_t j) {
       return dynamic ? sm.units[j & 7u] : blockIdx.x + j * gridDim.x;
     };
-    auto claim_ahead = [&](const uint32_t j_cur) { // thread 0 only; visible after the next barrier
+    // thread 0 only; visible after the next barrier
+    auto claim_ahead = [&](const uint32_t j_from, const uint32_t depth) {
       if (dynamic)
-        while (sm.n_claimed < j_cur + 5u)
+        while (sm.n_claimed < j_from + depth)
           {
             sm.units[sm.n_claimed & 7u] = gridDim.x + atomicAdd(a.sched, 1u);
             ++sm.n_claimed;
@@ -221,26 +239,15 @@ namespace bp4
         }
       return it;
     };
-    struct Batch
+    struct Batch // plain kernel: cut on the fly
     {
       uint32_t cell0;
       int      nc;
-      uint32_t pre_b, pre_e, post_b, post_e;
     };
     auto describe = [&](const It &it) {
       Batch d;
-      if (FUSED)
-        {
-          const uint4 w0 = __ldg(reinterpret_cast<const uint4 *>(a.batch + it.b));
-          const uint4 w1 = __ldg(reinterpret_cast<const uint4 *>(a.batch + it.b) + 1);
-          d.cell0 = w0.x, d.nc = (int)w0.y, d.pre_b = w0.z, d.pre_e = w0.w, d.post_b = w1.x, d.post_e = w1.y;
-        }
-      else
-        {
-          d.cell0 = it.u * CPB;
-          d.nc    = (int)min((uint64_t)CPB, a.n_cells - (uint64_t)d.cell0);
-          d.pre_b = d.pre_e = d.post_b = d.post_e = 0;
-        }
+      d.cell0 = it.u * CPB;
+      d.nc    = (int)min((uint64_t)CPB, a.n_cells - (uint64_t)d.cell0);
       return d;
     };
 
@@ -248,18 +255,18 @@ namespace bp4
     constexpr int ME = (CPB * 27 + kThreads - 1) / kThreads, MC = (CPB * NC + kThreads - 1) / kThreads;
     uint32_t      me[ME];
     double        mc[MC];
-    auto          fetch_meta = [&](const Batch &d) {
+    auto          fetch_meta = [&](const uint32_t cell0, const int nc) {
 #pragma unroll
       for (int u = 0; u < ME; ++u)
         {
           const int k = tid + u * kThreads;
-          me[u]       = k < d.nc * 27 ? __ldg(a.entity_index + (uint64_t)d.cell0 * 27 + k) : 0xFFFFFFFFu;
+          me[u]       = k < nc * 27 ? __ldg(a.entity_index + (uint64_t)cell0 * 27 + k) : 0xFFFFFFFFu;
         }
 #pragma unroll
       for (int u = 0; u < MC; ++u)
         {
           const int k = tid + u * kThreads;
-          mc[u]       = k < d.nc * NC ? __ldg(a.coef + (uint64_t)d.cell0 * NC + k) : 0.;
+          mc[u]       = k < nc * NC ? __ldg(a.coef + (uint64_t)cell0 * NC + k) : 0.;
         }
     };
     auto park_meta = [&](const int bf) {
@@ -278,6 +285,26 @@ namespace bp4
             sm.coef[bf][k / NC][k % NC] = mc[u];
         }
     };
+    // fused: the same items go from global to shared memory asynchronously (no registers held
+    // over the phases); they count towards the next mbarrier arrival of this thread
+    auto meta_async = [&](const int bf, const uint32_t cell0, const int nc) {
+#pragma unroll
+      for (int u = 0; u < ME; ++u)
+        {
+          const int k = tid + u * kThreads;
+          if (k < nc * 27)
+            cp_async4(smem_u32(&sm.eidx[bf][k / 27][k % 27]), a.entity_index + (uint64_t)cell0 * 27 + k);
+          else if (k < CPB * 27)
+            sm.eidx[bf][k / 27][k % 27] = 0xFFFFFFFFu;
+        }
+#pragma unroll
+      for (int u = 0; u < MC; ++u)
+        {
+          const int k = tid + u * kThreads;
+          if (k < nc * NC)
+            cp_async8(smem_u32(&sm.coef[bf][k / NC][k % NC]), a.coef + (uint64_t)cell0 * NC + k);
+        }
+    };
 
     // gather (vector_access_reduced.h:175-258): consecutive threads walk an entity's contiguous
     // DoF segment.  Thread tid owns elements tid + r * kThreads of EVERY cell of the batch, so the
@@ -287,8 +314,9 @@ namespace bp4
     // With kPipe the gather is software-pipelined: the loads of batch i+1 are issued
     // (gather_issue) right after the scatter of batch i and land in registers while the block
     // does other memory work; they are stored to the work rows (gather_store) afterwards.
-    // The fused kernel reads the direction through L2 (ld.cg): it was written by this block's
-    // own do_cg_update4b moments ago.
+    // The fused kernel reads the direction with plain loads, not ld.global.nc: it was written by
+    // this block's own do_cg_update4b moments ago (the L1 sees the stores of its own SM, every
+    // other DoF the block reads is constant during the kernel).
     constexpr bool kPipe = BP4_PIPE_GATHER(P);
     constexpr int R = (G::DOF + kThreads - 1) / kThreads, S = CPB * R;
     // only the last r can run past the end of the cell
@@ -309,7 +337,7 @@ namespace bp4
         }
 #pragma unroll
       for (int s1 = 0; s1 < S; ++s1)
-        gv[s1] = idx[s1] != 0xFFFFFFFFu ? (FUSED ? __ldcg(a.src + idx[s1]) : __ldg(a.src + idx[s1])) : 0.;
+        gv[s1] = idx[s1] != 0xFFFFFFFFu ? (FUSED ? a.src[idx[s1]] : __ldg(a.src + idx[s1])) : 0.;
     };
     auto gather_store = [&]() {
       uint32_t tt[R];
@@ -324,118 +352,104 @@ namespace bp4
             sm.work[cell * G::WORK + dtab_off_work<P>(tt[r])] = gv[s1];
         }
     };
-
-    // do_cg_update4b<3,double,true> (solver_cg_optimized.h:65-161) on the private run [pb, pe).
-    // The first sweep (KU entries per thread) is split into issue / finish so that its loads
-    // are in flight together with the gather's while the scatter goes out.
-    constexpr int KU = BP4_KU;
-    struct Sweep
-    {
-      double pr[KU], rr[KU], pp[KU], hh[KU], xx[KU];
-    };
-    auto pre_load = [&](Sweep &w, const uint32_t base, const uint32_t pe) {
+    // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13) is touched by
+    // this cell only -> plain store
+    auto scatter = [&](const int bf) {
+      constexpr int SU = BP4_SU;
+      uint32_t      tt[R];
 #pragma unroll
-      for (int k = 0; k < KU; ++k)
+      for (int r = 0; r < R; ++r)
+        tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
+#pragma unroll
+      for (int s0 = 0; s0 < S; s0 += SU)
         {
-          const uint32_t i  = base + k * kThreads;
-          const bool     ok = i < pe;
-          w.pr[k] = ok ? __ldg(a.prec + div3(i)) : 0.;
-          w.rr[k] = ok ? __ldcg(a.r + i) : 0.;
-          w.pp[k] = (ok && !a.first) ? __ldcg(a.p + i) : 0.;
-          w.hh[k] = (ok && !a.first) ? __ldcg(a.dst + i) : 0.;
-          w.xx[k] = (ok && a.update_x) ? __ldcg(a.x + i) : 0.;
+          double   v[SU];
+          uint32_t adr[SU];
+#pragma unroll
+          for (int u = 0; u < SU; ++u)
+            if (s0 + u < S)
+              {
+                const int      cell = (s0 + u) / R, r = (s0 + u) % R;
+                const uint32_t base = sm.eidx[bf][cell][dtab_ent(tt[r])];
+                adr[u] = on(r) && base != 0xFFFFFFFFu ? base + dtab_rel(tt[r]) : 0xFFFFFFFFu;
+                v[u]   = sm.work[cell * G::WORK + dtab_off_work<P>(tt[r])];
+              }
+#pragma unroll
+          for (int u = 0; u < SU; ++u)
+            if (s0 + u < S && adr[u] != 0xFFFFFFFFu)
+              {
+                if (dtab_ent(tt[(s0 + u) % R]) == 13u)
+                  a.dst[adr[u]] = v[u];
+                else
+                  atomicAdd(a.dst + adr[u], v[u]);
+              }
         }
     };
-    auto pre_store = [&](const Sweep &w, const uint32_t base, const uint32_t pe) {
-#pragma unroll
-      for (int k = 0; k < KU; ++k)
+    // the three compute phases on the nc cells in the work rows; `between` runs at the end of
+    // phase 1 and of phase 2 (before the barrier that closes them) and right after those barriers
+    auto phase_1 = [&](const int nc) {
+      // phase 1/3 items are handed out from the LAST thread downwards: the ragged final round
+      // of phase 2 lands on the first warps, so the two kinds of partial rounds end up on
+      // different warps (= different SM sub-partitions) instead of piling up on warp 0
+      if (!kFine)
         {
-          const uint32_t i = base + k * kThreads;
-          if (i < pe)
-            {
-              if (a.first)
-                a.p[i] = -w.pr[k] * w.rr[k];
-              else
-                {
-                  if (a.update_x)
-                    a.x[i] = w.xx[k] + (a.c1 * w.pp[k] + a.c2 * w.pr[k] * w.rr[k]);
-                  const double rn = w.rr[k] + a.alpha * w.hh[k];
-                  a.r[i]          = rn;
-                  a.p[i]          = a.beta * w.pp[k] - w.pr[k] * rn;
-                }
-              a.dst[i] = 0.;
-            }
+          for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
+            phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
+        }
+      else
+        {
+          // one 1-D line per item, consecutive lanes on consecutive rows (odd row stride:
+          // no bank conflicts); see phase1a
+          const int n_rows = nc * G::ITEMS13;
+          for (int it = tid; it < n_rows * G::N; it += kThreads)
+            phase1a<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
+          __syncthreads();
+          for (int it = tid; it < n_rows * Q; it += kThreads)
+            phase1b<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
+          __syncthreads();
+          for (int it = tid; it < n_rows * Q; it += kThreads)
+            phase1c<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
         }
     };
-    // everything after the first sweep (or all of it when `from_first`)
-    auto pre_rest = [&](const uint32_t pb, const uint32_t pe, const bool from_first) {
-      for (uint32_t base = pb + tid + (from_first ? 0 : KU * kThreads); base < pe; base += KU * kThreads)
+    auto phase_2 = [&](const int nc, const int bf) {
+      for (int it = tid; it < nc * G::ITEMS2; it += kThreads)
         {
-          Sweep w;
-          pre_load(w, base, pe);
-          pre_store(w, base, pe);
+          const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
+          const int qz = r / Q, qx = r % Q;
+          if constexpr (P >= BP4_P2_CALL_FROM)
+            phase2_call<P, QUAD>((uint32_t)((const unsigned char *)sm.coef[bf][cell] - smem_raw),
+                                 (uint32_t)((const unsigned char *)(sm.work + cell * G::WORK) - smem_raw), qx, qz,
+                                 sm.xq[qx], sm.xq[qz], sm.wq[qx] * sm.wq[qz]);
+          else
+            phase2<P, QUAD>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
+                            sm.wq[qx] * sm.wq[qz]);
         }
     };
-    // do_cg_update3b<3,double> (solver_cg_optimized.h:12-61) on the private run [pb, pe)
-    auto post_load = [&](Sweep &w, const uint32_t base, const uint32_t pe) {
-#pragma unroll
-      for (int k = 0; k < KU; ++k)
+    auto phase_3 = [&](const int nc) {
+      if (!kFine)
         {
-          const uint32_t i  = base + k * kThreads;
-          const bool     ok = i < pe;
-          w.pr[k] = ok ? __ldg(a.prec + div3(i)) : 0.;
-          w.rr[k] = ok ? __ldcg(a.r + i) : 0.;
-          w.pp[k] = ok ? __ldcg(a.p + i) : 0.;
-          w.hh[k] = ok ? __ldcg(a.dst + i) : 0.;
+          for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
+            phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
         }
-    };
-    auto post_finish = [&](const Sweep &first, const uint32_t pb, const uint32_t pe, const bool have_first) {
-      if (pe <= pb)
-        return;
-      double s[7] = {0., 0., 0., 0., 0., 0., 0.};
-      if (have_first)
-#pragma unroll
-        for (int k = 0; k < KU; ++k)
-          post_terms(s, first.rr[k], first.pp[k], first.hh[k], first.pr[k]);
-      for (uint32_t base = pb + tid + (have_first ? KU * kThreads : 0); base < pe; base += KU * kThreads)
+      else
         {
-          Sweep w;
-          post_load(w, base, pe);
-#pragma unroll
-          for (int k = 0; k < KU; ++k)
-            post_terms(s, w.rr[k], w.pp[k], w.hh[k], w.pr[k]);
-        }
-#pragma unroll
-      for (int k = 0; k < 7; ++k)
-        {
-          s[k] = warp_sum(s[k]);
-          if ((tid & 31) == 0)
-            atomicAdd(&sm.red[k], s[k]);
-        }
-    };
-    auto prefetch_pre = [&](const Batch &d) {
-      if (BP4_L2_PREFETCH && tid < 5)
-        {
-          if (tid == 0)
-            l2_prefetch_span(a.r, d.pre_b, d.pre_e);
-          else if (tid == 1 && !a.first)
-            l2_prefetch_span(a.p, d.pre_b, d.pre_e);
-          else if (tid == 2 && !a.first)
-            l2_prefetch_span(a.dst, d.pre_b, d.pre_e);
-          else if (tid == 3 && a.update_x)
-            l2_prefetch_span(a.x, d.pre_b, d.pre_e);
-          else if (tid == 4)
-            l2_prefetch_span(a.prec, div3(d.pre_b), div3(d.pre_e));
+          const int n_rows = nc * G::ITEMS13;
+          for (int it = tid; it < n_rows * Q; it += kThreads)
+            phase3a<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
+          __syncthreads();
+          for (int it = tid; it < n_rows * Q; it += kThreads)
+            phase3b<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
+          __syncthreads();
+          for (int it = tid; it < n_rows * G::N; it += kThreads)
+            phase3c<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
         }
     };
 
-    // cur = the batch in the work rows, nxt = the one being gathered, nn = the one whose private
-    // runs get their pre-update now (two batches ahead of their gather), n3 = L2 prefetch
     if (tid == 0)
       {
         sm.units[0]  = blockIdx.x;
         sm.n_claimed = 1;
-        claim_ahead(0);
+        claim_ahead(0, 5);
       }
     // All blocks start together and do the same amount of work per batch, so without help they
     // reach their memory windows together: HBM sees bursts and idles in between (trace:
@@ -444,214 +458,399 @@ namespace bp4
     if (a.stagger_ns)
       __nanosleep((unsigned)(((unsigned long long)(blockIdx.x * 2654435761u) * a.stagger_ns) >> 32));
     __syncthreads();
-    It cur_it;
-    cur_it.j = 0, cur_it.b = cur_it.b_end = 0;
-    enter(cur_it);
-    Batch cur{}, nxt{}, nn{};
-    It    nxt_it = cur_it, nn_it = cur_it;
-    if (cur_it.valid)
-      {
-        cur = describe(cur_it);
-        fetch_meta(cur);
-        park_meta(0);
-        nxt_it = advance(cur_it);
-        nn_it  = nxt_it;
-        if (nxt_it.valid)
-          {
-            nxt   = describe(nxt_it);
-            nn_it = advance(nxt_it);
-            if (nn_it.valid)
-              nn = describe(nn_it);
-          }
-        if (FUSED)
-          {
-            pre_rest(cur.pre_b, cur.pre_e, true);
-            if (nxt_it.valid)
-              pre_rest(nxt.pre_b, nxt.pre_e, true);
-            if (nn_it.valid)
-              prefetch_pre(nn);
-          }
-      }
-    __syncthreads();
-    if (kPipe && cur_it.valid)
-      {
-        gather_issue(0);
-        gather_store();
-      }
-    uint32_t done_b = 0, done_e = 0; // private runs completed by the previous batch: post pending
 
-    for (int i = 0; cur_it.valid; ++i)
+    if constexpr (!FUSED)
       {
-        const int nc = cur.nc, bf = i & 1;
-        BP4_TICK(0)
-        if (!kPipe)
+        // cur = the batch in the work rows, nxt = the one being gathered; the iterators run
+        // three batches ahead so that a claimed unit is known long before it is needed
+        It cur_it;
+        cur_it.j = 0, cur_it.b = cur_it.b_end = 0;
+        enter(cur_it);
+        Batch cur{}, nxt{}, nn{};
+        It    nxt_it = cur_it, nn_it = cur_it;
+        if (cur_it.valid)
           {
-            gather_issue(bf);
+            cur = describe(cur_it);
+            fetch_meta(cur.cell0, cur.nc);
+            park_meta(0);
+            nxt_it = advance(cur_it);
+            nn_it  = nxt_it;
+            if (nxt_it.valid)
+              {
+                nxt   = describe(nxt_it);
+                nn_it = advance(nxt_it);
+                if (nn_it.valid)
+                  nn = describe(nn_it);
+              }
+          }
+        __syncthreads();
+        if (kPipe && cur_it.valid)
+          {
+            gather_issue(0);
             gather_store();
           }
-        BP4_TICK(1)
-        __syncthreads();
-        BP4_TICK(2)
-        BP4_TRACE(i, 0)
-        BP4_TRACE(i, 4)
-        if (tid == 0)
-          claim_ahead(cur_it.j);
-        if (nxt_it.valid)
-          fetch_meta(nxt); // lands during the phases
-        // phase 1/3 items are handed out from the LAST thread downwards: the ragged final round
-        // of phase 2 lands on the first warps, so the two kinds of partial rounds end up on
-        // different warps (= different SM sub-partitions) instead of piling up on warp 0
-        if (!kFine)
+        for (int i = 0; cur_it.valid; ++i)
           {
-            for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
-              phase1<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
-          }
-        else
-          {
-            // one 1-D line per item, consecutive lanes on consecutive rows (odd row stride:
-            // no bank conflicts); see phase1a
-            const int n_rows = nc * G::ITEMS13;
-            for (int it = tid; it < n_rows * G::N; it += kThreads)
-              phase1a<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
-            __syncthreads();
-            for (int it = tid; it < n_rows * Q; it += kThreads)
-              phase1b<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
-            __syncthreads();
-            for (int it = tid; it < n_rows * Q; it += kThreads)
-              phase1c<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
-          }
-        BP4_TICK(3)
-        __syncthreads();
-        BP4_TICK(2)
-        for (int it = tid; it < nc * G::ITEMS2; it += kThreads)
-          {
-            const int cell = it / G::ITEMS2, r = it % G::ITEMS2;
-            const int qz = r / Q, qx = r % Q;
-            if constexpr (P >= BP4_P2_CALL_FROM)
-              phase2_call<P, QUAD>((uint32_t)((const unsigned char *)sm.coef[bf][cell] - smem_raw),
-                             (uint32_t)((const unsigned char *)(sm.work + cell * G::WORK) - smem_raw), qx, qz,
-                             sm.xq[qx], sm.xq[qz], sm.wq[qx] * sm.wq[qz]);
-            else
-              phase2<P, QUAD>(tb, sm.coef[bf][cell], sm.work + cell * G::WORK, qx, qz, sm.xq[qx], sm.xq[qz],
-                              sm.wq[qx] * sm.wq[qz]);
-          }
-        BP4_TICK(4)
-        __syncthreads();
-        BP4_TICK(2)
-        if (!kFine)
-          {
-            for (int it = kThreads - 1 - tid; it < nc * G::ITEMS13; it += kThreads)
-              phase3<P>(tb, sm.work + it * G::RW, sm.work + it * G::RW);
-          }
-        else
-          {
-            const int n_rows = nc * G::ITEMS13;
-            for (int it = tid; it < n_rows * Q; it += kThreads)
-              phase3a<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
-            __syncthreads();
-            for (int it = tid; it < n_rows * Q; it += kThreads)
-              phase3b<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
-            __syncthreads();
-            for (int it = tid; it < n_rows * G::N; it += kThreads)
-              phase3c<P>(tb, sm.work + (it % n_rows) * G::RW, it / n_rows);
-          }
-        if (nxt_it.valid)
-          park_meta(bf ^ 1);
-        // the previous batch's REDs and this block's earlier pre-updates were issued a whole
-        // batch ago: the fence that orders them before the loads below has nothing to wait for
-        if (FUSED)
-          __threadfence();
-        BP4_TICK(5)
-        __syncthreads();
-        BP4_TICK(2)
-        BP4_TRACE(i, 1)
-        // ---- memory window.  Loads are issued in groups that stay in flight together: the
-        // finished ranges' r, p, h (post) with the next batch's gather, then the scatter goes out
-        // while they travel; the pre-update's operands are requested before the barrier that
-        // releases the work rows and consumed after the gathered values have been parked.
-        Sweep      wpost, wpre;
-        const bool do_pre  = FUSED && nn_it.valid && nn.pre_e > nn.pre_b;
-        const bool do_post = FUSED && done_e > done_b;
-        if (do_post)
-          post_load(wpost, done_b + tid, done_e);
-        if (kPipe && nxt_it.valid)
-          gather_issue(bf ^ 1); // the next batch's DoFs (pre-updated one round ago)
-        // scatter-add (vector_access_reduced.h:437-521); the cell-interior entity (13) is
-        // touched by this cell only -> plain store
-        {
-          constexpr int SU = BP4_SU;
-          uint32_t      tt[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-            tt[r] = sm.dtab[on(r) ? tid + r * kThreads : 0];
-#pragma unroll
-          for (int s0 = 0; s0 < S; s0 += SU)
-            {
-              double   v[SU];
-              uint32_t adr[SU];
-#pragma unroll
-              for (int u = 0; u < SU; ++u)
-                if (s0 + u < S)
-                  {
-                    const int      cell = (s0 + u) / R, r = (s0 + u) % R;
-                    const uint32_t base = sm.eidx[bf][cell][dtab_ent(tt[r])];
-                    adr[u] = on(r) && base != 0xFFFFFFFFu ? base + dtab_rel(tt[r]) : 0xFFFFFFFFu;
-                    v[u]   = sm.work[cell * G::WORK + dtab_off_work<P>(tt[r])];
-                  }
-#pragma unroll
-              for (int u = 0; u < SU; ++u)
-                if (s0 + u < S && adr[u] != 0xFFFFFFFFu)
-                  {
-                    if (dtab_ent(tt[(s0 + u) % R]) == 13u)
-                      a.dst[adr[u]] = v[u];
-                    else
-                      atomicAdd(a.dst + adr[u], v[u]);
-                  }
-            }
-        }
-        BP4_TICK(6)
-        BP4_TRACE(i, 2)
-        const It n3_it = nn_it.valid ? advance(nn_it) : nn_it;
-        Batch    n3{};
-        if (n3_it.valid)
-          n3 = describe(n3_it);
-        if (FUSED)
-          {
-            post_finish(wpost, done_b, done_e, do_post);
-            if (do_pre)
-              pre_load(wpre, nn.pre_b + tid, nn.pre_e);
-          }
-        BP4_TICK(7)
-        __syncthreads();
-        BP4_TICK(2)
-        BP4_TRACE(i, 3)
-        if (kPipe && nxt_it.valid)
-          gather_store(); // the barrier after it is the one at the top of the next iteration
-        if (FUSED)
-          {
-            if (do_pre)
+            const int nc = cur.nc, bf = i & 1;
+            BP4_TICK(0)
+            if (!kPipe)
               {
-                pre_store(wpre, nn.pre_b + tid, nn.pre_e);
-                pre_rest(nn.pre_b, nn.pre_e, false);
+                gather_issue(bf);
+                gather_store();
               }
+            BP4_TICK(1)
+            __syncthreads();
+            BP4_TICK(2)
+            BP4_TRACE(i, 0)
+            BP4_TRACE(i, 4)
+            if (tid == 0)
+              claim_ahead(cur_it.j, a.claim_depth);
+            if (nxt_it.valid)
+              fetch_meta(nxt.cell0, nxt.nc); // lands during the phases
+            phase_1(nc);
+            BP4_TRACE(i, 5)
+            BP4_TICK(3)
+            __syncthreads();
+            BP4_TICK(2)
+            phase_2(nc, bf);
+            BP4_TRACE(i, 7)
+            BP4_TICK(4)
+            __syncthreads();
+            BP4_TICK(2)
+            phase_3(nc);
+            if (nxt_it.valid)
+              park_meta(bf ^ 1);
+            BP4_TRACE(i, 9)
+            BP4_TICK(5)
+            __syncthreads();
+            BP4_TICK(2)
+            BP4_TRACE(i, 1)
+            // ---- memory window: the next batch's gather loads are issued, then the scatter goes
+            // out while they travel
+            if (kPipe && nxt_it.valid)
+              gather_issue(bf ^ 1);
+            BP4_TRACE(i, 12)
+            scatter(bf);
+            BP4_TICK(6)
+            BP4_TRACE(i, 2)
+            const It n3_it = nn_it.valid ? advance(nn_it) : nn_it;
+            Batch    n3{};
             if (n3_it.valid)
-              prefetch_pre(n3);
-            done_b = cur.post_b, done_e = cur.post_e;
+              n3 = describe(n3_it);
+            BP4_TICK(7)
+            __syncthreads();
+            BP4_TICK(2)
+            BP4_TRACE(i, 3)
+            if (kPipe && nxt_it.valid)
+              gather_store(); // the barrier after it is the one at the top of the next iteration
+            BP4_TRACE(i, 18)
+            cur_it = nxt_it, cur = nxt;
+            nxt_it = nn_it, nxt = nn;
+            nn_it = n3_it, nn = n3;
           }
-        cur_it = nxt_it, cur = nxt;
-        nxt_it = nn_it, nxt = nn;
-        nn_it = n3_it, nn = n3;
       }
-    if (FUSED)
+    else
       {
-        // the last batch's private runs
-        __threadfence();
+        // ---- fused: do_cg_update4b / do_cg_update3b on the private runs ride along as "jobs".
+        // job_issue (right after a barrier: every thread is done with the rows) copies [b, e) of
+        // r, p, h and the diagonal into the staging rows asynchronously: every thread copies its
+        // share in 16-byte pieces (LDGSTS) and lets the mbarrier count it once those have landed.
+        // pre_job / post_job (one compute phase later) wait for the bytes and do the update from
+        // shared memory.  A run is cut into a first job of at most JOB DoFs and a second one.
+        // (cp.async.bulk was measured first: the request blocks the issuing warp for ~0.25 us
+        // per 5 KB row and the rows queue up behind each other - whoever asked last kept the
+        // whole block waiting at the next barrier for ~1 us per job.)
+        constexpr int  JOB        = Stage<P>::JOB;
+        JobSmem<JOB>  &js         = *reinterpret_cast<JobSmem<JOB> *>(smem_raw + sizeof(CellSmem<P, CPB, NC>));
+        const uint32_t job_bar    = smem_u32(&js.mbar);
+        uint32_t       job_parity = 0;
+        int            trace_i    = 0;
+        if (tid == 0)
+          mbar_init(job_bar, kThreads);
+        if (tid < 8 * (kThreads / 32))
+          js.redw[tid >> 3][tid & 7] = 0.;
+        auto job_split = [&](const uint32_t b, const uint32_t e) { return min(b + (uint32_t)JOB, e); };
+        // `always`: the arrival (and the matching wait) happens for an empty range too - the job
+        // then only carries the other asynchronous copies of its threads (metadata, descriptors)
+        auto job_issue = [&](const uint32_t b, const uint32_t e, const bool always) {
+          if (e > b)
+            {
+              const uint32_t lo = b & ~1u, n2 = (((e + 1u) & ~1u) - lo) >> 1;
+              const uint32_t q0 = div3(b) & ~1u, nq2 = (((div3(e - 1u) + 2u) & ~1u) - q0) >> 1;
+              for (uint32_t c = tid; c < n2; c += kThreads)
+                {
+                  cp_async16(smem_u32(&js.row[0][2 * c]), a.r + lo + 2 * c);
+                  cp_async16(smem_u32(&js.row[1][2 * c]), a.p + lo + 2 * c);
+                  cp_async16(smem_u32(&js.row[2][2 * c]), a.dst + lo + 2 * c);
+                }
+              for (uint32_t c = tid; c < nq2; c += kThreads)
+                cp_async16(smem_u32(&js.prec[2 * c]), a.prec + q0 + 2 * c);
+            }
+          if (e > b || always)
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(job_bar) : "memory");
+        };
+        auto job_wait = [&](const int ts) {
+          mbar_wait(job_bar, job_parity);
+          job_parity ^= 1u;
+          BP4_TRACE(trace_i, ts)
+        };
+        // DoFs per thread and job: all shared-memory reads of a job are issued before the first use
+        constexpr int KJ = (JOB + kThreads - 1) / kThreads;
+        // do_cg_update4b<3,double,true> (solver_cg_optimized.h:65-161) on [b, e)
+        auto pre_job = [&](const uint32_t b, const uint32_t e, const bool always, const int ts) {
+          if (e > b || always)
+            job_wait(ts);
+          if (e <= b)
+            return;
+          const uint32_t lo = b & ~1u, q0 = div3(b) & ~1u;
+          double         pr[KJ], rr[KJ], pp[KJ], hh[KJ];
+#pragma unroll
+          for (int k = 0; k < KJ; ++k)
+            {
+              const uint32_t i = min(b + tid + k * kThreads, e - 1u);
+              pr[k] = js.prec[div3(i) - q0];
+              rr[k] = js.row[0][i - lo];
+              pp[k] = js.row[1][i - lo];
+              hh[k] = js.row[2][i - lo];
+            }
+#pragma unroll
+          for (int k = 0; k < KJ; ++k)
+            {
+              const uint32_t i = b + tid + k * kThreads;
+              if (i < e)
+                {
+                  if (a.first)
+                    a.p[i] = -pr[k] * rr[k];
+                  else
+                    {
+                      if (a.update_x) // x += ..., fire and forget: x is not read in this kernel
+                        atomicAdd(a.x + i, a.c1 * pp[k] + a.c2 * pr[k] * rr[k]);
+                      const double rn = rr[k] + a.alpha * hh[k];
+                      a.r[i]          = rn;
+                      a.p[i]          = a.beta * pp[k] - pr[k] * rn;
+                    }
+                  a.dst[i] = 0.;
+                }
+            }
+        };
+        // do_cg_update3b<3,double> (solver_cg_optimized.h:12-61) on [b, e): the seven sums of a
+        // thread stay in registers from the first to the second post job of an iteration, then
+        // one warp reduction and a plain add into the warp's own slots (post_sums)
+        auto post_job = [&](double (&sj)[7], const uint32_t b, const uint32_t e, const bool always, const int ts) {
+          if (e > b || always)
+            job_wait(ts);
+          if (e <= b)
+            return;
+          const uint32_t lo = b & ~1u, q0 = div3(b) & ~1u;
+          double         pr[KJ], rr[KJ], pp[KJ], hh[KJ];
+#pragma unroll
+          for (int k = 0; k < KJ; ++k)
+            {
+              const uint32_t i  = b + tid + k * kThreads;
+              const bool     ok = i < e;
+              const uint32_t ic = ok ? i : b;
+              pr[k] = js.prec[div3(ic) - q0];
+              rr[k] = ok ? js.row[0][ic - lo] : 0.;
+              pp[k] = js.row[1][ic - lo];
+              hh[k] = ok ? js.row[2][ic - lo] : 0.;
+            }
+#pragma unroll
+          for (int k = 0; k < KJ; ++k)
+            post_terms(sj, rr[k], pp[k], hh[k], pr[k]);
+        };
+        auto post_sums = [&](double (&sj)[7]) {
+#pragma unroll
+          for (int k = 0; k < 7; ++k)
+            sj[k] = warp_sum(sj[k]);
+          if ((tid & 31) == 0)
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+              js.redw[tid >> 5][k] += sj[k];
+        };
+
+        // The descriptors of the batches i-2 .. i+4 live in a ring in shared memory and are read
+        // where they are needed; the only iterator kept in registers is the head (batch i+3).
+        // vm: bit k-1 set <=> batch i+k exists (k = 1..3).  All of this is uniform over the block.
+        auto ring_put = [&](const uint32_t k, const It &it) { // synchronous (prologue)
+          const uint4 w0 = __ldg(reinterpret_cast<const uint4 *>(a.batch + it.b));
+          const uint4 w1 = __ldg(reinterpret_cast<const uint4 *>(a.batch + it.b) + 1);
+          if (tid == 0)
+            {
+              uint4 *dst = reinterpret_cast<uint4 *>(&js.ring[k & 7u]);
+              dst[0] = w0, dst[1] = w1;
+            }
+        };
+        auto ring_fetch = [&](const uint32_t k, const It &it) { // asynchronous, see job_issue(always)
+          if (tid < 2)
+            cp_async16(smem_u32(&js.ring[k & 7u]) + 16u * tid,
+                       reinterpret_cast<const unsigned char *>(a.batch + it.b) + 16u * tid);
+        };
+        It hd;
+        hd.j = 0, hd.b = hd.b_end = 0;
+        enter(hd);
+        const bool any = hd.valid;
+        uint32_t   vm  = 0;
+        if (any)
+          {
+            ring_put(0, hd);
+            for (uint32_t k = 1; k <= 3; ++k)
+              if (hd.valid)
+                {
+                  hd = advance(hd);
+                  if (hd.valid)
+                    {
+                      ring_put(k, hd);
+                      vm |= 1u << (k - 1);
+                    }
+                }
+          }
         __syncthreads();
-        Sweep w;
-        post_finish(w, done_b, done_e, false);
+        if (any)
+          {
+            // batch 0: metadata and the pre-update of its runs, synchronously
+            const BatchDesc &d0 = js.ring[0];
+            fetch_meta(d0.cell0, (int)d0.n_cells);
+            park_meta(0);
+            const uint32_t pb = d0.pre_begin, pe = d0.pre_end, pm = job_split(pb, pe);
+            job_issue(pb, pm, false);
+            pre_job(pb, pm, false, 16);
+            __syncthreads();
+            job_issue(pm, pe, false);
+            pre_job(pm, pe, false, 17);
+            __syncthreads();
+            // first part of the pre-update of batch 1 (consumed at the end of phase 1 below)
+            const BatchDesc &d1 = js.ring[1];
+            const uint32_t   qb = (vm & 1u) ? d1.pre_begin : 0u, qe = (vm & 1u) ? d1.pre_end : 0u;
+            job_issue(qb, job_split(qb, qe), true);
+            if (kPipe)
+              {
+                gather_issue(0);
+                gather_store();
+              }
+          }
+        int i = 0;
+        for (bool cur_ok = any; cur_ok; ++i)
+          {
+            const int bf = i & 1;
+            trace_i      = i;
+            if (!kPipe)
+              {
+                gather_issue(bf);
+                gather_store();
+              }
+            __syncthreads();
+            BP4_TRACE(i, 0)
+            BP4_TRACE(i, 4)
+            const int nc = (int)js.ring[i & 7].n_cells;
+            if (tid == 0)
+              claim_ahead(hd.j, 2);
+            if (vm & 1u)
+              {
+                const BatchDesc &dn = js.ring[(i + 1) & 7];
+                meta_async(bf ^ 1, dn.cell0, (int)dn.n_cells);
+              }
+            phase_1(nc);
+            BP4_TRACE(i, 5)
+            // schedule of one iteration (each job is requested right after a barrier and consumed
+            // before the next one): first / second part of the next batch's pre-update at the end
+            // of phases 1 / 2, then the post-update of the runs finished two batches ago at the
+            // end of phase 3 / of the scatter (their REDs went out a whole batch earlier)
+            {
+              const BatchDesc &dn = js.ring[(i + 1) & 7];
+              const uint32_t   pb = (vm & 1u) ? dn.pre_begin : 0u, pe = (vm & 1u) ? dn.pre_end : 0u;
+              const uint32_t   pm = job_split(pb, pe);
+              pre_job(pb, pm, true, 16);
+              BP4_TRACE(i, 6)
+              __syncthreads();
+              job_issue(pm, pe, false);
+              phase_2(nc, bf);
+              BP4_TRACE(i, 7)
+              pre_job(pm, pe, false, 17);
+              BP4_TRACE(i, 8)
+            }
+            __syncthreads();
+            const BatchDesc &dold = js.ring[(i + 6) & 7]; // batch i - 2
+            const uint32_t   ob = i >= 2 ? dold.post_begin : 0u, oe = i >= 2 ? dold.post_end : 0u;
+            const uint32_t   om = job_split(ob, oe);
+            job_issue(ob, om, true); // carries the next batch's metadata too
+            phase_3(nc);
+            BP4_TRACE(i, 9)
+            double sj[7] = {0., 0., 0., 0., 0., 0., 0.};
+            post_job(sj, ob, om, true, 14);
+            BP4_TRACE(i, 10)
+            // every consumer of this block's stores and REDs is a thread of this block (its loads
+            // and asynchronous copies): the barriers order them.  No GPU-scope fence here:
+            // __threadfence is MEMBAR.SC.GPU + CCTL.IVALL, measured 0.7 us per batch and the
+            // whole L1 gone each time.
+            __syncthreads();
+            BP4_TRACE(i, 1)
+            job_issue(om, oe, false);
+            // ---- memory window
+            if (kPipe && (vm & 1u))
+              gather_issue(bf ^ 1); // the next batch's DoFs (pre-updated during this batch)
+            BP4_TRACE(i, 12)
+            scatter(bf);
+            BP4_TRACE(i, 2)
+            // the head moves on to batch i + 4
+            bool hv = false;
+            if (vm & 4u)
+              {
+                hd = advance(hd);
+                hv = hd.valid;
+                if (hv)
+                  ring_fetch(i + 4, hd);
+              }
+            if (oe > ob)
+              {
+                post_job(sj, om, oe, false, 15);
+                post_sums(sj);
+              }
+            BP4_TRACE(i, 13)
+            __syncthreads();
+            BP4_TRACE(i, 3)
+            if (kPipe && (vm & 1u))
+              gather_store(); // the barrier after it is the one at the top of the next iteration
+            BP4_TRACE(i, 18)
+            {
+              // first part of the pre-update of batch i + 2 (the `next` of the coming iteration);
+              // the arrival also covers the descriptor requested above
+              const BatchDesc &d2 = js.ring[(i + 2) & 7];
+              const uint32_t   pb = (vm & 2u) ? d2.pre_begin : 0u, pe = (vm & 2u) ? d2.pre_end : 0u;
+              job_issue(pb, job_split(pb, pe), true);
+            }
+            BP4_TRACE(i, 19)
+            cur_ok = (vm & 1u) != 0;
+            vm     = (vm >> 1) | (hv ? 4u : 0u);
+          }
+        if (any)
+          {
+            // the request made at the end of the last iteration carried nothing: retire it, then
+            // the post-updates of the last two batches, synchronously
+            job_wait(16);
+            __syncthreads();
+            double sj[7] = {0., 0., 0., 0., 0., 0., 0.};
+            for (int k = max(i - 2, 0); k < i; ++k)
+              {
+                const BatchDesc &dk = js.ring[k & 7];
+                const uint32_t   ob = dk.post_begin, oe = dk.post_end, om = job_split(ob, oe);
+                job_issue(ob, om, false);
+                post_job(sj, ob, om, false, 14);
+                __syncthreads();
+                job_issue(om, oe, false);
+                post_job(sj, om, oe, false, 15);
+                __syncthreads();
+              }
+            post_sums(sj);
+          }
         __syncthreads();
         if (tid < 7)
-          atomicAdd(a.acc + tid, sm.red[tid]);
+          {
+            double v = 0.;
+#pragma unroll
+            for (int wp = 0; wp < kThreads / 32; ++wp)
+              v += js.redw[wp][tid];
+            atomicAdd(a.acc + tid, v);
+          }
       }
     BP4_TICK_FLUSH
   }
@@ -996,6 +1195,13 @@ namespace bp4
     return (int)std::min<uint64_t>(std::max<uint64_t>(blocks, 1), (uint64_t)sms * 8);
   }
 
+  // dynamic shared memory of the fused instantiation: the staging rows follow the cell rows
+  template <int P>
+  constexpr size_t fused_smem()
+  {
+    return sizeof(CellSmem<P, Cfg<P>::CPB, 24>) + sizeof(JobSmem<(Stage<P>::OK ? Stage<P>::JOB : 2)>);
+  }
+
   template <int P>
   static cudaError_t init_degree(std::vector<uint32_t> &walk)
   {
@@ -1015,15 +1221,17 @@ namespace bp4
                              (int)sizeof(CellSmem<P, CPBQ, 81>));
     if (e != cudaSuccess)
       return e;
-    return cudaFuncSetAttribute(cell_kernel<P, CPB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(CellSmem<P, CPB, 24>));
+    if constexpr (Stage<P>::OK)
+      e = cudaFuncSetAttribute(cell_kernel<P, CPB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem<P>());
+    return e;
   }
 
   template <int P>
   static cudaError_t run_cell(const bool fused, const bool quad, const CellArgs &a, int sms, cudaStream_t st)
   {
     constexpr int  CPB = Cfg<P>::CPB, CPBQ = Cfg<P, true>::CPB;
-    if (fused && quad)
+    if (fused && (quad || !Stage<P>::OK))
       return cudaErrorInvalidValue;
     const uint64_t units = fused ? a.n_units : (a.n_cells + (quad ? CPBQ : CPB) - 1) / (quad ? CPBQ : CPB);
     const int      grid  = (int)std::min<uint64_t>(units, (uint64_t)sms * Cfg<P>::BLOCKS);
@@ -1031,7 +1239,7 @@ namespace bp4
       return cudaSuccess;
 #ifdef BP4_PHASE_TIMING
     unsigned long long *d_trace = nullptr;
-    const size_t        n_trace = (size_t)grid * kTraceBatches * 5;
+    const size_t        n_trace = (size_t)grid * kTraceBatches * 20;
     if (getenv("BP4_TRACE"))
       {
         cudaMalloc(&d_trace, n_trace * 8);
@@ -1040,7 +1248,10 @@ namespace bp4
     cudaMemcpyToSymbolAsync(g_trace, &d_trace, sizeof(d_trace), 0, cudaMemcpyHostToDevice, st);
 #endif
     if (fused)
-      cell_kernel<P, CPB, true, false><<<grid, Cfg<P>::THREADS, sizeof(CellSmem<P, CPB, 24>), st>>>(a);
+      {
+        if constexpr (Stage<P>::OK)
+          cell_kernel<P, CPB, true, false><<<grid, Cfg<P>::THREADS, fused_smem<P>(), st>>>(a);
+      }
     else if (quad)
       cell_kernel<P, CPBQ, false, true><<<grid, Cfg<P>::THREADS, sizeof(CellSmem<P, CPBQ, 81>), st>>>(a);
     else
@@ -1115,6 +1326,22 @@ namespace bp4
         case 6: return quad ? Cfg<6, true>::CPB : Cfg<6>::CPB;
         case 7: return quad ? Cfg<7, true>::CPB : Cfg<7>::CPB;
         case 8: return quad ? Cfg<8, true>::CPB : Cfg<8>::CPB;
+      }
+    return 0;
+  }
+
+  // longest private run (DoFs) one batch of the fused loop may carry; 0 = the degree has no fused kernel
+  uint32_t fused_run_limit(int degree)
+  {
+    switch (degree)
+      {
+        case 2: return Stage<2>::OK ? Stage<2>::LIMIT : 0;
+        case 3: return Stage<3>::OK ? Stage<3>::LIMIT : 0;
+        case 4: return Stage<4>::OK ? Stage<4>::LIMIT : 0;
+        case 5: return Stage<5>::OK ? Stage<5>::LIMIT : 0;
+        case 6: return Stage<6>::OK ? Stage<6>::LIMIT : 0;
+        case 7: return Stage<7>::OK ? Stage<7>::LIMIT : 0;
+        case 8: return Stage<8>::OK ? Stage<8>::LIMIT : 0;
       }
     return 0;
   }

@@ -19,6 +19,10 @@ namespace bp4
 #ifndef BP4_WIDE
 #  define BP4_WIDE(P) false
 #endif
+#ifndef BP4_STAGED
+// degrees with a fused cell kernel (in-loop vector updates staged through shared memory)
+#  define BP4_STAGED(P) ((P) <= 4)
+#endif
   constexpr int kBlocksPerSM = 2;
 
   // QUAD: all 27 geometry coefficients per cell (81 doubles) instead of the 8 tri-linear ones (24)
@@ -77,6 +81,41 @@ namespace bp4
     uint32_t pad[2];
   };
 
+  // Staging rows of the fused cell loop (appended to CellSmem in dynamic shared memory).  The
+  // in-loop do_cg_update4b / do_cg_update3b are cut into "jobs" of at most JOB DoFs; the bulk
+  // copy engine (cp.async.bulk + mbarrier) streams a job's r, p, h and diagonal entries into these
+  // rows while the block runs a compute phase, the threads consume them from shared memory at the
+  // end of that phase: no thread waits for a DRAM round trip or holds loaded values in registers
+  // (the register-staged variant made the memory window 3x longer).
+  // A job [b, e) may start at an odd index: the copy is widened to 16-byte boundaries, element i
+  // sits at row[..][i - (b & ~1)], diagonal entry i/3 at prec[i/3 - ((b/3) & ~1)].
+  template <int JOB>
+  struct alignas(16) JobSmem
+  {
+    static constexpr int ROW  = JOB + 2;
+    static constexpr int PREC = ((JOB / 3 + 4) + 1) & ~1;
+    double             row[3][ROW]; // r, p (= d), h
+    double             prec[PREC];
+    double             redw[8][8]; // the seven merged sums, one row per warp
+    BatchDesc          ring[8];    // descriptors of the batches i-2 .. i+4 of this block
+    unsigned long long mbar;
+    unsigned long long pad;
+  };
+  // JOB = DoFs per job that fit next to the cell kernel's own shared memory; a batch's pre / post
+  // run is handled by two jobs -> LIMIT.  OK: the degree has a fused kernel at all (the runs of
+  // the high degrees are far longer than what is left of the shared memory: Q5 2187 DoFs per range
+  // vs 146 per job)
+  template <int P>
+  struct Stage
+  {
+    static constexpr long avail = (long)Cfg<P>::budget - (long)sizeof(CellSmem<P, Cfg<P>::CPB, 24>) - 16 - 512 - 256;
+    // 3 rows of (JOB + 2) + JOB / 3 + 5 doubles
+    static constexpr long cap   = ((avail / 8 - 11) * 3) / 10;
+    static constexpr int  JOB   = cap < 64 ? 0 : (int)(cap & ~1L);
+    static constexpr int  LIMIT = 2 * JOB;
+    static constexpr bool OK    = BP4_STAGED(P) && JOB >= 64;
+  };
+
   struct CellArgs
   {
     const uint32_t *entity_index; // [n_cells][27]
@@ -87,6 +126,7 @@ namespace bp4
     double         *dst;          // plain: output vector; fused: h
     uint32_t       *sched;        // unit counter of this launch (zero at launch), null: strided
     uint32_t        stagger_ns;   // start offsets of the blocks are spread over [0, stagger_ns)
+    uint32_t        claim_depth;  // plain: units a block holds claimed (the current one included)
     // ---- fused (vmult_with_merged_sums) only ----
     const BatchDesc *batch;       // batches of all units
     const uint32_t  *unit_batch;  // [n_units + 1] first batch of every unit of this launch

@@ -12,6 +12,7 @@ namespace bp4
   cudaError_t launch_init_degree(int degree, std::vector<uint32_t> &walk);
   int         cells_per_block(int degree, bool quad = false);
   int         blocks_per_sm(int degree);
+  uint32_t    fused_run_limit(int degree);
   // plain: a.n_cells cells from a.entity_index on; fused: a.n_units units of a.unit_batch;
   // quad: a.coef holds all 27 coefficients per cell (plain kernel only)
   cudaError_t launch_cell(int degree, bool fused, bool quad, const CellArgs &a, int sms, cudaStream_t st);

@@ -24,7 +24,8 @@ for p in range(2, 9):
     ctx.equ(g, -1.0, src)
     for rep in range(2):                 # launch 0 of each kind warms up, launch 1 is the one to read
         ctx.vmult(dst, src)
-    ctx.set_fused(True)
+    if ctx.fused_info()[1] > 0:
+        ctx.set_fused(True)
     S = ctx.vmult_merged(x, g, d, h, prec, 0.0, 0.0, 0.0, 0.0)
     al = S[6] / S[0]
     be = al * (S[4] + al * S[5]) / S[6]

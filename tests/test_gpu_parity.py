@@ -99,8 +99,20 @@ def test_merged_sums_match_oracle(p, s, fused, constrained_rhs, bp4_lib, c_oracl
     rd, co = single(p, s)
     ctx = make_ctx(rd)
     _, n_private, n_units = ctx.fused_info()
-    assert n_private == rd.group_sizes[0] and n_units > 0
-    ctx.set_fused(fused)
+    assert n_units > 0
+    if p <= 4:
+        assert n_private == rd.group_sizes[0]
+        ctx.set_fused(fused)
+    else:
+        # no fused kernel above Q4 (a range's private run does not fit the staging rows left
+        # in shared memory): everything is streamed, asking for the fused loop is an error
+        from mf_data_locality_b200 import capi
+        assert n_private == 0
+        with pytest.raises(capi.Bp4Error, match="degree"):
+            ctx.set_fused(True)
+        if fused:
+            ctx.close()
+            return
     n = rd.n_owned
     rng = np.random.default_rng(3)
     free = np.ones(n)
@@ -129,6 +141,8 @@ def test_merged_sums_match_oracle(p, s, fused, constrained_rhs, bp4_lib, c_oracl
 def test_cg_merged_parity(p, s, fused, bp4_lib, c_oracle_lib):
     rd, co = single(p, s)
     ctx = make_ctx(rd)
+    if fused and p > 4:
+        pytest.skip("no fused kernel above Q4")
     ctx.set_fused(fused)
     prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
     vp = ctx.vector(rd.n_owned // 3, data=prec)
