@@ -570,6 +570,12 @@ namespace bp4
         if (tid < 8 * (kThreads / 32))
           js.redw[tid >> 3][tid & 7] = 0.;
         auto job_split = [&](const uint32_t b, const uint32_t e) { return min(b + (uint32_t)JOB, e); };
+        // A job [b, e) is handled in 16-byte pieces ("pairs" of DoFs, the first one at the even
+        // index lo = b & ~1): thread tid owns the pairs tid + k * kThreads, for the copy and for
+        // the update, so every shared-memory and global access of a job is a 128-bit one.
+        constexpr int      KC   = ((JOB + 2) / 2 + kThreads - 1) / kThreads; // pairs per thread
+        constexpr uint32_t ROWB = JobSmem<JOB>::ROW * 8u;                    // bytes per staging row
+        constexpr int      KQ   = (JobSmem<JOB>::PREC / 2 + kThreads - 1) / kThreads;
         // `always`: the arrival (and the matching wait) happens for an empty range too - the job
         // then only carries the other asynchronous copies of its threads (metadata, descriptors)
         auto job_issue = [&](const uint32_t b, const uint32_t e, const bool always) {
@@ -577,14 +583,26 @@ namespace bp4
             {
               const uint32_t lo = b & ~1u, n2 = (((e + 1u) & ~1u) - lo) >> 1;
               const uint32_t q0 = div3(b) & ~1u, nq2 = (((div3(e - 1u) + 2u) & ~1u) - q0) >> 1;
-              for (uint32_t c = tid; c < n2; c += kThreads)
+              const uint32_t s0 = smem_u32(&js.row[0][0]);
+              const double  *gr = a.r + lo, *gp = a.p + lo, *gh = a.dst + lo;
+#pragma unroll
+              for (int k = 0; k < KC; ++k)
                 {
-                  cp_async16(smem_u32(&js.row[0][2 * c]), a.r + lo + 2 * c);
-                  cp_async16(smem_u32(&js.row[1][2 * c]), a.p + lo + 2 * c);
-                  cp_async16(smem_u32(&js.row[2][2 * c]), a.dst + lo + 2 * c);
+                  const uint32_t c = tid + k * kThreads;
+                  if (c < n2)
+                    {
+                      cp_async16(s0 + 16u * c, gr + 2 * c);
+                      cp_async16(s0 + ROWB + 16u * c, gp + 2 * c);
+                      cp_async16(s0 + 2u * ROWB + 16u * c, gh + 2 * c);
+                    }
                 }
-              for (uint32_t c = tid; c < nq2; c += kThreads)
-                cp_async16(smem_u32(&js.prec[2 * c]), a.prec + q0 + 2 * c);
+#pragma unroll
+              for (int k = 0; k < KQ; ++k)
+                {
+                  const uint32_t c = tid + k * kThreads;
+                  if (c < nq2)
+                    cp_async16(smem_u32(&js.prec[2 * c]), a.prec + q0 + 2 * c);
+                }
             }
           if (e > b || always)
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(job_bar) : "memory");
@@ -594,43 +612,67 @@ namespace bp4
           job_parity ^= 1u;
           BP4_TRACE(trace_i, ts)
         };
-        // DoFs per thread and job: all shared-memory reads of a job are issued before the first use
-        constexpr int KJ = (JOB + kThreads - 1) / kThreads;
+        // the pairs of this thread: values of the three rows and the two diagonal entries
+        struct Pairs
+        {
+          double2 r[KC], p[KC], h[KC], d[KC];
+          bool    ok0[KC], ok1[KC];
+        };
+        auto job_load = [&](Pairs &w, const uint32_t b, const uint32_t e) {
+          const uint32_t lo = b & ~1u, n2 = (((e + 1u) & ~1u) - lo) >> 1, q0 = div3(b) & ~1u;
+#pragma unroll
+          for (int k = 0; k < KC; ++k)
+            {
+              const uint32_t c  = tid + k * kThreads;
+              const bool     in = c < n2;
+              const uint32_t cc = in ? c : 0u, i0 = lo + 2u * cc;
+              w.ok0[k] = in && i0 >= b;
+              w.ok1[k] = in && i0 + 1u < e;
+              w.r[k]   = *reinterpret_cast<const double2 *>(&js.row[0][2 * cc]);
+              w.p[k]   = *reinterpret_cast<const double2 *>(&js.row[1][2 * cc]);
+              w.h[k]   = *reinterpret_cast<const double2 *>(&js.row[2][2 * cc]);
+              w.d[k].x = js.prec[div3(max(i0, b)) - q0];
+              w.d[k].y = js.prec[div3(min(i0 + 1u, e - 1u)) - q0];
+            }
+        };
+        auto store2 = [&](double *v, const uint32_t i0, const bool ok0, const bool ok1, const double x, const double y) {
+          if (ok0 && ok1)
+            *reinterpret_cast<double2 *>(v + i0) = make_double2(x, y);
+          else if (ok0)
+            v[i0] = x;
+          else if (ok1)
+            v[i0 + 1] = y;
+        };
         // do_cg_update4b<3,double,true> (solver_cg_optimized.h:65-161) on [b, e)
         auto pre_job = [&](const uint32_t b, const uint32_t e, const bool always, const int ts) {
           if (e > b || always)
             job_wait(ts);
           if (e <= b)
             return;
-          const uint32_t lo = b & ~1u, q0 = div3(b) & ~1u;
-          double         pr[KJ], rr[KJ], pp[KJ], hh[KJ];
+          Pairs w;
+          job_load(w, b, e);
+          const uint32_t lo = b & ~1u;
 #pragma unroll
-          for (int k = 0; k < KJ; ++k)
+          for (int k = 0; k < KC; ++k)
             {
-              const uint32_t i = min(b + tid + k * kThreads, e - 1u);
-              pr[k] = js.prec[div3(i) - q0];
-              rr[k] = js.row[0][i - lo];
-              pp[k] = js.row[1][i - lo];
-              hh[k] = js.row[2][i - lo];
-            }
-#pragma unroll
-          for (int k = 0; k < KJ; ++k)
-            {
-              const uint32_t i = b + tid + k * kThreads;
-              if (i < e)
+              const uint32_t i0 = lo + 2u * (tid + k * kThreads);
+              if (a.first)
+                store2(a.p, i0, w.ok0[k], w.ok1[k], -w.d[k].x * w.r[k].x, -w.d[k].y * w.r[k].y);
+              else
                 {
-                  if (a.first)
-                    a.p[i] = -pr[k] * rr[k];
-                  else
+                  if (a.update_x) // x += ..., fire and forget: x is not read in this kernel
                     {
-                      if (a.update_x) // x += ..., fire and forget: x is not read in this kernel
-                        atomicAdd(a.x + i, a.c1 * pp[k] + a.c2 * pr[k] * rr[k]);
-                      const double rn = rr[k] + a.alpha * hh[k];
-                      a.r[i]          = rn;
-                      a.p[i]          = a.beta * pp[k] - pr[k] * rn;
+                      if (w.ok0[k])
+                        atomicAdd(a.x + i0, a.c1 * w.p[k].x + a.c2 * w.d[k].x * w.r[k].x);
+                      if (w.ok1[k])
+                        atomicAdd(a.x + i0 + 1, a.c1 * w.p[k].y + a.c2 * w.d[k].y * w.r[k].y);
                     }
-                  a.dst[i] = 0.;
+                  const double r0 = w.r[k].x + a.alpha * w.h[k].x, r1 = w.r[k].y + a.alpha * w.h[k].y;
+                  store2(a.r, i0, w.ok0[k], w.ok1[k], r0, r1);
+                  store2(a.p, i0, w.ok0[k], w.ok1[k], a.beta * w.p[k].x - w.d[k].x * r0,
+                         a.beta * w.p[k].y - w.d[k].y * r1);
                 }
+              store2(a.dst, i0, w.ok0[k], w.ok1[k], 0., 0.);
             }
         };
         // do_cg_update3b<3,double> (solver_cg_optimized.h:12-61) on [b, e): the seven sums of a
@@ -641,31 +683,36 @@ namespace bp4
             job_wait(ts);
           if (e <= b)
             return;
-          const uint32_t lo = b & ~1u, q0 = div3(b) & ~1u;
-          double         pr[KJ], rr[KJ], pp[KJ], hh[KJ];
+          Pairs w;
+          job_load(w, b, e);
 #pragma unroll
-          for (int k = 0; k < KJ; ++k)
+          for (int k = 0; k < KC; ++k)
             {
-              const uint32_t i  = b + tid + k * kThreads;
-              const bool     ok = i < e;
-              const uint32_t ic = ok ? i : b;
-              pr[k] = js.prec[div3(ic) - q0];
-              rr[k] = ok ? js.row[0][ic - lo] : 0.;
-              pp[k] = js.row[1][ic - lo];
-              hh[k] = ok ? js.row[2][ic - lo] : 0.;
+              post_terms(sj, w.ok0[k] ? w.r[k].x : 0., w.p[k].x, w.ok0[k] ? w.h[k].x : 0., w.d[k].x);
+              post_terms(sj, w.ok1[k] ? w.r[k].y : 0., w.p[k].y, w.ok1[k] ? w.h[k].y : 0., w.d[k].y);
+            }
+        };
+        // Transposed butterfly: at every step a lane keeps half of its values and hands the
+        // other half to its partner, so 7 sums over 32 lanes take 9 shuffles instead of 35;
+        // lane 4 m ends up with the warp's total of sum m.
+        auto post_sums = [&](double (&sj)[7]) {
+          const int  lane = tid & 31;
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+          double     w[4], u[2], t;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            {
+              const double hi = k + 4 < 7 ? sj[k + 4] : 0.;
+              w[k] = (h16 ? hi : sj[k]) + __shfl_xor_sync(0xffffffffu, h16 ? sj[k] : hi, 16);
             }
 #pragma unroll
-          for (int k = 0; k < KJ; ++k)
-            post_terms(sj, rr[k], pp[k], hh[k], pr[k]);
-        };
-        auto post_sums = [&](double (&sj)[7]) {
-#pragma unroll
-          for (int k = 0; k < 7; ++k)
-            sj[k] = warp_sum(sj[k]);
-          if ((tid & 31) == 0)
-#pragma unroll
-            for (int k = 0; k < 7; ++k)
-              js.redw[tid >> 5][k] += sj[k];
+          for (int k = 0; k < 2; ++k)
+            u[k] = (h8 ? w[k + 2] : w[k]) + __shfl_xor_sync(0xffffffffu, h8 ? w[k] : w[k + 2], 8);
+          t = (h4 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, h4 ? u[0] : u[1], 4);
+          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          t += __shfl_xor_sync(0xffffffffu, t, 1);
+          if ((lane & 3) == 0 && lane < 28)
+            js.redw[tid >> 5][lane >> 2] += t;
         };
 
         // The descriptors of the batches i-2 .. i+4 live in a ring in shared memory and are read
@@ -718,17 +765,21 @@ namespace bp4
             job_issue(pm, pe, false);
             pre_job(pm, pe, false, 17);
             __syncthreads();
-            // first part of the pre-update of batch 1 (consumed at the end of phase 1 below)
-            const BatchDesc &d1 = js.ring[1];
-            const uint32_t   qb = (vm & 1u) ? d1.pre_begin : 0u, qe = (vm & 1u) ? d1.pre_end : 0u;
-            job_issue(qb, job_split(qb, qe), true);
             if (kPipe)
               {
                 gather_issue(0);
                 gather_store();
               }
           }
-        int i = 0;
+        // Schedule of one iteration - each job is requested right after a barrier and consumed
+        // before the next one, one compute phase later:
+        //   phase 1: first part of the next batch's pre-update      phase 2: its second part
+        //   phase 3: first part of the post-update of the runs finished two batches ago (their
+        //            REDs went out a whole batch earlier)
+        //   window : its second part; it is consumed last, after the gathered values have been
+        //            parked - the copies that travel while the scatter's REDs go out are slow
+        int    i = 0;
+        double sj[7]; // lives from the end of phase 3 to the end of the iteration only
         for (bool cur_ok = any; cur_ok; ++i)
           {
             const int bf = i & 1;
@@ -741,24 +792,22 @@ namespace bp4
             __syncthreads();
             BP4_TRACE(i, 0)
             BP4_TRACE(i, 4)
-            const int nc = (int)js.ring[i & 7].n_cells;
+            const int        nc = (int)js.ring[i & 7].n_cells;
+            const BatchDesc &dn = js.ring[(i + 1) & 7];
+            {
+              // the arrival also covers the descriptor requested in the previous window
+              const uint32_t pb = (vm & 1u) ? dn.pre_begin : 0u, pe = (vm & 1u) ? dn.pre_end : 0u;
+              job_issue(pb, job_split(pb, pe), true);
+            }
             if (tid == 0)
               claim_ahead(hd.j, 2);
             if (vm & 1u)
-              {
-                const BatchDesc &dn = js.ring[(i + 1) & 7];
-                meta_async(bf ^ 1, dn.cell0, (int)dn.n_cells);
-              }
+              meta_async(bf ^ 1, dn.cell0, (int)dn.n_cells);
             phase_1(nc);
             BP4_TRACE(i, 5)
-            // schedule of one iteration (each job is requested right after a barrier and consumed
-            // before the next one): first / second part of the next batch's pre-update at the end
-            // of phases 1 / 2, then the post-update of the runs finished two batches ago at the
-            // end of phase 3 / of the scatter (their REDs went out a whole batch earlier)
             {
-              const BatchDesc &dn = js.ring[(i + 1) & 7];
-              const uint32_t   pb = (vm & 1u) ? dn.pre_begin : 0u, pe = (vm & 1u) ? dn.pre_end : 0u;
-              const uint32_t   pm = job_split(pb, pe);
+              const uint32_t pb = (vm & 1u) ? dn.pre_begin : 0u, pe = (vm & 1u) ? dn.pre_end : 0u;
+              const uint32_t pm = job_split(pb, pe);
               pre_job(pb, pm, true, 16);
               BP4_TRACE(i, 6)
               __syncthreads();
@@ -775,7 +824,9 @@ namespace bp4
             job_issue(ob, om, true); // carries the next batch's metadata too
             phase_3(nc);
             BP4_TRACE(i, 9)
-            double sj[7] = {0., 0., 0., 0., 0., 0., 0.};
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+              sj[k] = 0.;
             post_job(sj, ob, om, true, 14);
             BP4_TRACE(i, 10)
             // every consumer of this block's stores and REDs is a thread of this block (its loads
@@ -800,35 +851,27 @@ namespace bp4
                 if (hv)
                   ring_fetch(i + 4, hd);
               }
+            __syncthreads();
+            BP4_TRACE(i, 3)
+            if (kPipe && (vm & 1u))
+              gather_store(); // the barrier after it is the one at the top of the next iteration
+            BP4_TRACE(i, 18)
             if (oe > ob)
               {
                 post_job(sj, om, oe, false, 15);
                 post_sums(sj);
               }
             BP4_TRACE(i, 13)
-            __syncthreads();
-            BP4_TRACE(i, 3)
-            if (kPipe && (vm & 1u))
-              gather_store(); // the barrier after it is the one at the top of the next iteration
-            BP4_TRACE(i, 18)
-            {
-              // first part of the pre-update of batch i + 2 (the `next` of the coming iteration);
-              // the arrival also covers the descriptor requested above
-              const BatchDesc &d2 = js.ring[(i + 2) & 7];
-              const uint32_t   pb = (vm & 2u) ? d2.pre_begin : 0u, pe = (vm & 2u) ? d2.pre_end : 0u;
-              job_issue(pb, job_split(pb, pe), true);
-            }
-            BP4_TRACE(i, 19)
             cur_ok = (vm & 1u) != 0;
             vm     = (vm >> 1) | (hv ? 4u : 0u);
           }
         if (any)
           {
-            // the request made at the end of the last iteration carried nothing: retire it, then
             // the post-updates of the last two batches, synchronously
-            job_wait(16);
             __syncthreads();
-            double sj[7] = {0., 0., 0., 0., 0., 0., 0.};
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+              sj[k] = 0.;
             for (int k = max(i - 2, 0); k < i; ++k)
               {
                 const BatchDesc &dk = js.ring[k & 7];

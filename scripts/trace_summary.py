@@ -10,10 +10,10 @@ import numpy as np
 
 SLOTS = 20
 # stamps in program order and what ends at each of them
-ORDER = [(0, "top (after the barrier that closes gather_store)"), (5, "phase 1"), (6, "pre job A"),
-         (7, "barrier + phase 2"), (8, "pre job B"), (9, "barrier + phase 3 + park"), (10, "post job A"),
-         (11, "fences"), (1, "barrier"), (12, "gather issue"), (2, "scatter"), (13, "post job B"),
-         (3, "barrier"), (18, "gather store"), (19, "request of the next pre job")]
+ORDER = [(0, "top (after the barrier that closes the previous iteration)"), (5, "request of pre job A + phase 1"),
+         (6, "pre job A"), (7, "barrier + phase 2"), (8, "pre job B"), (9, "barrier + phase 3 + park"),
+         (10, "post job A"), (1, "barrier"), (12, "gather issue"), (2, "scatter"), (3, "barrier"),
+         (18, "gather store"), (13, "post job B")]
 
 raw = np.fromfile(sys.argv[1], dtype=np.uint64)
 pos, launch = 0, 0
@@ -39,7 +39,7 @@ while pos < raw.size:
         else:
             prev = k
     for a, b, name in [(5, 16, "pre job A: wait"), (7, 17, "pre job B: wait"), (9, 14, "post job A: wait"),
-                       (2, 15, "post job B: wait")]:
+                       (18, 15, "post job B: wait")]:
         good = ok & (t[:, :, a] > 0) & (t[:, :, b] > 0)
         if good.sum():
             d = (t[:, :, b] - t[:, :, a])[good] * 1e-3
