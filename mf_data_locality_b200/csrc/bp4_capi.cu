@@ -207,7 +207,7 @@ namespace
         c->pool.erase(it);
       }
     else
-      CU(cudaMalloc(out, sizeof(double) * (n + 2))); // + 2: slack for 16-byte aligned bulk prefetches
+      CU(cudaMalloc(out, sizeof(double) * (n + 2))); // + 2: the fused loop copies runs in 16-byte pieces, one element past either end
     if (zero)
       CU(cudaMemsetAsync(*out, 0, sizeof(double) * n, c->stream));
     return 0;

@@ -57,7 +57,7 @@ namespace bp4
     double   coef[2][CPB][NCOEF]; // double-buffered: the next batch's metadata is prefetched
     double   xq[G::Q];
     double   wq[G::Q];
-    double   red[8];           // fused: the block's share of the seven merged sums
+    double   red[8];           // (spare)
     uint32_t units[8];         // ring of the units this block has claimed
     uint32_t n_claimed;
     uint32_t eidx[2][CPB][28];
@@ -82,10 +82,10 @@ namespace bp4
   };
 
   // Staging rows of the fused cell loop (appended to CellSmem in dynamic shared memory).  The
-  // in-loop do_cg_update4b / do_cg_update3b are cut into "jobs" of at most JOB DoFs; the bulk
-  // copy engine (cp.async.bulk + mbarrier) streams a job's r, p, h and diagonal entries into these
-  // rows while the block runs a compute phase, the threads consume them from shared memory at the
-  // end of that phase: no thread waits for a DRAM round trip or holds loaded values in registers
+  // in-loop do_cg_update4b / do_cg_update3b are cut into "jobs" of at most JOB DoFs; asynchronous
+  // copies (cp.async + mbarrier) bring a job's r, p, h and diagonal entries into these rows while
+  // the block runs a compute phase, the threads consume them from shared memory at the end of
+  // that phase: no thread waits for a DRAM round trip or holds loaded values in registers
   // (the register-staged variant made the memory window 3x longer).
   // A job [b, e) may start at an odd index: the copy is widened to 16-byte boundaries, element i
   // sits at row[..][i - (b & ~1)], diagonal entry i/3 at prec[i/3 - ((b/3) & ~1)].
