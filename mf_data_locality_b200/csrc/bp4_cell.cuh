@@ -192,7 +192,9 @@ namespace bp4
     // Both staging arrays are organised as one row per phase-1/3 item (cell, c, j) with an
     // ODD row stride: consecutive lanes of phase 1/3 then hit an arithmetic progression with
     // odd stride (a bijection modulo the 16 eight-byte banks) and the (qz, qx) lanes of
-    // phase 2 hit consecutive addresses -> no shared-memory bank conflicts in any phase.
+    // phase 2 hit consecutive addresses -> no shared-memory bank conflicts inside a cell (ncu:
+    // none in phases 1 and 3; in phase 2 the warps that straddle two cells lose a wavefront,
+    // the table-driven gather/scatter addresses conflict - DESIGN.md section 6).
     //   dofs[row][k][i]            staged cell DoFs
     //   work[row][a][qz][qx]       a = 0 value, 1 xi-derivative/flux, 2 zeta-derivative/flux
     static constexpr int RD  = (N * N) | 1;

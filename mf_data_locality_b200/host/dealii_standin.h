@@ -43,10 +43,10 @@ namespace dealii
 
   // f(begin, end) on disjoint chunks of [0, n), one host thread per chunk (set-up loops over cells)
   template <typename F>
-  inline void parallel_chunks(const std::uint64_t n, F &&f)
+  inline void parallel_chunks(const std::uint64_t n, F &&f, const std::uint64_t grain = 4096)
   {
     const unsigned int nt = (unsigned int)std::max<std::uint64_t>(
-      1, std::min<std::uint64_t>({(std::uint64_t)std::thread::hardware_concurrency(), parallel_cap(), n / 4096 + 1}));
+      1, std::min<std::uint64_t>({(std::uint64_t)std::thread::hardware_concurrency(), parallel_cap(), n / grain + 1, n ? n : 1}));
     std::vector<std::string> errors(nt);
     std::vector<std::thread> workers;
     auto                     run = [&](const unsigned int t) {
@@ -242,15 +242,37 @@ namespace dealii
             shared[n] = lo != hi;
           }
       });
-      rank_offset.assign(tria->n_ranks + 1, 0);
-      for (std::uint64_t n = 0; n < n_nodes; ++n)
-        ++rank_offset[owner[n] + 1];
-      for (unsigned int r = 0; r < tria->n_ranks; ++r)
-        rank_offset[r + 1] += rank_offset[r];
+      // numbers in lattice order inside every rank: count per slice and rank, prefix sums over
+      // (rank, slice), every slice numbers its own nodes
+      const unsigned int                      n_slices = 64, nr = tria->n_ranks;
+      std::vector<std::vector<std::uint64_t>> cnt(n_slices, std::vector<std::uint64_t>(nr, 0));
+      parallel_chunks(n_slices, [&](const std::uint64_t a, const std::uint64_t b) {
+        for (std::uint64_t sl = a; sl < b; ++sl)
+          for (std::uint64_t n = n_nodes * sl / n_slices; n < n_nodes * (sl + 1) / n_slices; ++n)
+            ++cnt[sl][owner[n]];
+      }, 1);
+      rank_offset.assign(nr + 1, 0);
+      std::uint64_t run = 0;
+      for (unsigned int r = 0; r < nr; ++r)
+        {
+          rank_offset[r] = run;
+          for (unsigned int sl = 0; sl < n_slices; ++sl)
+            {
+              const std::uint64_t c = cnt[sl][r];
+              cnt[sl][r]            = run;
+              run += c;
+            }
+        }
+      rank_offset[nr] = run;
       node_number.resize(n_nodes);
-      std::vector<std::uint64_t> next(rank_offset.begin(), rank_offset.end() - 1);
-      for (std::uint64_t n = 0; n < n_nodes; ++n)
-        node_number[n] = (std::uint32_t)next[owner[n]]++;
+      parallel_chunks(n_slices, [&](const std::uint64_t a, const std::uint64_t b) {
+        for (std::uint64_t sl = a; sl < b; ++sl)
+          {
+            std::vector<std::uint64_t> next = cnt[sl];
+            for (std::uint64_t n = n_nodes * sl / n_slices; n < n_nodes * (sl + 1) / n_slices; ++n)
+              node_number[n] = (std::uint32_t)next[owner[n]]++;
+          }
+      }, 1);
     }
 
     const FESystem      &get_fe() const { return fe; }

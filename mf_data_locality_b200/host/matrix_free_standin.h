@@ -179,10 +179,17 @@ namespace dealii
       // owned constrained DoFs, local indices ascending (get_constrained_dofs)
       constrained_dofs.clear();
       {
+        const unsigned int                      n_slices = 64;
+        std::vector<std::vector<std::uint32_t>> found(n_slices);
+        parallel_chunks(n_slices, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t sl = a; sl < b; ++sl)
+            for (std::uint64_t node = dh.n_nodes * sl / n_slices; node < dh.n_nodes * (sl + 1) / n_slices; ++node)
+              if (dh.owner[node] == rank && con.node_is_constrained(node))
+                found[sl].push_back(dh.node_number[node]);
+        }, 1);
         std::vector<std::uint32_t> nodes;
-        for (std::uint64_t node = 0; node < dh.n_nodes; ++node)
-          if (dh.owner[node] == rank && con.node_is_constrained(node))
-            nodes.push_back(dh.node_number[node]);
+        for (const auto &f : found)
+          nodes.insert(nodes.end(), f.begin(), f.end());
         std::sort(nodes.begin(), nodes.end());
         const std::uint64_t first = dh.rank_offset[rank];
         for (const std::uint32_t n : nodes)

@@ -21,6 +21,7 @@
 //    contiguous numbering", poisson_operator.h:198) -- in the reference as here; for p = 2
 //    (one node per entity) it is a valid input of the operator.
 #pragma once
+#include <array>
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
@@ -72,11 +73,16 @@ public:
                                                    " vs " + std::to_string(n_own));
         // new_numbers[i] = old owned index that moves to position i (:139-144)
         std::vector<std::uint32_t> new_of_old(n_own);
-        for (std::uint64_t i = 0; i < n_own; ++i)
-          new_of_old[new_numbers[i]] = (std::uint32_t)(first + i);
-        for (std::uint64_t n = 0; n < dof_handler.n_nodes; ++n)
-          if (dof_handler.owner[n] == rank)
-            new_node_number[n] = new_of_old[dof_handler.node_number[n] - first];
+        dealii::parallel_chunks(n_own, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t i = a; i < b; ++i)
+            new_of_old[new_numbers[i]] = (std::uint32_t)(first + i);
+        });
+        dealii::parallel_chunks(dof_handler.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t n = a; n < b; ++n)
+            if (dof_handler.owner[n] == rank)
+              new_node_number[n] = new_of_old[dof_handler.node_number[n] - first];
+        });
+        lap("apply");
     };
     std::vector<std::string> errors(n_ranks);
     std::vector<std::thread> workers;
@@ -236,8 +242,10 @@ private:
               });
             }
         });
-        for (const std::uint64_t k : key)
-          AssertThrow(k != unset, "owned node never touched by a local cell");
+        dealii::parallel_chunks(n_own, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t i = a; i < b; ++i)
+            AssertThrow(key[i] != unset, "owned node never touched by a local cell");
+        });
         return key;
       }
     auto touch = [&](const std::uint64_t node) {
@@ -314,29 +322,54 @@ private:
     if (grouping_strat != 0)
       {
         const std::vector<unsigned char> tc = touch_count(mf, grouping_strat == 2);
-        for (std::uint64_t i = 0; i < n_own; ++i)
-          group[i] = tc[i] == 1 ? 0 : 1;
+        dealii::parallel_chunks(n_own, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t i = a; i < b; ++i)
+            group[i] = tc[i] == 1 ? 0 : 1;
+        });
       }
-    for (std::uint64_t n = 0; n < dh.n_nodes; ++n)
-      if (dh.owner[n] == rank && dh.shared[n])
-        group[dh.node_number[n] - first] = 2;
+    dealii::parallel_chunks(dh.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+      for (std::uint64_t n = a; n < b; ++n)
+        if (dh.owner[n] == rank && dh.shared[n])
+          group[dh.node_number[n] - first] = 2;
+    });
     // order by key inside each group.  First-touch keys are a permutation of 0 .. n_own-1: one
     // scatter instead of a sort; last-touch keys have gaps (every touch draws a new number)
     std::vector<std::uint32_t> by_key(n_own);
     if (renumber_strat == 1)
-      for (std::uint64_t i = 0; i < n_own; ++i)
-        by_key[key[i]] = (std::uint32_t)i;
+      dealii::parallel_chunks(n_own, [&](const std::uint64_t a, const std::uint64_t b) {
+        for (std::uint64_t i = a; i < b; ++i)
+          by_key[key[i]] = (std::uint32_t)i;
+      });
     else
       {
         std::iota(by_key.begin(), by_key.end(), 0u);
         std::sort(by_key.begin(), by_key.end(), [&](std::uint32_t a, std::uint32_t b) { return key[a] < key[b]; });
       }
-    std::vector<std::uint32_t> out;
-    out.reserve(n_own);
-    for (unsigned char g = 0; g < 3; ++g)
-      for (const std::uint32_t i : by_key)
-        if (group[i] == g)
-          out.push_back(i);
+    // stable partition by group: count per slice and group, prefix sums, every slice writes its own
+    const unsigned int                        n_slices = 64;
+    std::vector<std::array<std::uint64_t, 3>> cnt(n_slices, std::array<std::uint64_t, 3>{{0, 0, 0}});
+    dealii::parallel_chunks(n_slices, [&](const std::uint64_t a, const std::uint64_t b) {
+      for (std::uint64_t sl = a; sl < b; ++sl)
+        for (std::uint64_t q = n_own * sl / n_slices; q < n_own * (sl + 1) / n_slices; ++q)
+          ++cnt[sl][group[by_key[q]]];
+    }, 1);
+    std::uint64_t run = 0;
+    for (unsigned int g = 0; g < 3; ++g)
+      for (unsigned int sl = 0; sl < n_slices; ++sl)
+        {
+          const std::uint64_t c = cnt[sl][g];
+          cnt[sl][g]            = run;
+          run += c;
+        }
+    std::vector<std::uint32_t> out(n_own);
+    dealii::parallel_chunks(n_slices, [&](const std::uint64_t a, const std::uint64_t b) {
+      for (std::uint64_t sl = a; sl < b; ++sl)
+        {
+          std::array<std::uint64_t, 3> at = cnt[sl];
+          for (std::uint64_t q = n_own * sl / n_slices; q < n_own * (sl + 1) / n_slices; ++q)
+            out[at[group[by_key[q]]]++] = by_key[q];
+        }
+    }, 1);
     return out;
   }
 
