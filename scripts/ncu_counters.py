@@ -21,7 +21,8 @@ def main(csv_path, log_path, out_path):
     ix = {h: i for i, h in enumerate(hdr)}
     per = {}                                    # (degree, fused) -> list of launches -> metric -> value
     for r in rows[1:]:
-        m = re.search(r"cell_kernel<(?:\(int\))?(\d+), (?:\(int\))?\d+, (?:\(bool\))?(\d)>", r[ix["Kernel Name"]])
+        m = re.search(r"cell_kernel<(?:\(int\))?(\d+), (?:\(int\))?\d+, (?:\(bool\))?(\d)(?:, (?:\(bool\))?\d)?>",
+                      r[ix["Kernel Name"]])
         if not m:
             continue
         key = (int(m.group(1)), int(m.group(2)))
