@@ -26,6 +26,9 @@
 // claim bookkeeping makes the register-starved high-degree kernels spill), hence P <= 5.
 #  define BP4_DYNAMIC(P) ((P) <= 5)
 #endif
+#ifndef BP4_PRE_UNROLL
+#  define BP4_PRE_UNROLL 4 // measured: 1 -> 0.496 ms, 2 -> 0.484, 4 -> 0.474 (6.3 TB/s), 6/8 -> 0.48 (Q4 s=18)
+#endif
 #ifndef BP4_POST_UNROLL
 #  define BP4_POST_UNROLL 4 // measured: 1 -> 0.233 ms, 4 -> 0.211 ms (6.45 TB/s), 2 and 8 slower (Q4 s=18)
 #endif
@@ -945,22 +948,41 @@ namespace bp4
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const double   c1 = alpha_old != 0. ? alpha + alpha_old / beta_old : 0.;
     const double   c2 = alpha_old != 0. ? alpha_old / beta_old : 0.;
-    for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride)
+    // BP4_PRE_UNROLL independent elements per trip: all their loads are in flight together
+    constexpr int U = BP4_PRE_UNROLL;
+    for (uint64_t i0 = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end; i0 += U * stride)
       {
-        const double pr = prec[i / 3];
-        if (alpha == 0.)
-          p[i] = -pr * r[i];
-        else
+        double pr[U], ri[U], pi[U], hi[U], xi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
           {
-            double       ri = r[i];
-            const double pi = p[i];
-            if (alpha_old != 0.)
-              x[i] += c1 * pi + c2 * pr * ri;
-            ri += alpha * h[i];
-            r[i] = ri;
-            p[i] = beta * pi - pr * ri;
+            const uint64_t i  = i0 + u * stride;
+            const bool     ok = i < end;
+            pr[u] = ok ? prec[i / 3] : 0.;
+            ri[u] = ok ? r[i] : 0.;
+            pi[u] = ok && alpha != 0. ? p[i] : 0.;
+            hi[u] = ok && alpha != 0. ? h[i] : 0.;
+            xi[u] = ok && alpha_old != 0. ? x[i] : 0.;
           }
-        h[i] = 0.;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          {
+            const uint64_t i = i0 + u * stride;
+            if (i < end)
+              {
+                if (alpha == 0.)
+                  p[i] = -pr[u] * ri[u];
+                else
+                  {
+                    if (alpha_old != 0.)
+                      x[i] = xi[u] + (c1 * pi[u] + c2 * pr[u] * ri[u]);
+                    const double rn = ri[u] + alpha * hi[u];
+                    r[i] = rn;
+                    p[i] = beta * pi[u] - pr[u] * rn;
+                  }
+                h[i] = 0.;
+              }
+          }
       }
   }
 
