@@ -202,8 +202,8 @@ int bp4h_get_node_of_local(void *h, std::uint64_t *out)
       {
         std::vector<std::uint64_t> lattice_of_number; // only for ghosts: search by number
         for (std::uint64_t n = 0; n < dh.n_nodes; ++n)
-          if (dh.owner[n] != rank)
-            {
+          if (dh.owner[n] != rank && dh.shared[n]) // ghosts are shared nodes; the others may carry
+            {                                      // stale numbers (Renumber's neighbour shortcut)
               const auto it = std::lower_bound(part.ghost_nodes.begin(), part.ghost_nodes.end(), dh.node_number[n]);
               if (it != part.ghost_nodes.end() && *it == dh.node_number[n])
                 out[n_own + (it - part.ghost_nodes.begin())] = n;

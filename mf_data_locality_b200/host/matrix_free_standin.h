@@ -35,8 +35,10 @@ namespace dealii
 
     // `rank` defaults to the triangulation's own rank; Renumber also builds the object for the
     // other ranks (every process derives the whole numbering, no host message passing)
+    // order_only: just the cell loop order of `rank_` (cell_order, cell_pos, batches, ranges) --
+    // what Renumber needs of a NEIGHBOUR rank to number the nodes it shares with it
     void reinit(const DoFHandler &dh, const AffineConstraints &con, const unsigned int n_q_points_1d_,
-                const AdditionalData &ad = AdditionalData(), const int rank_ = -1)
+                const AdditionalData &ad = AdditionalData(), const int rank_ = -1, const bool order_only = false)
     {
       dof_handler   = &dh;
       constraints   = &con;
@@ -109,6 +111,9 @@ namespace dealii
         for (unsigned int b = task_info.cell_partition_data[r]; b < task_info.cell_partition_data[r + 1]; ++b)
           for (unsigned int i = batch_start[b]; i < batch_start[b + 1]; ++i)
             range_of_pos[i] = r;
+
+      if (order_only)
+        return;
 
       // vector partitioner: owned range + ghost nodes sorted by (current) global number
       auto part   = std::make_shared<Utilities::MPI::Partitioner>();

@@ -84,6 +84,54 @@ public:
         });
         lap("apply");
     };
+    // Default strategy on several ranks: this process needs the complete numbering of ITS rank
+    // only.  Of the other ranks it only ever references nodes shared between ranks (its ghosts),
+    // and those are the last group of their owner, ordered by first touch: their numbers follow
+    // from the owner's cell loop order alone (shared_numbers_of), no pass over the owner's nodes.
+    const unsigned int this_rank = dof_handler.get_triangulation().this_rank;
+    // (BP4_RENUMBER_ALL_RANKS=1: number every rank completely, as for the other strategies)
+    if (n_ranks > 1 && assembly_strat == 0 && renumber_strat == 1 && std::getenv("BP4_RENUMBER_ALL_RANKS") == nullptr)
+      {
+        renumber_rank(this_rank);
+        const unsigned int                      n_slices = 64;
+        std::vector<std::vector<std::uint64_t>> found(n_slices);
+        dealii::parallel_chunks(n_slices, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t sl = a; sl < b; ++sl)
+            for (std::uint64_t n = dof_handler.n_nodes * sl / n_slices; n < dof_handler.n_nodes * (sl + 1) / n_slices; ++n)
+              if (dof_handler.shared[n] && dof_handler.owner[n] != this_rank)
+                found[sl].push_back(n);
+        }, 1);
+        std::vector<std::vector<std::uint64_t>> shared_of(n_ranks); // lattice order inside a rank
+        for (const auto &f : found)
+          for (const std::uint64_t n : f)
+            shared_of[dof_handler.owner[n]].push_back(n);
+        std::vector<std::string> errs(n_ranks);
+        dealii::parallel_chunks(n_ranks, [&](const std::uint64_t a, const std::uint64_t b) {
+          const unsigned int cap_before = dealii::parallel_cap();
+          dealii::parallel_cap()        = std::max(1u, 16u / n_ranks);
+          for (std::uint64_t q = a; q < b; ++q)
+            if (q != this_rank)
+              try
+                {
+                  shared_numbers_of((unsigned int)q, dof_handler, constraints, mf_data, shared_of[q], new_node_number);
+                }
+              catch (const std::exception &e)
+                {
+                  errs[q] = e.what();
+                }
+          dealii::parallel_cap() = cap_before;
+        }, 1);
+        for (const auto &e : errs)
+          AssertThrow(e.empty(), e);
+        // every other node of the other ranks keeps its old number: never referenced here
+        dealii::parallel_chunks(dof_handler.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+          for (std::uint64_t n = a; n < b; ++n)
+            if (dof_handler.owner[n] != this_rank && !dof_handler.shared[n])
+              new_node_number[n] = dof_handler.node_number[n];
+        });
+        dof_handler.node_number.swap(new_node_number);
+        return;
+      }
     std::vector<std::string> errors(n_ranks);
     std::vector<std::thread> workers;
     for (unsigned int rank = 1; rank < n_ranks; ++rank)
@@ -182,6 +230,52 @@ private:
         for (unsigned int i = 1; i < p; ++i)
           w.push_back({{i, j, k}});
     return w;
+  }
+
+  // New numbers of the nodes rank q owns AND shares with other ranks (`nodes`, all of them), for
+  // (cell_assembly, first_touch, any grouping): they form q's last group (grouping(): group 2),
+  // ordered by first touch = (loop position of the first of q's cells around the node, position
+  // of the node in that cell's object walk).
+  void shared_numbers_of(const unsigned int q, const dealii::DoFHandler &dh, const dealii::AffineConstraints &con,
+                         const dealii::MatrixFree::AdditionalData &mf_data, const std::vector<std::uint64_t> &nodes,
+                         std::vector<std::uint32_t> &new_node_number) const
+  {
+    // nodes q owns and shares that THIS rank does not see are in the list too (shared with a
+    // third rank): the list is complete for q, which is what the positions below need
+    dealii::MatrixFree mf;
+    mf.reinit(dh, con, dh.get_fe().degree + 1, mf_data, (int)q, true);
+    const std::uint64_t first = dh.rank_offset[q], n_own = dh.rank_offset[q + 1] - first;
+    // first cell (loop position) of every node, and the nodes of every such cell
+    std::vector<std::pair<std::uint32_t, std::uint64_t>> by_pos(nodes.size());
+    for (std::size_t k = 0; k < nodes.size(); ++k)
+      {
+        std::uint32_t      ps[8];
+        const unsigned int n  = mf.incident_positions(nodes[k], ps);
+        std::uint32_t      lo = 0xFFFFFFFFu;
+        for (unsigned int j = 0; j < n; ++j)
+          lo = std::min(lo, ps[j]);
+        AssertThrow(lo != 0xFFFFFFFFu, "shared node without a cell of its owner");
+        by_pos[k] = {lo, nodes[k]};
+      }
+    std::sort(by_pos.begin(), by_pos.end());
+    std::uint64_t next = first + n_own - nodes.size(); // the last group of q
+    for (std::size_t k = 0; k < by_pos.size();)
+      {
+        const std::uint32_t pos = by_pos[k].first;
+        std::size_t         e   = k;
+        while (e < by_pos.size() && by_pos[e].first == pos)
+          ++e;
+        // the nodes [k, e) are first touched by the cell at `pos`, in the order of its walk
+        walk_cell_objects(dh, mf.cell_order[pos], [&](const std::uint64_t node, unsigned int) {
+          if (dh.owner[node] != q || !dh.shared[node])
+            return;
+          const auto it = std::lower_bound(by_pos.begin() + k, by_pos.begin() + e, std::make_pair(pos, node));
+          if (it != by_pos.begin() + e && it->second == node)
+            new_node_number[node] = (std::uint32_t)next++;
+        });
+        k = e;
+      }
+    AssertThrow(next == first + n_own, "shared nodes of a neighbour rank: count mismatch");
   }
 
   // cell_assembly / cellbatch_assembly with first_touch_renumber / last_touch_renumber
