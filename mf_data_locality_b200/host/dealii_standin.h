@@ -225,23 +225,52 @@ namespace dealii
       shared.assign(n_nodes, 0);
       AssertThrow(tria->n_ranks <= 255, "at most 255 ranks");
       // owner = min rank over the (up to 8) cells touching a node; shared = more than one rank.
-      // Node by node from the lattice, in parallel.
-      parallel_chunks(n_nodes, [&](const std::uint64_t n0, const std::uint64_t n1) {
-        std::uint64_t cells[8];
-        for (std::uint64_t n = n0; n < n1; ++n)
+      // Row by row of the lattice, in parallel; per direction the one or two candidate cell
+      // coordinates of a lattice coordinate and their shares of the active-cell index are tabulated.
+      std::array<std::vector<std::array<std::uint64_t, 2>>, 3> part;
+      std::array<std::vector<unsigned char>, 3>                two;
+      for (int d = 0; d < 3; ++d)
+        {
+          part[d].resize(nn[d]);
+          two[d].resize(nn[d]);
+          for (std::uint64_t t = 0; t < nn[d]; ++t)
+            {
+              const std::uint32_t q  = (std::uint32_t)(t / p);
+              const std::uint32_t hi = std::min<std::uint32_t>(q, tria->n_cells_dir[d] - 1);
+              const std::uint32_t lo = (t % p == 0 && q > 0) ? q - 1 : hi;
+              part[d][t]             = {{tria->index_part(d, lo), tria->index_part(d, hi)}};
+              two[d][t]              = lo != hi;
+            }
+        }
+      const std::uint64_t chunk = std::max<std::uint64_t>(tria->cells_per_rank(), 1);
+      const unsigned int  last  = tria->n_ranks - 1;
+      parallel_chunks(nn[1] * nn[2], [&](const std::uint64_t r0, const std::uint64_t r1) {
+        for (std::uint64_t row = r0; row < r1; ++row)
           {
-            const unsigned int nc = incident_cells(n, cells);
-            unsigned char      lo = 255, hi = 0;
-            for (unsigned int k = 0; k < nc; ++k)
+            const std::uint64_t y = row % nn[1], z = row / nn[1];
+            const unsigned int  ny = two[1][y] ? 2 : 1, nz = two[2][z] ? 2 : 1;
+            std::uint64_t       yz[4];
+            unsigned int        nyz = 0;
+            for (unsigned int b = 0; b < nz; ++b)
+              for (unsigned int a = 0; a < ny; ++a)
+                yz[nyz++] = part[1][y][a] + part[2][z][b];
+            unsigned char *o = owner.data() + row * nn[0], *sh = shared.data() + row * nn[0];
+            for (std::uint64_t x = 0; x < nn[0]; ++x)
               {
-                const unsigned char r = (unsigned char)tria->subdomain_id(cells[k]);
-                lo = std::min(lo, r);
-                hi = std::max(hi, r);
+                const unsigned int nx = two[0][x] ? 2 : 1;
+                unsigned int       lo = 255, hi = 0;
+                for (unsigned int k = 0; k < nyz; ++k)
+                  for (unsigned int a = 0; a < nx; ++a)
+                    {
+                      const unsigned int r = (unsigned int)std::min<std::uint64_t>((part[0][x][a] + yz[k]) / chunk, last);
+                      lo = std::min(lo, r);
+                      hi = std::max(hi, r);
+                    }
+                o[x]  = (unsigned char)lo;
+                sh[x] = lo != hi;
               }
-            owner[n]  = lo;
-            shared[n] = lo != hi;
           }
-      });
+      }, 16);
       // numbers in lattice order inside every rank: count per slice and rank, prefix sums over
       // (rank, slice), every slice numbers its own nodes
       const unsigned int                      n_slices = 64, nr = tria->n_ranks;
@@ -309,6 +338,36 @@ namespace dealii
           for (std::uint32_t x = lo[0]; x <= hi[0]; ++x)
             cells[n++] = part[0][x - lo[0]] + part[1][y - lo[1]] + part[2][z - lo[2]];
       return n;
+    }
+
+    // f(node_begin, node_end) on the lattice rows of the bounding box of `rank`'s cells, in parallel:
+    // every node the rank owns or touches lies in there, so the per-node passes of the set-up
+    // cost what the rank's share of the lattice costs, not what the whole lattice costs
+    template <typename F>
+    void parallel_rank_nodes(const unsigned int rank, F &&f) const
+    {
+      const std::uint64_t chunk = tria->cells_per_rank();
+      const std::uint64_t c0 = chunk * rank, c1 = rank + 1 == tria->n_ranks ? tria->n_global_active_cells() : c0 + chunk;
+      std::uint32_t       lo[3] = {~0u, ~0u, ~0u}, hi[3] = {0, 0, 0};
+      for (std::uint64_t c = c0; c < c1; ++c)
+        for (int d = 0; d < 3; ++d)
+          {
+            lo[d] = std::min(lo[d], tria->cells[c][d]);
+            hi[d] = std::max(hi[d], tria->cells[c][d]);
+          }
+      if (c1 <= c0)
+        return;
+      const unsigned int  p  = fe.degree;
+      const std::uint64_t x0 = std::uint64_t(lo[0]) * p, x1 = std::uint64_t(hi[0] + 1) * p + 1;
+      const std::uint64_t y0 = std::uint64_t(lo[1]) * p, ny = std::uint64_t(hi[1] + 1) * p + 1 - y0;
+      const std::uint64_t z0 = std::uint64_t(lo[2]) * p, nz = std::uint64_t(hi[2] + 1) * p + 1 - z0;
+      parallel_chunks(ny * nz, [&](const std::uint64_t r0, const std::uint64_t r1) {
+        for (std::uint64_t row = r0; row < r1; ++row)
+          {
+            const std::uint64_t base = ((z0 + row / ny) * nn[1] + (y0 + row % ny)) * nn[0];
+            f(base + x0, base + x1);
+          }
+      }, 16);
     }
 
     template <typename F>

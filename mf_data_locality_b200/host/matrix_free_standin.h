@@ -4,6 +4,7 @@
 // range tables, the vector partitioner, constrained DoFs.  Behaviour recalled from deal.II
 // 9.3 with the non-observable choices exposed in AdditionalData.
 #pragma once
+#include <mutex>
 #include "dealii_standin.h"
 
 namespace dealii
@@ -58,8 +59,13 @@ namespace dealii
           parallel_chunks(c1 - c0, [&](const std::uint64_t a, const std::uint64_t b) {
             for (std::uint64_t c = c0 + a; c < c0 + b; ++c)
               {
-                bool nc = false;
-                dh.for_each_cell_node(c, [&](std::uint64_t node, int, int, int) { nc |= dh.owner[node] != rank; });
+                // all nodes of an entity (vertex, line, face, interior) sit on the same cells and
+                // hence have the same owner: one representative per entity is enough
+                bool               nc = false;
+                const unsigned int pd = dh.get_fe().degree, rep[3] = {0, 1, pd};
+                for (unsigned int a = 0; a < 27; ++a)
+                  if (pd > 1 || (a % 3 != 1 && (a / 3) % 3 != 1 && a / 9 != 1))
+                    nc |= dh.owner[dh.cell_node(c, rep[a % 3], rep[(a / 3) % 3], rep[a / 9])] != rank;
                 needs_comm[c - c0] = nc;
               }
           });
@@ -145,26 +151,32 @@ namespace dealii
             }
           const std::uint64_t first = dh.rank_offset[rank];
           // my shared owned nodes and the other ranks among the (up to 8) cells touching them
-          for (std::uint64_t node = 0; node < dh.n_nodes; ++node)
-            {
-              if (dh.owner[node] != rank || !dh.shared[node])
-                continue;
-              const std::uint32_t ln = dh.node_number[node] - (std::uint32_t)first;
-              std::uint64_t       cells[8];
-              const unsigned int  ncell = dh.incident_cells(node, cells);
-              unsigned int        ranks[8], nr = 0;
-              for (unsigned int q = 0; q < ncell; ++q)
-                {
-                  const unsigned int r   = tria.subdomain_id(cells[q]);
-                  bool               dup = r == rank;
-                  for (unsigned int k = 0; k < nr; ++k)
-                    dup |= ranks[k] == r;
-                  if (!dup)
-                    ranks[nr++] = r;
-                }
-              for (unsigned int k = 0; k < nr; ++k)
-                exports[ranks[k]].push_back(ln);
-            }
+          // (row by row of the rank's box; the lists are sorted below, so the order of the
+          // insertions does not matter)
+          std::mutex merge;
+          dh.parallel_rank_nodes(rank, [&](const std::uint64_t n0, const std::uint64_t n1) {
+            for (std::uint64_t node = n0; node < n1; ++node)
+              {
+                if (dh.owner[node] != rank || !dh.shared[node])
+                  continue;
+                const std::uint32_t ln = dh.node_number[node] - (std::uint32_t)first;
+                std::uint64_t       cells[8];
+                const unsigned int  ncell = dh.incident_cells(node, cells);
+                unsigned int        ranks[8], nr = 0;
+                for (unsigned int q = 0; q < ncell; ++q)
+                  {
+                    const unsigned int r   = tria.subdomain_id(cells[q]);
+                    bool               dup = r == rank;
+                    for (unsigned int k = 0; k < nr; ++k)
+                      dup |= ranks[k] == r;
+                    if (!dup)
+                      ranks[nr++] = r;
+                  }
+                std::lock_guard<std::mutex> lock(merge);
+                for (unsigned int k = 0; k < nr; ++k)
+                  exports[ranks[k]].push_back(ln);
+              }
+          });
           part->import_offset.assign(1, 0);
           part->export_offset.assign(1, 0);
           for (unsigned int r = 0; r < tria.n_ranks; ++r)
@@ -184,17 +196,26 @@ namespace dealii
       // owned constrained DoFs, local indices ascending (get_constrained_dofs)
       constrained_dofs.clear();
       {
-        const unsigned int                      n_slices = 64;
-        std::vector<std::vector<std::uint32_t>> found(n_slices);
-        parallel_chunks(n_slices, [&](const std::uint64_t a, const std::uint64_t b) {
-          for (std::uint64_t sl = a; sl < b; ++sl)
-            for (std::uint64_t node = dh.n_nodes * sl / n_slices; node < dh.n_nodes * (sl + 1) / n_slices; ++node)
-              if (dh.owner[node] == rank && con.node_is_constrained(node))
-                found[sl].push_back(dh.node_number[node]);
-        }, 1);
         std::vector<std::uint32_t> nodes;
-        for (const auto &f : found)
-          nodes.insert(nodes.end(), f.begin(), f.end());
+        std::mutex                 merge;
+        dh.parallel_rank_nodes(rank, [&](const std::uint64_t n0, const std::uint64_t n1) {
+          std::uint32_t row[64];
+          unsigned int  nr = 0;
+          auto          flush = [&] {
+            std::lock_guard<std::mutex> lock(merge);
+            nodes.insert(nodes.end(), row, row + nr);
+            nr = 0;
+          };
+          for (std::uint64_t node = n0; node < n1; ++node)
+            if (dh.owner[node] == rank && con.node_is_constrained(node))
+              {
+                row[nr++] = dh.node_number[node];
+                if (nr == 64)
+                  flush();
+              }
+          if (nr)
+            flush();
+        });
         std::sort(nodes.begin(), nodes.end());
         const std::uint64_t first = dh.rank_offset[rank];
         for (const std::uint32_t n : nodes)

@@ -221,7 +221,7 @@ namespace Poisson
       // per owned node: the one range around it, or invalid if there are several / it is shared
       // with another rank / Dirichlet (node by node from the lattice, in parallel)
       std::vector<std::uint32_t> only_range(n_nodes, numbers::invalid_unsigned_int);
-      parallel_chunks(dh.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+      dh.parallel_rank_nodes(rank, [&](const std::uint64_t a, const std::uint64_t b) {
         for (std::uint64_t n = a; n < b; ++n)
           {
             if (dh.owner[n] != rank || dh.shared[n] || constraints.node_is_constrained(n))

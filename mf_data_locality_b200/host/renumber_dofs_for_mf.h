@@ -77,7 +77,7 @@ public:
           for (std::uint64_t i = a; i < b; ++i)
             new_of_old[new_numbers[i]] = (std::uint32_t)(first + i);
         });
-        dealii::parallel_chunks(dof_handler.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+        dof_handler.parallel_rank_nodes(rank, [&](const std::uint64_t a, const std::uint64_t b) {
           for (std::uint64_t n = a; n < b; ++n)
             if (dof_handler.owner[n] == rank)
               new_node_number[n] = new_of_old[dof_handler.node_number[n] - first];
@@ -298,7 +298,7 @@ private:
         const std::uint32_t        n_cells = mf.n_physical_cells();
         std::vector<std::uint64_t> first_key(n_cells + 1, 0);
         std::vector<std::uint32_t> first_pos(n_own, 0xFFFFFFFFu); // loop position of the first cell
-        dealii::parallel_chunks(dh.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+        dh.parallel_rank_nodes(rank, [&](const std::uint64_t a, const std::uint64_t b) {
           for (std::uint64_t node = a; node < b; ++node)
             {
               if (dh.owner[node] != rank)
@@ -382,7 +382,7 @@ private:
     // around it -- the same count the sweep over the loop produces, node by node in parallel
     std::vector<unsigned char>        count(n_own, 0);
     const std::vector<std::uint32_t> &group_of_pos = by_range ? mf.range_of_pos : mf.batch_of_pos;
-    dealii::parallel_chunks(dh.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+    dh.parallel_rank_nodes(rank, [&](const std::uint64_t a, const std::uint64_t b) {
       for (std::uint64_t node = a; node < b; ++node)
         {
           if (dh.owner[node] != rank || mf.get_constraints().node_is_constrained(node))
@@ -421,7 +421,7 @@ private:
             group[i] = tc[i] == 1 ? 0 : 1;
         });
       }
-    dealii::parallel_chunks(dh.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
+    dh.parallel_rank_nodes(rank, [&](const std::uint64_t a, const std::uint64_t b) {
       for (std::uint64_t n = a; n < b; ++n)
         if (dh.owner[n] == rank && dh.shared[n])
           group[dh.node_number[n] - first] = 2;
