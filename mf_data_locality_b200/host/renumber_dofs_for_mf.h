@@ -11,9 +11,11 @@
 //    (renumber_dofs_for_mf.h:340-356 loops c innermost), so the algorithm runs on lattice
 //    NODES with flat arrays; DoF number = 3 * node number + component.  This is what lets a
 //    50-800 M DoF numbering finish in seconds on the host.
-//  * Every process computes the numbering of ALL ranks (the mesh is structured and cheap to
-//    re-derive), which replaces the ghost-number exchange inside
-//    DoFHandler::renumber_dofs (renumber_dofs_for_mf.h:144).
+//  * No ghost-number exchange (DoFHandler::renumber_dofs, renumber_dofs_for_mf.h:144): the mesh is
+//    structured, so a process derives the numbers of its ghosts itself.  For the default
+//    strategy (cell assembly, first touch) it numbers its own rank completely and, of every
+//    other rank, only the nodes shared between ranks -- the owner's last group, ordered by the
+//    owner's cell loop (shared_numbers_of); for the other strategies it numbers all ranks.
 //  * assembly strategy 1 (cellbatch_assembly, :363-459) numbers batch by batch, FE_Q slot by
 //    slot, lane by lane.  The reference walks the (p+1)^3 slots of a scalar element there; on
 //    lattice nodes that is exactly this walk.  It interleaves the nodes of one entity over the
