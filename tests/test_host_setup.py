@@ -79,6 +79,25 @@ def test_all_renumber_strategies_bit_exact(host, strategy, p, s, n_ranks):
         pr.close()
 
 
+def test_neighbour_shortcut_equals_full_numbering(host, monkeypatch):
+    """default strategy on several ranks: a process numbers its own rank completely and, of the
+    other ranks, only the nodes shared between ranks (from the owner's cell loop order).  Same
+    tables as numbering every rank completely (BP4_RENUMBER_ALL_RANKS=1)."""
+    for (p, s, n_ranks) in [(3, 8, 8), (4, 7, 4), (2, 8, 2)]:
+        for r in range(n_ranks):
+            monkeypatch.delenv("BP4_RENUMBER_ALL_RANKS", raising=False)
+            a = host.Problem(p, s, device=-1, n_ranks=n_ranks, rank=r)
+            monkeypatch.setenv("BP4_RENUMBER_ALL_RANKS", "1")
+            b = host.Problem(p, s, device=-1, n_ranks=n_ranks, rank=r)
+            assert np.array_equal(a.node_of_local(), b.node_of_local())
+            assert np.array_equal(a.entity_index(), b.entity_index())
+            for x, y in zip(a.plan(), b.plan()):
+                assert np.array_equal(x, y)
+            a.close()
+            b.close()
+    monkeypatch.delenv("BP4_RENUMBER_ALL_RANKS", raising=False)
+
+
 def test_renumber_strategies(host):
     """base numbering is rejected by the compressed operator, like the reference's AssertThrow
     "Expected contiguous numbering" (poisson_operator.h:198), and so is the cellbatch assembly
