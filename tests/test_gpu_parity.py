@@ -317,3 +317,29 @@ def test_benchmark_scale_parity(p, s, merged, bp4_lib, c_oracle_lib):
     assert abs(it - ito) <= 1
     assert rel_l2(x, xo) <= (1e-8 if ito < 100 else 1e-6)
     prob.close()
+
+
+@pytest.mark.parametrize("p,s", [(4, 16), (3, 16), (2, 16)])
+def test_fused_cg_at_medium_scale(p, s, bp4_lib, c_oracle_lib):
+    """the in-loop form of the merged iteration (vector updates staged through shared memory
+    inside the cell kernel) with several units per thread block: descriptor ring wrap-around,
+    unit claims, two jobs per run - the 100-iteration solve through the C++ plugin against the C
+    oracle, and the same solve with the streamed form"""
+    from mf_data_locality_b200 import capi, host
+    rd, co = single(p, s)
+    prob = host.Problem(p, s, plugin="merged", device=0)
+    ctx = capi.Context.from_handle(prob.ctx_handle(), p, prob.n_cells, prob.n_owned, prob.n_ghost)
+    _, n_private, n_units = ctx.fused_info()
+    assert n_private == rd.group_sizes[0] and n_units > 2 * 296
+    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    xo, ito, _ = co.cg(rd.rhs, prec, merged=True)
+    sols = []
+    for fused in (True, False):
+        ctx.set_fused(fused)
+        assert ctx.fused_info()[0] is fused
+        x, it = prob.run_cg_solver(rd.rhs)
+        assert abs(it - ito) <= 1
+        assert rel_l2(x, xo) <= (1e-8 if ito < 100 else 1e-6)
+        sols.append(x)
+    assert rel_l2(sols[0], sols[1]) <= 1e-6
+    prob.close()
