@@ -175,9 +175,9 @@ int bp4_compress_add(bp4_ctx *ctx, bp4_vec *v);          /* ghost contributions 
 /* ---- measurement / developer hooks (not part of the drop-in surface) ------------------- */
 /* fused = 1: do_cg_update4b/3b inside the cell kernel on the private DoFs of the ranges
  * (degrees 2..4, tri-linear geometry, descriptor with range tables; anything else is a state
- * error), 0 (default): streamed over the whole vector by pre_kernel / post_kernel.  The
- * environment variable BP4_FUSED=1 selects the fused form at creation where it exists.  Same
- * sums up to summation order.                                                                */
+ * error), 0: streamed over the whole vector by pre_kernel / post_kernel.  Default: the form
+ * measured faster - fused at degree 4 on a single rank, streamed otherwise; the environment
+ * variable BP4_FUSED=0/1 or this call pin it.  Same sums up to summation order.             */
 int bp4_debug_set_fused(bp4_ctx *ctx, int on);
 int bp4_fused_info(bp4_ctx *ctx, int *fused, uint64_t *n_private, uint64_t *n_units);
 typedef enum bp4_kernel_id

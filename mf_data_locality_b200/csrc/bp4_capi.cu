@@ -56,10 +56,13 @@ namespace
   while (0)
 
 // Which form of vmult_with_merged_sums a context starts with when the descriptor carries range
-// tables: 1 = vector updates inside the cell loop, 0 = streamed before/after it.  Set from the
-// B200 measurements in profiles/README.md; bp4_debug_set_fused / BP4_FUSED override it.
+// tables: true = vector updates inside the cell loop, false = streamed before/after it.  Set from
+// the B200 measurements: the in-loop form wins at Q4 on one rank (2.12 vs 2.14 ms),
+// loses at Q2/Q3 and has no kernel above Q4; on several ranks the loop is three launches with a
+// unit-granular tail each, which has not been measured to pay - bp4_comm_init goes back to the
+// streamed form.  bp4_debug_set_fused / BP4_FUSED override both.
 #ifndef BP4_FUSED_DEFAULT
-#  define BP4_FUSED_DEFAULT 0
+#  define BP4_FUSED_DEFAULT(P) ((P) == 4)
 #endif
 
 struct bp4_vec
@@ -98,6 +101,7 @@ struct bp4_ctx
   // fused merged loop (vmult_with_merged_sums): units of whole cell-batch ranges, their batches
   // and the private DoF runs the vector updates are hooked to (bp4_kernels.cuh, BatchDesc)
   int             fused      = 0;      // 1: do_cg_update4b/3b on private DoFs inside the cell kernel
+  bool            fused_pinned = false; // chosen by BP4_FUSED / bp4_debug_set_fused: comm_init keeps it
   uint64_t        n_private  = 0;      // [0, n_private) are private to one range, the rest is streamed
   uint32_t        unit_part[4] = {0, 0, 0, 0}; // first unit of the three cell partitions (+ end)
   bp4::BatchDesc *d_batch      = nullptr;
@@ -432,9 +436,12 @@ static int ctx_create_impl(const bp4_desc *d, bp4_ctx *c)
       for (const bp4::BatchDesc &b : batches)
         if (b.pre_end - b.pre_begin > limit || b.post_end - b.post_begin > limit)
           c->n_private = 0; // the updates of every DoF are streamed then
-      c->fused     = BP4_FUSED_DEFAULT && c->n_private > 0;
+      c->fused     = BP4_FUSED_DEFAULT(d->degree) && c->n_private > 0;
       if (const char *e = getenv("BP4_FUSED")) // developer knob: 0 = pre kernel + cells + post kernel
-        c->fused = c->n_private > 0 && atoi(e) != 0;
+        {
+          c->fused        = c->n_private > 0 && atoi(e) != 0;
+          c->fused_pinned = true;
+        }
     }
 
   // ghost exchange plan
@@ -803,7 +810,8 @@ int bp4_debug_set_fused(bp4_ctx *c, int on)
     return fail(BP4_ERR_STATE, "no private DoF runs: the context was created without range tables, with "
                                "quadratic geometry, at a degree without a fused kernel (> 4), or with runs "
                                "too long for its staging rows");
-  c->fused = on != 0;
+  c->fused        = on != 0;
+  c->fused_pinned = true;
   return 0;
 }
 
@@ -1187,6 +1195,8 @@ int bp4_comm_init(bp4_ctx *c, int rank, int n_ranks, const unsigned char id[BP4_
   NC(ncclCommInitRank(&c->comm, n_ranks, u, rank));
   c->rank    = rank;
   c->n_ranks = n_ranks;
+  if (n_ranks > 1 && !c->fused_pinned)
+    c->fused = 0; // see BP4_FUSED_DEFAULT
   return p2p_setup(c);
 }
 

@@ -615,36 +615,48 @@ namespace bp4
           job_parity ^= 1u;
           BP4_TRACE(trace_i, ts)
         };
-        // the pairs of this thread: values of the three rows and the two diagonal entries
+        // the full pairs of a job [b, e) start at the first even index >= b and end at the last
+        // even index <= e; an odd first / last element is left to one thread each (job_edges)
         struct Pairs
         {
           double2 r[KC], p[KC], h[KC], d[KC];
-          bool    ok0[KC], ok1[KC];
+          bool    ok[KC];
         };
         auto job_load = [&](Pairs &w, const uint32_t b, const uint32_t e) {
-          const uint32_t lo = b & ~1u, n2 = (((e + 1u) & ~1u) - lo) >> 1, q0 = div3(b) & ~1u;
+          const uint32_t lo = b & ~1u, c0 = b & 1u, q0 = div3(b) & ~1u;
+          const uint32_t nf = (e & ~1u) > lo + 2u * c0 ? (((e & ~1u) - lo) >> 1) - c0 : 0u; // full pairs
 #pragma unroll
           for (int k = 0; k < KC; ++k)
             {
-              const uint32_t c  = tid + k * kThreads;
-              const bool     in = c < n2;
-              const uint32_t cc = in ? c : 0u, i0 = lo + 2u * cc;
-              w.ok0[k] = in && i0 >= b;
-              w.ok1[k] = in && i0 + 1u < e;
+              const uint32_t t = tid + k * kThreads;
+              w.ok[k]          = t < nf;
+              const uint32_t cc = c0 + (w.ok[k] ? t : 0u), i0 = lo + 2u * cc;
               w.r[k]   = *reinterpret_cast<const double2 *>(&js.row[0][2 * cc]);
               w.p[k]   = *reinterpret_cast<const double2 *>(&js.row[1][2 * cc]);
               w.h[k]   = *reinterpret_cast<const double2 *>(&js.row[2][2 * cc]);
-              w.d[k].x = js.prec[div3(max(i0, b)) - q0];
+              w.d[k].x = js.prec[div3(min(i0, e - 1u)) - q0];
               w.d[k].y = js.prec[div3(min(i0 + 1u, e - 1u)) - q0];
             }
         };
-        auto store2 = [&](double *v, const uint32_t i0, const bool ok0, const bool ok1, const double x, const double y) {
-          if (ok0 && ok1)
-            *reinterpret_cast<double2 *>(v + i0) = make_double2(x, y);
-          else if (ok0)
-            v[i0] = x;
-          else if (ok1)
-            v[i0 + 1] = y;
+        // f(i) for the odd element at either end of [b, e), on the last two threads of the block
+        auto job_edges = [&](const uint32_t b, const uint32_t e, auto &&f) {
+          if (tid == kThreads - 1 && (b & 1u))
+            f(b);
+          if (tid == kThreads - 2 && (e & 1u)) // e - 1 is even: never the odd first element
+            f(e - 1u);
+        };
+        auto pre_one = [&](const uint32_t i, const double rr, const double pp, const double hh, const double pr) {
+          if (a.first)
+            a.p[i] = -pr * rr;
+          else
+            {
+              if (a.update_x)
+                atomicAdd(a.x + i, a.c1 * pp + a.c2 * pr * rr);
+              const double rn = rr + a.alpha * hh;
+              a.r[i]          = rn;
+              a.p[i]          = a.beta * pp - pr * rn;
+            }
+          a.dst[i] = 0.;
         };
         // do_cg_update4b<3,double,true> (solver_cg_optimized.h:65-161) on [b, e)
         auto pre_job = [&](const uint32_t b, const uint32_t e, const bool always, const int ts) {
@@ -654,29 +666,31 @@ namespace bp4
             return;
           Pairs w;
           job_load(w, b, e);
-          const uint32_t lo = b & ~1u;
+          const uint32_t lo = b & ~1u, c0 = b & 1u, q0 = div3(b) & ~1u;
 #pragma unroll
           for (int k = 0; k < KC; ++k)
-            {
-              const uint32_t i0 = lo + 2u * (tid + k * kThreads);
-              if (a.first)
-                store2(a.p, i0, w.ok0[k], w.ok1[k], -w.d[k].x * w.r[k].x, -w.d[k].y * w.r[k].y);
-              else
-                {
-                  if (a.update_x) // x += ..., fire and forget: x is not read in this kernel
-                    {
-                      if (w.ok0[k])
+            if (w.ok[k])
+              {
+                const uint32_t i0 = lo + 2u * (c0 + tid + k * kThreads);
+                if (a.first)
+                  *reinterpret_cast<double2 *>(a.p + i0) = make_double2(-w.d[k].x * w.r[k].x, -w.d[k].y * w.r[k].y);
+                else
+                  {
+                    if (a.update_x) // x += ..., fire and forget: x is not read in this kernel
+                      {
                         atomicAdd(a.x + i0, a.c1 * w.p[k].x + a.c2 * w.d[k].x * w.r[k].x);
-                      if (w.ok1[k])
                         atomicAdd(a.x + i0 + 1, a.c1 * w.p[k].y + a.c2 * w.d[k].y * w.r[k].y);
-                    }
-                  const double r0 = w.r[k].x + a.alpha * w.h[k].x, r1 = w.r[k].y + a.alpha * w.h[k].y;
-                  store2(a.r, i0, w.ok0[k], w.ok1[k], r0, r1);
-                  store2(a.p, i0, w.ok0[k], w.ok1[k], a.beta * w.p[k].x - w.d[k].x * r0,
-                         a.beta * w.p[k].y - w.d[k].y * r1);
-                }
-              store2(a.dst, i0, w.ok0[k], w.ok1[k], 0., 0.);
-            }
+                      }
+                    const double r0 = w.r[k].x + a.alpha * w.h[k].x, r1 = w.r[k].y + a.alpha * w.h[k].y;
+                    *reinterpret_cast<double2 *>(a.r + i0) = make_double2(r0, r1);
+                    *reinterpret_cast<double2 *>(a.p + i0) =
+                      make_double2(a.beta * w.p[k].x - w.d[k].x * r0, a.beta * w.p[k].y - w.d[k].y * r1);
+                  }
+                *reinterpret_cast<double2 *>(a.dst + i0) = make_double2(0., 0.);
+              }
+          job_edges(b, e, [&](const uint32_t i) {
+            pre_one(i, js.row[0][i - lo], js.row[1][i - lo], js.row[2][i - lo], js.prec[div3(i) - q0]);
+          });
         };
         // do_cg_update3b<3,double> (solver_cg_optimized.h:12-61) on [b, e): the seven sums of a
         // thread stay in registers from the first to the second post job of an iteration, then
@@ -688,12 +702,20 @@ namespace bp4
             return;
           Pairs w;
           job_load(w, b, e);
+          const uint32_t lo = b & ~1u, q0 = div3(b) & ~1u;
 #pragma unroll
           for (int k = 0; k < KC; ++k)
             {
-              post_terms(sj, w.ok0[k] ? w.r[k].x : 0., w.p[k].x, w.ok0[k] ? w.h[k].x : 0., w.d[k].x);
-              post_terms(sj, w.ok1[k] ? w.r[k].y : 0., w.p[k].y, w.ok1[k] ? w.h[k].y : 0., w.d[k].y);
+              // (a thread without a pair reads whatever sits at the first pair's slot: mask all of it)
+              if (w.ok[k])
+                {
+                  post_terms(sj, w.r[k].x, w.p[k].x, w.h[k].x, w.d[k].x);
+                  post_terms(sj, w.r[k].y, w.p[k].y, w.h[k].y, w.d[k].y);
+                }
             }
+          job_edges(b, e, [&](const uint32_t i) {
+            post_terms(sj, js.row[0][i - lo], js.row[1][i - lo], js.row[2][i - lo], js.prec[div3(i) - q0]);
+          });
         };
         // Transposed butterfly: at every step a lane keeps half of its values and hands the
         // other half to its partner, so 7 sums over 32 lanes take 9 shuffles instead of 35;
