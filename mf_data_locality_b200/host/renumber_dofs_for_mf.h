@@ -48,9 +48,9 @@ public:
       return;
     AssertThrow(assembly_strat <= 1 && renumber_strat <= 2 && grouping_strat <= 2,
                 "unknown renumbering strategy");
-    const unsigned int         n_ranks = dof_handler.get_triangulation().n_ranks;
-    std::vector<std::uint32_t> new_node_number(dof_handler.n_nodes);
-    // the ranks' numberings are independent of each other: one host thread per rank
+    const unsigned int n_ranks = dof_handler.get_triangulation().n_ranks;
+    // The ranks' numberings are independent of each other (a rank reads and rewrites the numbers
+    // of its own nodes only), so they are applied in place and may run concurrently.
     auto renumber_rank = [&](const unsigned int rank) {
         const bool show = std::getenv("BP4_SETUP_TIMING") != nullptr && rank == 0;
         auto       t0   = std::chrono::steady_clock::now();
@@ -61,7 +61,7 @@ public:
           t0 = t1;
         };
         dealii::MatrixFree matrix_free;
-        matrix_free.reinit(dof_handler, constraints, dof_handler.get_fe().degree + 1, mf_data, (int)rank);
+        matrix_free.reinit(dof_handler, constraints, dof_handler.get_fe().degree + 1, mf_data, (int)rank, true);
         lap("matrix_free.reinit");
         const std::uint64_t first = dof_handler.rank_offset[rank],
                             n_own = dof_handler.rank_offset[rank + 1] - first;
@@ -82,7 +82,7 @@ public:
         dof_handler.parallel_rank_nodes(rank, [&](const std::uint64_t a, const std::uint64_t b) {
           for (std::uint64_t n = a; n < b; ++n)
             if (dof_handler.owner[n] == rank)
-              new_node_number[n] = new_of_old[dof_handler.node_number[n] - first];
+              dof_handler.node_number[n] = new_of_old[dof_handler.node_number[n] - first];
         });
         lap("apply");
     };
@@ -95,18 +95,6 @@ public:
     if (n_ranks > 1 && assembly_strat == 0 && renumber_strat == 1 && std::getenv("BP4_RENUMBER_ALL_RANKS") == nullptr)
       {
         renumber_rank(this_rank);
-        const unsigned int                      n_slices = 64;
-        std::vector<std::vector<std::uint64_t>> found(n_slices);
-        dealii::parallel_chunks(n_slices, [&](const std::uint64_t a, const std::uint64_t b) {
-          for (std::uint64_t sl = a; sl < b; ++sl)
-            for (std::uint64_t n = dof_handler.n_nodes * sl / n_slices; n < dof_handler.n_nodes * (sl + 1) / n_slices; ++n)
-              if (dof_handler.shared[n] && dof_handler.owner[n] != this_rank)
-                found[sl].push_back(n);
-        }, 1);
-        std::vector<std::vector<std::uint64_t>> shared_of(n_ranks); // lattice order inside a rank
-        for (const auto &f : found)
-          for (const std::uint64_t n : f)
-            shared_of[dof_handler.owner[n]].push_back(n);
         std::vector<std::string> errs(n_ranks);
         dealii::parallel_chunks(n_ranks, [&](const std::uint64_t a, const std::uint64_t b) {
           const unsigned int cap_before = dealii::parallel_cap();
@@ -115,7 +103,7 @@ public:
             if (q != this_rank)
               try
                 {
-                  shared_numbers_of((unsigned int)q, dof_handler, constraints, mf_data, shared_of[q], new_node_number);
+                  shared_numbers_of((unsigned int)q, dof_handler, constraints, mf_data);
                 }
               catch (const std::exception &e)
                 {
@@ -126,12 +114,6 @@ public:
         for (const auto &e : errs)
           AssertThrow(e.empty(), e);
         // every other node of the other ranks keeps its old number: never referenced here
-        dealii::parallel_chunks(dof_handler.n_nodes, [&](const std::uint64_t a, const std::uint64_t b) {
-          for (std::uint64_t n = a; n < b; ++n)
-            if (dof_handler.owner[n] != this_rank && !dof_handler.shared[n])
-              new_node_number[n] = dof_handler.node_number[n];
-        });
-        dof_handler.node_number.swap(new_node_number);
         return;
       }
     std::vector<std::string> errors(n_ranks);
@@ -163,7 +145,6 @@ public:
       w.join();
     for (const auto &e : errors)
       AssertThrow(e.empty(), e);
-    dof_handler.node_number.swap(new_node_number);
   }
 
   std::string get_renumber_string() const
@@ -234,50 +215,48 @@ private:
     return w;
   }
 
-  // New numbers of the nodes rank q owns AND shares with other ranks (`nodes`, all of them), for
-  // (cell_assembly, first_touch, any grouping): they form q's last group (grouping(): group 2),
-  // ordered by first touch = (loop position of the first of q's cells around the node, position
-  // of the node in that cell's object walk).
-  void shared_numbers_of(const unsigned int q, const dealii::DoFHandler &dh, const dealii::AffineConstraints &con,
-                         const dealii::MatrixFree::AdditionalData &mf_data, const std::vector<std::uint64_t> &nodes,
-                         std::vector<std::uint32_t> &new_node_number) const
+  // New numbers of the nodes rank q owns AND shares with other ranks, for (cell_assembly,
+  // first_touch, any grouping): they form q's last group (grouping(): group 2), ordered by first
+  // touch = (loop position of the first of q's cells around the node, position of the node in
+  // that cell's object walk).  Only q's cells that hold such a node are looked at.
+  void shared_numbers_of(const unsigned int q, dealii::DoFHandler &dh, const dealii::AffineConstraints &con,
+                         const dealii::MatrixFree::AdditionalData &mf_data) const
   {
-    // nodes q owns and shares that THIS rank does not see are in the list too (shared with a
-    // third rank): the list is complete for q, which is what the positions below need
     dealii::MatrixFree mf;
     mf.reinit(dh, con, dh.get_fe().degree + 1, mf_data, (int)q, true);
     const std::uint64_t first = dh.rank_offset[q], n_own = dh.rank_offset[q + 1] - first;
-    // first cell (loop position) of every node, and the nodes of every such cell
-    std::vector<std::pair<std::uint32_t, std::uint64_t>> by_pos(nodes.size());
-    for (std::size_t k = 0; k < nodes.size(); ++k)
+    const unsigned int  p = dh.get_fe().degree, rep[3] = {0, 1, p};
+    std::vector<std::uint64_t> order; // the shared nodes of q in the order of their first touch
+    for (std::uint32_t pos = 0; pos < mf.n_physical_cells(); ++pos)
       {
-        std::uint32_t      ps[8];
-        const unsigned int n  = mf.incident_positions(nodes[k], ps);
-        std::uint32_t      lo = 0xFFFFFFFFu;
-        for (unsigned int j = 0; j < n; ++j)
-          lo = std::min(lo, ps[j]);
-        AssertThrow(lo != 0xFFFFFFFFu, "shared node without a cell of its owner");
-        by_pos[k] = {lo, nodes[k]};
-      }
-    std::sort(by_pos.begin(), by_pos.end());
-    std::uint64_t next = first + n_own - nodes.size(); // the last group of q
-    for (std::size_t k = 0; k < by_pos.size();)
-      {
-        const std::uint32_t pos = by_pos[k].first;
-        std::size_t         e   = k;
-        while (e < by_pos.size() && by_pos[e].first == pos)
-          ++e;
-        // the nodes [k, e) are first touched by the cell at `pos`, in the order of its walk
-        walk_cell_objects(dh, mf.cell_order[pos], [&](const std::uint64_t node, unsigned int) {
+        const std::uint64_t cell = mf.cell_order[pos];
+        // all nodes of an entity sit on the same cells: one representative per entity tells
+        // whether the cell holds a node that q owns and shares
+        bool any = false;
+        for (unsigned int a = 0; a < 27 && !any; ++a)
+          if (p > 1 || (a % 3 != 1 && (a / 3) % 3 != 1 && a / 9 != 1))
+            {
+              const std::uint64_t node = dh.cell_node(cell, rep[a % 3], rep[(a / 3) % 3], rep[a / 9]);
+              any = dh.shared[node] && dh.owner[node] == q;
+            }
+        if (!any)
+          continue;
+        walk_cell_objects(dh, cell, [&](const std::uint64_t node, unsigned int) {
           if (dh.owner[node] != q || !dh.shared[node])
             return;
-          const auto it = std::lower_bound(by_pos.begin() + k, by_pos.begin() + e, std::make_pair(pos, node));
-          if (it != by_pos.begin() + e && it->second == node)
-            new_node_number[node] = (std::uint32_t)next++;
+          std::uint32_t      ps[8];
+          const unsigned int n  = mf.incident_positions(node, ps);
+          std::uint32_t      lo = 0xFFFFFFFFu;
+          for (unsigned int j = 0; j < n; ++j)
+            lo = std::min(lo, ps[j]);
+          if (lo == pos) // this cell is the first one of q's loop that touches the node
+            order.push_back(node);
         });
-        k = e;
       }
-    AssertThrow(next == first + n_own, "shared nodes of a neighbour rank: count mismatch");
+    AssertThrow(order.size() <= n_own, "shared nodes of a neighbour rank: count mismatch");
+    const std::uint64_t base = first + n_own - order.size(); // the last group of q
+    for (std::size_t k = 0; k < order.size(); ++k)
+      dh.node_number[order[k]] = (std::uint32_t)(base + k);
   }
 
   // cell_assembly / cellbatch_assembly with first_touch_renumber / last_touch_renumber
