@@ -34,6 +34,29 @@
 
 namespace dealii
 {
+  // std::vector that leaves trivially constructible elements uninitialised on resize(): the big
+  // per-node arrays are written completely by parallel passes right after they are sized, so the
+  // pages are first touched by the worker threads instead of being zeroed by one
+  template <typename T>
+  struct default_init_allocator : std::allocator<T>
+  {
+    template <typename U>
+    struct rebind
+    {
+      using other = default_init_allocator<U>;
+    };
+    template <typename U, typename... Args>
+    void construct(U *ptr, Args &&...args)
+    {
+      if constexpr (sizeof...(Args) == 0)
+        ::new (static_cast<void *>(ptr)) U;
+      else
+        ::new (static_cast<void *>(ptr)) U(std::forward<Args>(args)...);
+    }
+  };
+  template <typename T>
+  using raw_vector = std::vector<T, default_init_allocator<T>>;
+
   // threads one parallel_chunks call may use; callers that already run several workers lower it
   inline unsigned int &parallel_cap()
   {
@@ -221,8 +244,8 @@ namespace dealii
         nn[d] = std::uint64_t(tria->n_cells_dir[d]) * p + 1;
       n_nodes = nn[0] * nn[1] * nn[2];
       AssertThrow(n_nodes < 0xFFFFFFFFull, "node lattice exceeds 32-bit node numbers");
-      owner.assign(n_nodes, (unsigned char)255);
-      shared.assign(n_nodes, 0);
+      owner.resize(n_nodes); // every entry of the three arrays is written by the passes below
+      shared.resize(n_nodes);
       AssertThrow(tria->n_ranks <= 255, "at most 255 ranks");
       // owner = min rank over the (up to 8) cells touching a node; shared = more than one rank.
       // Row by row of the lattice, in parallel; per direction the one or two candidate cell
@@ -401,9 +424,9 @@ namespace dealii
 
     std::array<std::uint64_t, 3> nn{{1, 1, 1}};
     std::uint64_t                n_nodes = 0;
-    std::vector<unsigned char>   owner;       // [n_nodes] owning rank
-    std::vector<unsigned char>   shared;      // [n_nodes] touched by cells of several ranks
-    std::vector<std::uint32_t>   node_number; // [n_nodes] current global node number
+    raw_vector<unsigned char>    owner;       // [n_nodes] owning rank
+    raw_vector<unsigned char>    shared;      // [n_nodes] touched by cells of several ranks
+    raw_vector<std::uint32_t>    node_number; // [n_nodes] current global node number
     std::vector<std::uint64_t>   rank_offset; // [n_ranks+1] first node number of each rank
 
   private:

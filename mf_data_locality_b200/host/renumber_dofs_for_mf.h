@@ -69,12 +69,12 @@ public:
         std::vector<std::uint64_t> key = cell_assembly(matrix_free);
         AssertThrow(key.size() == n_own, "Expected " + std::to_string(n_own) + " nodes");
         lap("cell_assembly");
-        const std::vector<std::uint32_t> new_numbers = grouping(matrix_free, key);
+        const auto new_numbers = grouping(matrix_free, key);
         lap("grouping");
         AssertThrow(new_numbers.size() == n_own, "Dimension mismatch " + std::to_string(new_numbers.size()) +
                                                    " vs " + std::to_string(n_own));
         // new_numbers[i] = old owned index that moves to position i (:139-144)
-        std::vector<std::uint32_t> new_of_old(n_own);
+        dealii::raw_vector<std::uint32_t> new_of_old(n_own); // written completely below
         dealii::parallel_chunks(n_own, [&](const std::uint64_t a, const std::uint64_t b) {
           for (std::uint64_t i = a; i < b; ++i)
             new_of_old[new_numbers[i]] = (std::uint32_t)(first + i);
@@ -388,7 +388,7 @@ private:
 
   // grouping (:492-535) with base_grouping (:537-554) / touch_count_grouping (:556-590);
   // "multi-domain" nodes = owned nodes that also sit on a ghost cell (domain_dof_mapping, :673-730)
-  std::vector<std::uint32_t> grouping(const dealii::MatrixFree &mf, const std::vector<std::uint64_t> &key) const
+  dealii::raw_vector<std::uint32_t> grouping(const dealii::MatrixFree &mf, const std::vector<std::uint64_t> &key) const
   {
     const dealii::DoFHandler &dh    = mf.get_dof_handler();
     const unsigned int        rank  = mf.get_rank();
@@ -409,7 +409,7 @@ private:
     });
     // order by key inside each group.  First-touch keys are a permutation of 0 .. n_own-1: one
     // scatter instead of a sort; last-touch keys have gaps (every touch draws a new number)
-    std::vector<std::uint32_t> by_key(n_own);
+    dealii::raw_vector<std::uint32_t> by_key(n_own); // both written completely below
     if (renumber_strat == 1)
       dealii::parallel_chunks(n_own, [&](const std::uint64_t a, const std::uint64_t b) {
         for (std::uint64_t i = a; i < b; ++i)
@@ -436,7 +436,7 @@ private:
           cnt[sl][g]            = run;
           run += c;
         }
-    std::vector<std::uint32_t> out(n_own);
+    dealii::raw_vector<std::uint32_t> out(n_own);
     dealii::parallel_chunks(n_slices, [&](const std::uint64_t a, const std::uint64_t b) {
       for (std::uint64_t sl = a; sl < b; ++sl)
         {
