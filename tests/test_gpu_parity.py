@@ -343,3 +343,25 @@ def test_fused_cg_at_medium_scale(p, s, bp4_lib, c_oracle_lib):
         sols.append(x)
     assert rel_l2(sols[0], sols[1]) <= 1e-6
     prob.close()
+
+
+def test_default_form_of_the_merged_iteration(bp4_lib, monkeypatch):
+    """which form vmult_with_merged_sums starts with follows the B200 measurements:
+    vector updates inside the cell loop at Q4 on one rank, streamed at the other degrees;
+    BP4_FUSED pins either"""
+    monkeypatch.delenv("BP4_FUSED", raising=False)
+    for p, want in ((4, True), (3, False), (2, False), (5, False)):
+        rd, _ = single(p, 5)
+        ctx = make_ctx(rd)
+        assert ctx.fused_info()[0] is want
+        ctx.close()
+    monkeypatch.setenv("BP4_FUSED", "0")
+    rd, _ = single(4, 5)
+    ctx = make_ctx(rd)
+    assert ctx.fused_info()[0] is False
+    ctx.close()
+    monkeypatch.setenv("BP4_FUSED", "1")
+    rd, _ = single(3, 5)
+    ctx = make_ctx(rd)
+    assert ctx.fused_info()[0] is True
+    ctx.close()
