@@ -227,3 +227,46 @@ def test_quadratic_cells_against_dense_assembly(p, s):
     free = np.ones(rd.n_owned, bool)
     free[rd.constrained] = False
     assert np.allclose(np.repeat(d, 3)[free], np.diag(Ag)[free], rtol=1e-12)
+
+
+def _manufactured_error(p, s):
+    """max nodal error of the discrete solution of -Laplace(u_c) = f_c on the deformed mesh for
+    u_c = (c + 1) sin(pi x) sin(pi y) sin(pi z) (zero on the boundary of the unit cube, which the
+    interior deformation of curved_manifold.h leaves in place).  The load vector is assembled
+    here from the oracle's tables and geometry; operator, diagonal and CG are the oracle's."""
+    rd = O.build_problem(p, s)[0]
+    t = O.make_tables(p)
+    dmap = O.local_dof_map(p, rd.entity_index)
+    coef = O.cell_coefficients(rd)
+    v0, v1, v3, v4, v9, v10, v12, v13 = (coef[:, i][:, None, None, None, :] for i in range(8))
+
+    def phys(x1d):                       # tri-linear map of the tensor grid x1d^3, [cell][z][y][x][3]
+        x, y, z = x1d[None, None, None, :, None], x1d[None, None, :, None, None], x1d[None, :, None, None, None]
+        return v0 + x * v1 + y * v3 + x * y * v4 + z * v9 + x * z * v10 + y * z * v12 + x * y * z * v13
+
+    def exact(X):
+        return np.sin(np.pi * X[..., 0]) * np.sin(np.pi * X[..., 1]) * np.sin(np.pi * X[..., 2])
+    _, det = O.do_invert(O.jacobians(coef, t.xq))
+    w = t.wq[:, None, None] * t.wq[None, :, None] * t.wq[None, None, :]
+    fq = 3 * np.pi ** 2 * exact(phys(t.xq)) * det * w[None]
+    load = np.einsum("kc,jb,ia,ncba->nkji", t.S, t.S, t.S, fq, optimize=True).reshape(rd.n_cells, -1)
+    valid = dmap >= 0
+    b = np.zeros(rd.n_owned)
+    for c in range(3):
+        np.add.at(b, (dmap + c)[valid], (c + 1) * load[valid])
+    prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
+    x, it, _ = COracle(rd).cg(b, prec, merged=True, max_steps=5000, tol=1e-30, reduce=1e-13)
+    assert it < 5000
+    ue = exact(phys(t.xn)).reshape(rd.n_cells, -1)
+    return max(np.abs(x[(dmap + c)[valid]] - (c + 1) * ue[valid]).max() / (c + 1) for c in range(3))
+
+
+@pytest.mark.parametrize("p,levels", [(2, (6, 9, 12)), (3, (6, 9)), (4, (3, 6, 9))])
+def test_manufactured_solution_converges(p, levels, c_oracle_lib):
+    """SURVEY 8(c) pin 3: the whole chain (geometry, operator, Dirichlet rows, GLL diagonal, CG)
+    solves a Poisson problem with a known solution, and the nodal error drops at least like
+    h^(p+1) under uniform refinement (s -> s + 3 halves h)."""
+    errs = [_manufactured_error(p, s) for s in levels]
+    rates = [np.log2(a / b) for a, b in zip(errs, errs[1:])]
+    assert errs[-1] < {2: 5e-5, 3: 1e-5, 4: 5e-7}[p]
+    assert rates[-1] > p + 0.7, (errs, rates)
