@@ -229,20 +229,27 @@ def test_quadratic_cells_against_dense_assembly(p, s):
     assert np.allclose(np.repeat(d, 3)[free], np.diag(Ag)[free], rtol=1e-12)
 
 
-def _manufactured_error(p, s):
+def _manufactured_error(p, s, quadratic=False):
     """max nodal error of the discrete solution of -Laplace(u_c) = f_c on the deformed mesh for
     u_c = (c + 1) sin(pi x) sin(pi y) sin(pi z) (zero on the boundary of the unit cube, which the
     interior deformation of curved_manifold.h leaves in place).  The load vector is assembled
     here from the oracle's tables and geometry; operator, diagonal and CG are the oracle's."""
-    rd = O.build_problem(p, s)[0]
+    rd = O.build_problem(p, s, quadratic=quadratic)[0]
     t = O.make_tables(p)
     dmap = O.local_dof_map(p, rd.entity_index)
     coef = O.cell_coefficients(rd)
-    v0, v1, v3, v4, v9, v10, v12, v13 = (coef[:, i][:, None, None, None, :] for i in range(8))
+    if quadratic:                        # X = sum_m v_m x^a y^b z^c, m = a + 3 b + 9 c
+        v = coef.reshape(-1, 3, 3, 3, 3)
 
-    def phys(x1d):                       # tri-linear map of the tensor grid x1d^3, [cell][z][y][x][3]
-        x, y, z = x1d[None, None, None, :, None], x1d[None, None, :, None, None], x1d[None, :, None, None, None]
-        return v0 + x * v1 + y * v3 + x * y * v4 + z * v9 + x * z * v10 + y * z * v12 + x * y * z * v13
+        def phys(x1d):
+            P = np.stack([np.ones_like(x1d), x1d, x1d * x1d])
+            return np.einsum("ncbad,ax,by,cz->nzyxd", v, P, P, P, optimize=True)
+    else:
+        v0, v1, v3, v4, v9, v10, v12, v13 = (coef[:, i][:, None, None, None, :] for i in range(8))
+
+        def phys(x1d):                   # tri-linear map of the tensor grid x1d^3, [cell][z][y][x][3]
+            x, y, z = x1d[None, None, None, :, None], x1d[None, None, :, None, None], x1d[None, :, None, None, None]
+            return v0 + x * v1 + y * v3 + x * y * v4 + z * v9 + x * z * v10 + y * z * v12 + x * y * z * v13
 
     def exact(X):
         return np.sin(np.pi * X[..., 0]) * np.sin(np.pi * X[..., 1]) * np.sin(np.pi * X[..., 2])
@@ -255,7 +262,13 @@ def _manufactured_error(p, s):
     for c in range(3):
         np.add.at(b, (dmap + c)[valid], (c + 1) * load[valid])
     prec = O.finish_inverse_diagonal(O.inverse_diagonal(rd))
-    x, it, _ = COracle(rd).cg(b, prec, merged=True, max_steps=5000, tol=1e-30, reduce=1e-13)
+    if quadratic:                        # the C restatement carries the tri-linear geometry only
+        ctl = O.ReductionControl(5000, 1e-30, 1e-13)
+        x = np.zeros(rd.n_owned)
+        O.solver_cg_merged(lambda vec: O.vmult_cells(rd, t, vec), x, b, prec, ctl)
+        it = ctl.last_step
+    else:
+        x, it, _ = COracle(rd).cg(b, prec, merged=True, max_steps=5000, tol=1e-30, reduce=1e-13)
     assert it < 5000
     ue = exact(phys(t.xn)).reshape(rd.n_cells, -1)
     return max(np.abs(x[(dmap + c)[valid]] - (c + 1) * ue[valid]).max() / (c + 1) for c in range(3))
@@ -270,3 +283,10 @@ def test_manufactured_solution_converges(p, levels, c_oracle_lib):
     rates = [np.log2(a / b) for a, b in zip(errs, errs[1:])]
     assert errs[-1] < {2: 5e-5, 3: 1e-5, 4: 5e-7}[p]
     assert rates[-1] > p + 0.7, (errs, rates)
+
+
+def test_manufactured_solution_quadratic_geometry():
+    """the same pin for the genuinely quadratic cells (all 27 coefficient vectors of
+    poisson_operator.h:577-602): numpy oracle end to end"""
+    errs = [_manufactured_error(2, s, quadratic=True) for s in (6, 9)]
+    assert errs[-1] < 5e-4 and np.log2(errs[0] / errs[1]) > 2.7, errs
